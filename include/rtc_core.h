@@ -1,0 +1,139 @@
+/*
+ * rtc_core.h -- C ABI of the B200-native rtigo3 path-tracing core (librtcore.so).
+ *
+ * This is the drop-in boundary: the fourteen OptiX host entry points the reference's Device class
+ * calls are replaced by the functions below.  Plain pointers and sizes only;
+ * device addresses travel as uint64_t exactly like CUdeviceptr does in the reference.  Every
+ * function returns 0 on success and a non-zero code on failure; rtc_last_error() then holds
+ * "ERROR: file(line): call (code) text", the CU_CHECK format of apps/rtigo3/inc/CheckMacros.h:39-79.
+ * Not thread-safe by contract (the reference drives each Device from one host thread).
+ *
+ *   reference call site (apps/rtigo3/src/...)                         replacement
+ *   ---------------------------------------------------------------  -------------------------------
+ *   Device.cpp:245-316  cuCtxCreate, cuStreamCreate,                  rtc_context_create
+ *                       optixDeviceContextCreate, initPipeline
+ *   Device.cpp:320-358  ~Device                                       rtc_context_destroy
+ *   Device.cpp:1391-1405 optixAccelComputeMemoryUsage+optixAccelBuild rtc_gas_build
+ *                       (OPTIX_BUILD_INPUT_TYPE_TRIANGLES)
+ *   Device.cpp:1427-1443 createInstance, :1471-1482 optixAccelBuild   rtc_ias_build
+ *                       (INSTANCES), :1492-1532 createHitGroupRecords
+ *   DeviceSingleGPU.cpp:164, DeviceMultiGPUZeroCopy.cpp:141,          rtc_launch
+ *   DeviceMultiGPUPeerAccess.cpp:180, DeviceMultiGPULocalCopy.cpp:190
+ *                       optixLaunch
+ *   DeviceMultiGPULocalCopy.cpp:279-337 compositor kernel launch      rtc_composite
+ *   Application.cpp:2262-2295 CPU tonemapper ("PERF Add a native CUDA rtc_tonemap
+ *                       kernel doing this", :2275)
+ *   Device.cpp synchronizeStream (cuStreamSynchronize)                rtc_synchronize
+ *   cuMemAlloc / cuMemFree / cuMemcpyHtoDAsync / cuMemcpyDtoHAsync    rtc_malloc / rtc_free / rtc_upload / rtc_download
+ *
+ * Program selection that OptiX did through entry-function names (raygen variant by strategy,
+ * Device.cpp:634-648; miss program by m_miss, :660-672; environment light callable, :705) is an
+ * argument of rtc_launch.
+ */
+#ifndef RTC_CORE_H
+#define RTC_CORE_H
+
+#include "rtigo3_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rtc_context rtc_context;
+
+/* One instance = Device::createInstance + the per-instance hit record (GeometryInstanceData). */
+typedef struct {
+  float    transform[12];   /* object -> world, row-major 3x4 (OptixInstance::transform) */
+  uint32_t instanceId;      /* OptixInstance::instanceId; must equal the array position */
+  uint32_t gas;             /* handle returned by rtc_gas_build */
+  int      materialIndex;
+  int      lightIndex;      /* < 0: not a light */
+} rtc_instance_desc;
+
+/* One ray / one hit of the query interface (BASELINE config 3 and the parity hook). 32 B and 20 B. */
+typedef struct { float ox, oy, oz, tmin, dx, dy, dz, tmax; } rtc_ray;
+typedef struct { float t, u, v; uint32_t inst; uint32_t prim; } rtc_hit;   /* miss: t = -1, inst = prim = 0xffffffff */
+
+typedef struct {
+  uint64_t radianceRays;     /* closest-hit rays traced by extend since the last reset */
+  uint64_t shadowRays;       /* any-hit rays traced by connect */
+  uint64_t pathSamples;      /* paths started by generate */
+  uint64_t kernelLaunches;   /* kernels of this library launched */
+  double   lastTraceMs;      /* device time of the last rtc_trace_* call (CUDA events on the context stream) */
+} rtc_stats;
+
+/* BVH statistics and raw arrays, so the CPU oracle can walk the identical tree and count
+ * the nodes / triangles / instances each ray touches (the algorithmic-bytes figure). */
+typedef struct {
+  uint32_t numNodes;         /* 80 B wide nodes (all GAS + the instance level) */
+  uint32_t numTris;          /* 48 B triangle records */
+  uint32_t numInstances;
+  uint32_t numTlasLeaves;
+  uint32_t tlasRoot;
+  uint32_t reserved;
+} rtc_scene_info;
+
+enum { RTC_RAYGEN_FULL_FRAME = 0,      /* __raygen__path_tracer            (raygeneration.cu:167) */
+       RTC_RAYGEN_LOCAL_COPY = 1 };    /* __raygen__path_tracer_local_copy (raygeneration.cu:259) */
+
+enum { RTC_BUILD_DEFAULT = 0,          /* GPU LBVH for large inputs, host SAH for small ones */
+       RTC_BUILD_HOST_SAH = 1,
+       RTC_BUILD_GPU_LBVH = 2 };
+
+int         rtc_version(void);
+const char* rtc_last_error(void);
+
+int rtc_context_create(int deviceOrdinal, rtc_context** out);
+int rtc_context_destroy(rtc_context* ctx);
+int rtc_synchronize(rtc_context* ctx);
+/* The context's stream as a cudaStream_t value (for callers that enqueue their own work, e.g. NCCL). */
+uint64_t rtc_context_stream(rtc_context* ctx);
+
+int rtc_malloc(rtc_context* ctx, uint64_t bytes, uint64_t* dptr);
+int rtc_free(rtc_context* ctx, uint64_t dptr);
+int rtc_upload(rtc_context* ctx, uint64_t dst, const void* src, uint64_t bytes);     /* async on the context stream */
+int rtc_download(rtc_context* ctx, void* dst, uint64_t src, uint64_t bytes);         /* async on the context stream */
+int rtc_memset(rtc_context* ctx, uint64_t dst, int value, uint64_t bytes);
+int rtc_host_alloc(rtc_context* ctx, uint64_t bytes, void** ptr);                    /* pinned */
+int rtc_host_free(rtc_context* ctx, void* ptr);
+
+/* attributes: device pointer to vertex records, position = 3 floats at offset 0, strideBytes apart
+ * (48 for TriangleAttributes); indices: device pointer to numTris uint32 triplets. */
+int rtc_gas_build(rtc_context* ctx, uint64_t attributes, uint32_t strideBytes, uint32_t numVerts,
+                  uint64_t indices, uint32_t numTris, uint32_t buildFlags, uint32_t* gas);
+/* Builds the instance level, the per-instance tables and returns SystemData::topObject. */
+int rtc_ias_build(rtc_context* ctx, const rtc_instance_desc* instances, uint32_t numInstances, uint64_t* topObject);
+/* Per-instance material switch (Device::updateMaterial's hit-record update, Device.cpp:1112-1167). */
+int rtc_scene_info_get(rtc_context* ctx, uint64_t topObject, rtc_scene_info* info);
+/* Copies the raw BVH out: nodes (80 B each), tris (48 B each), instances (64 B each: 3x4 inverse + root),
+ * tlasLeaves (uint32 instance ids).  Any pointer may be NULL. */
+int rtc_scene_export(rtc_context* ctx, uint64_t topObject, void* nodes, void* tris, void* instances, void* tlasLeaves);
+/* Copies out the 3x4 world->object matrix of one instance. */
+int rtc_instance_inverse(rtc_context* ctx, uint64_t topObject, uint32_t instance, float out[12]);
+
+/*
+ * One optixLaunch-equivalent per iteration in [iterationFirst, iterationFirst + iterationCount):
+ * sys is the HOST copy of SystemData (pointers inside are device pointers owned by the caller);
+ * sys->iterationIndex is ignored in favour of the range.  raygen = RTC_RAYGEN_*, miss = RT_MISS_*.
+ * Asynchronous on the context stream.
+ */
+int rtc_launch(rtc_context* ctx, const rt_SystemData* sys, uint32_t launchWidth, uint32_t launchHeight,
+               int raygen, int miss, int iterationFirst, int iterationCount);
+
+/* Ray queries against a built scene; rays/hits/occluded are device pointers.  occluded: one uint32 per ray. */
+int rtc_trace_closest(rtc_context* ctx, uint64_t topObject, uint64_t rays, uint64_t numRays, uint64_t hits);
+int rtc_trace_any(rtc_context* ctx, uint64_t topObject, uint64_t rays, uint64_t numRays, uint64_t occluded);
+/* Primary rays of one iteration, one rtc_ray per launch index (skipped indices get tmax = -1). */
+int rtc_generate_primary(rtc_context* ctx, const rt_SystemData* sys, uint32_t launchWidth, uint32_t launchHeight,
+                         int iteration, uint64_t rays);
+
+int rtc_composite(rtc_context* ctx, const rt_CompositorData* args);
+int rtc_tonemap(rtc_context* ctx, const rt_TonemapperParams* params, uint64_t rgba, uint64_t rgb8, uint64_t numPixels);
+
+int rtc_stats_get(rtc_context* ctx, rtc_stats* out);   /* synchronises the context stream */
+int rtc_stats_reset(rtc_context* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTC_CORE_H */

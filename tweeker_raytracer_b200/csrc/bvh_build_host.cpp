@@ -1,0 +1,255 @@
+// bvh_build_host.cpp -- quality builder for the wide BVH: binned-SAH binary tree on the host,
+// greedy surface-area collapse to 8 children, octant slot assignment, conservative quantisation.
+//
+// Replaces optixAccelBuild (apps/rtigo3/src/Device.cpp:1401 triangles, :1478 instances), which has no
+// source in the reference.  Used for the instance level and for small / medium geometry; the GPU LBVH
+// builder (bvh_build_gpu.cu) takes over for large inputs and emits the same node format through
+// emit_wide_from_binary().
+#include "rtc_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+namespace {
+
+struct Box
+{
+  float lo[3], hi[3];
+  void clear() { for (int k = 0; k < 3; ++k) { lo[k] = std::numeric_limits<float>::infinity(); hi[k] = -lo[k]; } }
+  void grow(const float* l, const float* h) { for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], l[k]); hi[k] = std::max(hi[k], h[k]); } }
+  float halfArea() const
+  {
+    const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    return dx * dy + dy * dz + dz * dx;
+  }
+};
+
+struct BinNode
+{
+  Box      box;
+  int32_t  left = -1, right = -1;   // -1: leaf
+  uint32_t first = 0, count = 0;    // leaf range in the ordered primitive list
+};
+
+constexpr int kBins = 32;
+constexpr uint32_t kLeafMax = 3;    // a leaf child of a wide node carries 1..3 primitives (3 bits of meta)
+
+struct Builder
+{
+  const PrimBox* prims;
+  std::vector<uint32_t> order;
+  std::vector<BinNode> nodes;
+
+  int build(uint32_t first, uint32_t count)
+  {
+    const int idx = (int)nodes.size();
+    nodes.emplace_back();
+    Box box, cbox; box.clear(); cbox.clear();
+    for (uint32_t i = first; i < first + count; ++i)
+    {
+      const PrimBox& p = prims[order[i]];
+      box.grow(p.lo, p.hi);
+      float c[3]; for (int k = 0; k < 3; ++k) c[k] = 0.5f * (p.lo[k] + p.hi[k]);
+      cbox.grow(c, c);
+    }
+    nodes[idx].box = box;
+    nodes[idx].first = first; nodes[idx].count = count;
+    if (count <= 1) return idx;
+
+    int bestAxis = -1, bestSplit = 0; float bestCost = std::numeric_limits<float>::infinity();
+    for (int axis = 0; axis < 3; ++axis)
+    {
+      const float ext = cbox.hi[axis] - cbox.lo[axis];
+      if (!(ext > 0.0f)) continue;
+      Box bb[kBins]; uint32_t bc[kBins];
+      for (int b = 0; b < kBins; ++b) { bb[b].clear(); bc[b] = 0; }
+      const float scale = (float)kBins / ext;
+      for (uint32_t i = first; i < first + count; ++i)
+      {
+        const PrimBox& p = prims[order[i]];
+        int b = (int)((0.5f * (p.lo[axis] + p.hi[axis]) - cbox.lo[axis]) * scale);
+        b = std::min(std::max(b, 0), kBins - 1);
+        bb[b].grow(p.lo, p.hi); bc[b]++;
+      }
+      float rightArea[kBins]; uint32_t rightCount[kBins]; Box acc; acc.clear(); uint32_t n = 0;
+      for (int b = kBins - 1; b > 0; --b) { if (bc[b]) acc.grow(bb[b].lo, bb[b].hi); n += bc[b]; rightArea[b] = n ? acc.halfArea() : 0.0f; rightCount[b] = n; }
+      acc.clear(); n = 0;
+      for (int b = 0; b < kBins - 1; ++b)
+      {
+        if (bc[b]) acc.grow(bb[b].lo, bb[b].hi);
+        n += bc[b];
+        if (n == 0 || rightCount[b + 1] == 0) continue;
+        const float cost = acc.halfArea() * (float)n + rightArea[b + 1] * (float)rightCount[b + 1];
+        if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestSplit = b; }
+      }
+    }
+    // SAH termination for small leaves: intersecting `count` primitives vs. one more node level
+    if (count <= kLeafMax)
+    {
+      const float leafCost = box.halfArea() * (float)count;
+      if (bestAxis < 0 || bestCost + 1.2f * box.halfArea() >= leafCost) return idx;
+    }
+    uint32_t mid;
+    if (bestAxis < 0)
+    {
+      mid = first + count / 2;
+    }
+    else
+    {
+      const float ext = cbox.hi[bestAxis] - cbox.lo[bestAxis];
+      const float scale = (float)kBins / ext;
+      const float clo = cbox.lo[bestAxis];
+      auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](uint32_t pi) {
+        const PrimBox& p = prims[pi];
+        int b = (int)((0.5f * (p.lo[bestAxis] + p.hi[bestAxis]) - clo) * scale);
+        b = std::min(std::max(b, 0), kBins - 1);
+        return b <= bestSplit;
+      });
+      mid = (uint32_t)(it - order.begin());
+      if (mid == first || mid == first + count) mid = first + count / 2;
+    }
+    const int l = build(first, mid - first);
+    const int r = build(mid, first + count - mid);
+    nodes[idx].left = l; nodes[idx].right = r;
+    return idx;
+  }
+};
+
+inline float pow2f(int e) { uint32_t u = (uint32_t)(e + 127) << 23; float f; std::memcpy(&f, &u, 4); return f; }
+
+struct Emitter
+{
+  const std::vector<BinNode>& bn;
+  const std::vector<uint32_t>& order;
+  WideBvh& out;
+
+  // writes wide node `dst` for the binary subtree `src`
+  void emit(uint32_t dst, int src)
+  {
+    // 1. collect up to 8 children: open the inner child with the largest surface area first
+    int kids[8]; int n = 0;
+    if (bn[src].left < 0) { kids[n++] = src; }
+    else { kids[n++] = bn[src].left; kids[n++] = bn[src].right; }
+    while (n < 8)
+    {
+      int best = -1; float bestArea = -1.0f;
+      for (int i = 0; i < n; ++i)
+        if (bn[kids[i]].left >= 0) { const float a = bn[kids[i]].box.halfArea(); if (a > bestArea) { bestArea = a; best = i; } }
+      if (best < 0) break;
+      const int k = kids[best];
+      kids[best] = bn[k].left;
+      kids[n++] = bn[k].right;
+    }
+
+    // 2. assign children to octant slots: greedy max of dot(child centre - node centre, slot sign vector)
+    const Box& box = bn[src].box;
+    float centre[3]; for (int k = 0; k < 3; ++k) centre[k] = 0.5f * (box.lo[k] + box.hi[k]);
+    float cost[8][8];
+    for (int i = 0; i < n; ++i)
+    {
+      const Box& cb = bn[kids[i]].box;
+      float d[3]; for (int k = 0; k < 3; ++k) d[k] = 0.5f * (cb.lo[k] + cb.hi[k]) - centre[k];
+      for (int s = 0; s < 8; ++s)
+        cost[i][s] = ((s & 4) ? d[0] : -d[0]) + ((s & 2) ? d[1] : -d[1]) + ((s & 1) ? d[2] : -d[2]);
+    }
+    int slotOf[8]; bool slotUsed[8] = {}; bool kidDone[8] = {};
+    for (int round = 0; round < n; ++round)
+    {
+      int bi = -1, bs = -1; float bc = -std::numeric_limits<float>::infinity();
+      for (int i = 0; i < n; ++i) if (!kidDone[i])
+        for (int s = 0; s < 8; ++s) if (!slotUsed[s] && cost[i][s] > bc) { bc = cost[i][s]; bi = i; bs = s; }
+      slotOf[bi] = bs; slotUsed[bs] = true; kidDone[bi] = true;
+    }
+    int kidAt[8]; for (int s = 0; s < 8; ++s) kidAt[s] = -1;
+    for (int i = 0; i < n; ++i) kidAt[slotOf[i]] = kids[i];
+
+    // 3. quantisation frame.  Per axis: grid step 2^e with (hi - p) <= 254 steps, origin p a sixteenth of a
+    //    step below the box, so every child plane keeps slack on the grid (see DESIGN.md "conservative boxes").
+    float maxExt = 0.0f; for (int k = 0; k < 3; ++k) maxExt = std::max(maxExt, box.hi[k] - box.lo[k]);
+    int   e[3]; float p[3], step[3];
+    for (int k = 0; k < 3; ++k)
+    {
+      float ext = std::max(box.hi[k] - box.lo[k], std::max(maxExt * 0x1p-20f, 1.0e-30f));
+      int ek; std::frexp(ext / 253.0f, &ek);            // 2^ek > ext/253
+      ek = std::min(std::max(ek, -120), 120);
+      for (;;)
+      {
+        step[k] = pow2f(ek);
+        p[k] = box.lo[k] - step[k] * 0.0625f;
+        if (!(p[k] < box.lo[k])) p[k] = std::nextafterf(box.lo[k], -std::numeric_limits<float>::infinity());
+        if (std::fmaf(254.0f, step[k], p[k]) >= box.hi[k] || ek >= 120) break;
+        ++ek;
+      }
+      e[k] = ek;
+    }
+
+    Node8 node; std::memset(&node, 0, sizeof(node));
+    node.px = p[0]; node.py = p[1]; node.pz = p[2];
+    node.ex = (uint8_t)(e[0] + 127); node.ey = (uint8_t)(e[1] + 127); node.ez = (uint8_t)(e[2] + 127);
+
+    // 4. children: inner ones get one contiguous block of wide nodes, leaf primitives one contiguous run
+    uint32_t numInner = 0;
+    for (int s = 0; s < 8; ++s) if (kidAt[s] >= 0 && bn[kidAt[s]].left >= 0) { node.imask |= (uint8_t)(1u << s); ++numInner; }
+    node.childBase = (uint32_t)out.nodes.size();
+    out.nodes.resize(out.nodes.size() + numInner);
+    node.triBase = (uint32_t)out.primOrder.size();
+    uint32_t triOffset = 0;
+    uint8_t* qlo[3] = { node.qlox, node.qloy, node.qloz };
+    uint8_t* qhi[3] = { node.qhix, node.qhiy, node.qhiz };
+    for (int s = 0; s < 8; ++s)
+    {
+      if (kidAt[s] < 0) { for (int k = 0; k < 3; ++k) { qlo[k][s] = 255; qhi[k][s] = 0; } continue; }
+      const BinNode& c = bn[kidAt[s]];
+      for (int k = 0; k < 3; ++k)
+      {
+        int ql = (int)std::floor(((double)c.box.lo[k] - (double)p[k]) / (double)step[k]);
+        int qh = (int)std::ceil(((double)c.box.hi[k] - (double)p[k]) / (double)step[k]);
+        ql = std::min(std::max(ql, 0), 255); qh = std::min(std::max(qh, 0), 255);
+        // keep at least 1/64 step of slack, evaluated with the arithmetic the kernels use (q * step + p)
+        while (ql > 0 && !(std::fmaf((float)ql, step[k], p[k]) <= c.box.lo[k] - step[k] * 0.015625f)) --ql;
+        while (qh < 255 && !(std::fmaf((float)qh, step[k], p[k]) >= c.box.hi[k] + step[k] * 0.015625f)) ++qh;
+        qlo[k][s] = (uint8_t)ql; qhi[k][s] = (uint8_t)qh;
+      }
+      if (c.left < 0)
+      {
+        node.meta[s] = (uint8_t)((c.count << 5) | triOffset);
+        for (uint32_t i = 0; i < c.count; ++i) out.primOrder.push_back(order[c.first + i]);
+        triOffset += c.count;
+      }
+    }
+    out.nodes[dst] = node;
+    uint32_t rel = 0;
+    for (int s = 0; s < 8; ++s)
+      if (node.imask & (1u << s)) { emit(node.childBase + rel, kidAt[s]); ++rel; }
+  }
+};
+
+} // namespace
+
+void build_wide_bvh_host(const PrimBox* prims, uint32_t numPrims, WideBvh& out)
+{
+  out.nodes.clear(); out.primOrder.clear();
+  for (int k = 0; k < 3; ++k) { out.lo[k] = 0.0f; out.hi[k] = 0.0f; }
+  if (numPrims == 0)
+  {
+    // one empty node: every slot is empty, traversal falls straight through
+    Node8 node; std::memset(&node, 0, sizeof(node));
+    node.ex = node.ey = node.ez = 127;
+    for (int s = 0; s < 8; ++s) { node.qlox[s] = node.qloy[s] = node.qloz[s] = 255; }
+    out.nodes.push_back(node);
+    return;
+  }
+  Builder b; b.prims = prims;
+  b.order.resize(numPrims);
+  for (uint32_t i = 0; i < numPrims; ++i) b.order[i] = i;
+  b.nodes.reserve(2 * (size_t)numPrims);
+  const int root = b.build(0, numPrims);
+  for (int k = 0; k < 3; ++k) { out.lo[k] = b.nodes[root].box.lo[k]; out.hi[k] = b.nodes[root].box.hi[k]; }
+  out.nodes.reserve(numPrims / 2 + 8);
+  out.primOrder.reserve(numPrims);
+  out.nodes.emplace_back();
+  Emitter em{ b.nodes, b.order, out };
+  em.emit(0, root);
+}

@@ -1,0 +1,524 @@
+// kernels_shade.cu -- the shading side of the wavefront integrator: generate, shade, accumulate, plus
+// composite, tonemap and primary-ray export.  Built with -fmad=false (see shade.cuh).
+//
+//   generate   = __raygen__path_tracer prologue          (raygeneration.cu:173-201, :44-59)
+//   shade      = __closesthit__radiance / __miss__env_*  (closesthit.cu:126-279, miss.cu:41-109)
+//                + the integrator epilogue               (raygeneration.cu:92-145)
+//   accumulate = NaN filter + running average            (raygeneration.cu:220-253, :312-342)
+//   composite  = compositor kernel                       (compositor.cu:38-65)
+//   tonemap    = Application::screenshot loop            (Application.cpp:2262-2295)
+//
+// Path state lives in SoA arrays indexed by path id (WavefrontBuffers); queues hold path ids and are
+// compacted with warp ballots (one atomicAdd per warp).
+#include "shade.cuh"
+
+namespace {
+
+constexpr int kBlock = 256;
+constexpr uint32_t kNoPixel = 0xffffffffu;
+
+struct WfArgs
+{
+  WavefrontBuffers wf;
+  rt_SystemData sys;
+  uint32_t launchWidth, launchHeight;
+  int raygen, miss;
+  int iterFirst, iterCount;
+  uint32_t numPaths;
+};
+
+// Appends `value` for every lane with pred set; returns nothing.  All 32 lanes must call it.
+__device__ __forceinline__ void warp_append(uint32_t* __restrict__ queue, uint32_t* __restrict__ counter, bool pred, uint32_t value)
+{
+  const uint32_t mask = __ballot_sync(0xffffffffu, pred);
+  if (mask == 0u) return;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs((int)mask) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (pred) queue[base + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = value;
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_generate(const __grid_constant__ WfArgs a, uint32_t* __restrict__ queue, uint32_t* __restrict__ count)
+{
+  const uint32_t pixelsPerIter = a.launchWidth * a.launchHeight;
+  const uint32_t n = a.numPaths;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride)
+  {
+    const uint32_t p = base + threadIdx.x;
+    bool alive = false;
+    if (p < n)
+    {
+      const uint32_t it = p / pixelsPerIter, idx = p - it * pixelsPerIter;
+      const uint32_t y = idx / a.launchWidth, x = idx - y * a.launchWidth;
+      uint32_t seed = 0, col = 0; float3 pos, wi;
+      alive = start_path(a.sys, a.launchWidth, x, y, a.iterFirst + (int)it, seed, pos, wi, col);
+      if (alive)
+      {
+        a.wf.rayOrg[p] = make_float4(pos.x, pos.y, pos.z, a.sys.sceneEpsilon);
+        a.wf.rayDir[p] = make_float4(wi.x, wi.y, wi.z, RT_DEFAULT_MAX);
+        a.wf.throughput[p] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+        a.wf.radiance[p] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
+        a.wf.misc[p] = make_uint4(seed, 0u, (uint32_t)RT_MATERIAL_STACK_EMPTY, col);
+      }
+      else
+      {
+        a.wf.misc[p] = make_uint4(0u, 0u, 0u, kNoPixel);
+      }
+    }
+    warp_append(queue, count, alive, p);
+  }
+}
+
+__device__ __forceinline__ float3 xf_vector(const float4 r0, const float4 r1, const float4 r2, float3 v)
+{
+  return f3(r0.x * v.x + r0.y * v.y + r0.z * v.z, r1.x * v.x + r1.y * v.y + r1.z * v.z, r2.x * v.x + r2.y * v.y + r2.z * v.z);
+}
+__device__ __forceinline__ float3 xf_normal(const float4 r0, const float4 r1, const float4 r2, float3 v)
+{
+  return f3(r0.x * v.x + r1.x * v.y + r2.x * v.z, r0.y * v.x + r1.y * v.y + r2.y * v.z, r0.z * v.x + r1.z * v.y + r2.z * v.z);
+}
+__device__ __forceinline__ float3 ld3(const float* p) { return f3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); }
+
+__global__ void __launch_bounds__(kBlock)
+k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
+        const uint32_t* __restrict__ queueIn, const uint32_t* __restrict__ countIn,
+        uint32_t* __restrict__ queueOut, uint32_t* __restrict__ countOut,
+        uint32_t* __restrict__ shadowQueue, uint32_t* __restrict__ shadowCount)
+{
+  const rt_SystemData& sys = a.sys;
+  const uint32_t n = *countIn;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride)
+  {
+    const uint32_t i = base + threadIdx.x;
+    bool continues = false, shadow = false;
+    uint32_t p = 0;
+    if (i < n)
+    {
+      p = queueIn[i];
+      const float4 ro = a.wf.rayOrg[p], rd = a.wf.rayDir[p];
+      const float4 tp = a.wf.throughput[p];
+      float4 Lf = a.wf.radiance[p];
+      uint4 misc = a.wf.misc[p];
+      const float4 hit = a.wf.hit[p];
+      const uint32_t hitInst = a.wf.hitInst[p];
+
+      Prd prd;
+      prd.pos = f3(ro.x, ro.y, ro.z);
+      prd.wi = f3(rd.x, rd.y, rd.z);
+      prd.seed = misc.x;
+      int depth = (int)misc.y;
+      int stackIdx = (int)misc.z;
+      float3 throughput = f3(tp.x, tp.y, tp.z);
+      float3 radiance = f3(Lf.x, Lf.y, Lf.z);
+      prd.pdf = tp.w;
+      prd.flags = __float_as_uint(Lf.w);
+      prd.f_over_pdf = f3(0.0f);
+      prd.absorption_ior = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+      prd.sigma_t = f3(0.0f);
+
+      // ---- per-segment reset (raygeneration.cu:63-78)
+      prd.wo = -prd.wi;
+      prd.ior = make_float2(1.0f, 1.0f);
+      prd.distance = RT_DEFAULT_MAX;
+      prd.flags &= RT_FLAG_CLEAR_MASK;
+      if (RT_MATERIAL_STACK_FIRST <= stackIdx)
+      {
+        const float4 top = a.wf.absStack[(size_t)p * 4 + stackIdx];
+        prd.flags |= RT_FLAG_VOLUME;
+        prd.sigma_t = f3(top.x, top.y, top.z);
+        prd.ior.x = top.w;
+        if (RT_MATERIAL_STACK_FIRST <= stackIdx - 1) prd.ior.y = a.wf.absStack[(size_t)p * 4 + stackIdx - 1].w;
+      }
+
+      if (hitInst == 0xffffffffu)
+      {
+        miss_program(sys, a.miss, prd);
+      }
+      else
+      {
+        // ---- __closesthit__radiance (closesthit.cu:126-305)
+        const rt_GeometryInstanceData gi = sc.geomInst[hitInst];
+        const uint32_t prim = __float_as_uint(hit.w);
+        const uint32_t* ix = reinterpret_cast<const uint32_t*>(gi.indices) + 3u * (size_t)prim;
+        const uint32_t i0 = __ldg(ix), i1 = __ldg(ix + 1), i2 = __ldg(ix + 2);
+        const float* A0 = reinterpret_cast<const float*>(gi.attributes) + 12u * (size_t)i0;
+        const float* A1 = reinterpret_cast<const float*>(gi.attributes) + 12u * (size_t)i1;
+        const float* A2 = reinterpret_cast<const float*>(gi.attributes) + 12u * (size_t)i2;
+        const float bx = hit.y, by = hit.z;
+        const float alpha = 1.0f - bx - by;
+        const float3 p0 = ld3(A0), p1 = ld3(A1), p2 = ld3(A2);
+        const float3 ng = cross(p1 - p0, p2 - p0);
+        const float3 tg = ld3(A0 + 3) * alpha + ld3(A1 + 3) * bx + ld3(A2 + 3) * by;
+        const float3 ns = ld3(A0 + 6) * alpha + ld3(A1 + 6) * bx + ld3(A2 + 6) * by;
+
+        const float4* o2w = sc.objectToWorld + (size_t)hitInst * 3u;
+        const float4* w2o = sc.instances + (size_t)hitInst * 4u;
+        const float4 w0 = __ldg(o2w), w1 = __ldg(o2w + 1), w2 = __ldg(o2w + 2);
+        const float4 v0 = __ldg(w2o), v1 = __ldg(w2o + 1), v2 = __ldg(w2o + 2);
+
+        State state;
+        state.normalGeo = normalize(xf_normal(v0, v1, v2, ng));
+        state.tangent   = normalize(xf_vector(w0, w1, w2, tg));
+        state.normal    = normalize(xf_normal(v0, v1, v2, ns));
+
+        prd.distance = hit.x;
+        prd.pos = prd.pos + prd.wi * prd.distance;
+        prd.flags |= (0.0f <= dot(prd.wo, state.normalGeo)) ? RT_FLAG_FRONTFACE : 0u;
+        if ((prd.flags & RT_FLAG_FRONTFACE) == 0u)
+        {
+          state.normalGeo = -state.normalGeo;
+          state.tangent = -state.tangent;
+          state.normal = -state.normal;
+        }
+        prd.radiance = f3(0.0f);
+
+        bool emissive = false;
+        if (0 <= gi.lightIndex && (prd.flags & RT_FLAG_FRONTFACE))
+        {
+          const float cosTheta = dot(prd.wo, state.normalGeo);
+          if (RT_DENOMINATOR_EPSILON < cosTheta)
+          {
+            const rt_LightDefinition& light = reinterpret_cast<const rt_LightDefinition*>(sys.lightDefinitions)[gi.lightIndex];
+            float3 emission = f3(light.emission);
+            const float lightPdf = (prd.distance * prd.distance) / (light.area * cosTheta);
+            if ((prd.flags & RT_FLAG_DIFFUSE) && RT_DENOMINATOR_EPSILON < lightPdf)
+              emission = emission * power_heuristic(prd.pdf, lightPdf);
+            prd.radiance = emission;
+            prd.flags |= RT_FLAG_TERMINATE;
+            emissive = true;
+          }
+        }
+        if (!emissive)
+        {
+          prd.f_over_pdf = f3(0.0f);
+          prd.pdf = 0.0f;
+          const rt_MaterialDefinition material = reinterpret_cast<const rt_MaterialDefinition*>(sys.materialDefinitions)[gi.materialIndex];
+          state.albedo = f3(material.albedo);
+          prd.flags = (prd.flags & ~RT_FLAG_DIFFUSE) | RT_FLAG_HIT | material.flags;
+          bsdf_sample(material, state, prd);
+
+          const int numLights = sys.numLights;
+          if ((prd.flags & RT_FLAG_DIFFUSE) && 0 < numLights)
+          {
+            const float2 sample = rng2(prd.seed);
+            LightSample ls; ls.pdf = 0.0f; ls.distance = 0.0f; ls.direction = f3(0.0f); ls.emission = f3(0.0f);
+            if (1 < numLights)
+            {
+              int idx = (int)floorf(rng(prd.seed) * (float)numLights);
+              idx = idx < 0 ? 0 : (idx > numLights - 1 ? numLights - 1 : idx);
+              ls.index = idx;
+            }
+            else ls.index = 0;
+            const int type = reinterpret_cast<const rt_LightDefinition*>(sys.lightDefinitions)[ls.index].type;
+            if (type == RT_LIGHT_PARALLELOGRAM) light_parallelogram(sys, prd.pos, sample, ls);
+            else if (a.miss == RT_MISS_SPHERE)  light_env_sphere(sys, sample, ls);
+            else                                light_env_constant(numLights, sample, ls);
+            if (0.0f < ls.pdf)
+            {
+              const float4 bp = bsdf_eval(material, state, prd, ls.direction);
+              const float3 f = f3(bp.x, bp.y, bp.z);
+              if (0.0f < bp.w && !is_null(f))
+              {
+                // the shadow ray is traced by `connect`; its contribution is what closesthit.cu:289-299 would add
+                // if the ray is unoccluded, already multiplied by the throughput the integrator applies at :100
+                if (prd.flags & RT_FLAG_VOLUME)
+                  ls.emission = ls.emission * f3(rt_expf(-ls.distance * prd.sigma_t.x), rt_expf(-ls.distance * prd.sigma_t.y), rt_expf(-ls.distance * prd.sigma_t.z));
+                const float weightMis = power_heuristic(ls.pdf, bp.w);
+                const float3 c = f * ls.emission * (weightMis * dot(ls.direction, state.normal) / ls.pdf);
+                float3 tseg = throughput;
+                if (prd.flags & RT_FLAG_VOLUME)
+                  tseg = tseg * f3(rt_expf(-prd.distance * prd.sigma_t.x), rt_expf(-prd.distance * prd.sigma_t.y), rt_expf(-prd.distance * prd.sigma_t.z));
+                const float3 tc = tseg * c;
+                a.wf.shadowOrg[p] = make_float4(prd.pos.x, prd.pos.y, prd.pos.z, sys.sceneEpsilon);
+                a.wf.shadowDir[p] = make_float4(ls.direction.x, ls.direction.y, ls.direction.z, ls.distance - sys.sceneEpsilon);
+                a.wf.shadowContrib[p] = make_float4(tc.x, tc.y, tc.z, 0.0f);
+                shadow = true;
+              }
+            }
+          }
+        }
+      }
+
+      // ---- integrator epilogue (raygeneration.cu:92-145)
+      if (prd.flags & RT_FLAG_VOLUME)
+        throughput = throughput * f3(rt_expf(-prd.distance * prd.sigma_t.x), rt_expf(-prd.distance * prd.sigma_t.y), rt_expf(-prd.distance * prd.sigma_t.z));
+      radiance = radiance + throughput * prd.radiance;
+
+      bool ended = (prd.flags & RT_FLAG_TERMINATE) || prd.pdf <= 0.0f || is_null(prd.f_over_pdf);
+      if (!ended)
+      {
+        throughput = throughput * prd.f_over_pdf;
+        if (sys.pathLengths.x <= depth)
+        {
+          const float probability = fmax3(throughput);
+          if (probability < rng(prd.seed)) ended = true;
+          else throughput = divs(throughput, probability);
+        }
+      }
+      if (!ended)
+      {
+        if ((prd.flags & (RT_FLAG_THINWALLED | RT_FLAG_TRANSMISSION)) == RT_FLAG_TRANSMISSION)
+        {
+          if (prd.flags & RT_FLAG_FRONTFACE)
+          {
+            stackIdx = (stackIdx + 1 < RT_MATERIAL_STACK_LAST) ? stackIdx + 1 : RT_MATERIAL_STACK_LAST;
+            a.wf.absStack[(size_t)p * 4 + stackIdx] = prd.absorption_ior;
+          }
+          else
+          {
+            stackIdx = (stackIdx - 1 > RT_MATERIAL_STACK_EMPTY) ? stackIdx - 1 : RT_MATERIAL_STACK_EMPTY;
+          }
+        }
+        ++depth;
+        continues = depth < sys.pathLengths.y;
+      }
+
+      a.wf.radiance[p] = make_float4(radiance.x, radiance.y, radiance.z, __uint_as_float(prd.flags));
+      if (continues)
+      {
+        a.wf.rayOrg[p] = make_float4(prd.pos.x, prd.pos.y, prd.pos.z, sys.sceneEpsilon);
+        a.wf.rayDir[p] = make_float4(prd.wi.x, prd.wi.y, prd.wi.z, RT_DEFAULT_MAX);
+        a.wf.throughput[p] = make_float4(throughput.x, throughput.y, throughput.z, prd.pdf);
+        misc.x = prd.seed; misc.y = (uint32_t)depth; misc.z = (uint32_t)stackIdx;
+        a.wf.misc[p] = misc;
+      }
+    }
+    warp_append(queueOut, countOut, continues, p);
+    warp_append(shadowQueue, shadowCount, shadow, p);
+  }
+}
+
+// One thread per launch index; applies the batch's iterations in order (running average is order dependent).
+__global__ void __launch_bounds__(kBlock)
+k_accumulate(const __grid_constant__ WfArgs a)
+{
+  const uint32_t pixelsPerIter = a.launchWidth * a.launchHeight;
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= pixelsPerIter) return;
+  const uint32_t col = a.wf.misc[idx].w;
+  if (col == kNoPixel) return;
+  const uint32_t y = idx / a.launchWidth;
+  float4* buffer; size_t index;
+  if (a.raygen == RTC_RAYGEN_LOCAL_COPY) { buffer = reinterpret_cast<float4*>(a.sys.texelBuffer); index = idx; }
+  else { buffer = reinterpret_cast<float4*>(a.sys.outputBuffer); index = (size_t)y * (size_t)a.sys.resolution.x + col; }
+  float4 dst = buffer[index];
+  bool wrote = false;
+  for (int b = 0; b < a.iterCount; ++b)
+  {
+    const float4 L = a.wf.radiance[(size_t)b * pixelsPerIter + idx];
+    float3 r = f3(L.x, L.y, L.z);
+    if (isnan(r.x) || isnan(r.y) || isnan(r.z)) continue;
+    const int it = a.iterFirst + b;
+    if (0 < it)
+    {
+      const float t = 1.0f / (float)(it + 1);
+      r = f3(dst.x + t * (r.x - dst.x), dst.y + t * (r.y - dst.y), dst.z + t * (r.z - dst.z));
+    }
+    dst = make_float4(r.x, r.y, r.z, 1.0f);
+    wrote = true;
+  }
+  if (wrote) buffer[index] = dst;
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_generate_primary(const __grid_constant__ rt_SystemData sys, uint32_t w, uint32_t h, int iteration, float4* __restrict__ rays)
+{
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= w * h) return;
+  const uint32_t y = idx / w, x = idx - y * w;
+  uint32_t seed, col; float3 pos, wi;
+  if (start_path(sys, w, x, y, iteration, seed, pos, wi, col))
+  {
+    rays[2 * (size_t)idx] = make_float4(pos.x, pos.y, pos.z, sys.sceneEpsilon);
+    rays[2 * (size_t)idx + 1] = make_float4(wi.x, wi.y, wi.z, RT_DEFAULT_MAX);
+  }
+  else
+  {
+    rays[2 * (size_t)idx] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    rays[2 * (size_t)idx + 1] = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
+  }
+}
+
+// compositor.cu:38-65
+__global__ void __launch_bounds__(kBlock)
+k_composite(const __grid_constant__ rt_CompositorData a)
+{
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t y = blockIdx.y;
+  if (x >= (uint32_t)a.launchWidth || y >= (uint32_t)a.resolution.y) return;
+  const uint32_t xBlock = x >> a.tileShift.x, yBlock = y >> a.tileShift.y;
+  const uint32_t xTile = xBlock * (uint32_t)a.deviceCount + (((uint32_t)a.deviceIndex + yBlock) % (uint32_t)a.deviceCount);
+  const uint32_t xPixel = xTile * (uint32_t)a.tileSize.x + (x & (uint32_t)(a.tileSize.x - 1));
+  if (xPixel < (uint32_t)a.resolution.x)
+  {
+    const float4* src = reinterpret_cast<const float4*>(a.tileBuffer);
+    float4* dst = reinterpret_cast<float4*>(a.outputBuffer);
+    dst[(size_t)y * (size_t)a.resolution.x + xPixel] = src[(size_t)y * (size_t)a.launchWidth + x];
+  }
+}
+
+// Application.cpp:2262-2295
+__global__ void __launch_bounds__(kBlock)
+k_tonemap(const __grid_constant__ rt_TonemapperParams p, const float4* __restrict__ rgba, uint8_t* __restrict__ rgb, uint64_t n)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float invGamma = 1.0f / p.gamma;
+  const float3 colorBalance = f3(p.colorBalance[0], p.colorBalance[1], p.colorBalance[2]);
+  const float invWhitePoint = p.brightness / p.whitePoint;
+  const float crushBlacks = p.crushBlacks + p.crushBlacks + 1.0f;
+  const float3 lumw = f3(0.3f, 0.59f, 0.11f);
+  const float4 px = rgba[i];
+  const float3 hdr = f3(px.x, px.y, px.z);
+  float3 ldr = (colorBalance * invWhitePoint) * hdr;
+  const float3 num = ldr * p.burnHighlights + f3(1.0f), den = ldr + f3(1.0f);
+  ldr = ldr * f3(num.x / den.x, num.y / den.y, num.z / den.z);
+  float lum = dot(ldr, lumw);
+  ldr = f3(lum) + (ldr - f3(lum)) * p.saturation;
+  ldr = f3(fmaxf(0.0f, ldr.x), fmaxf(0.0f, ldr.y), fmaxf(0.0f, ldr.z));
+  lum = dot(ldr, lumw);
+  if (lum < 1.0f)
+  {
+    const float3 crushed = f3(rt_powf(ldr.x, crushBlacks), rt_powf(ldr.y, crushBlacks), rt_powf(ldr.z, crushBlacks));
+    ldr = crushed + (ldr - crushed) * sqrtf(lum);
+    ldr = f3(fmaxf(0.0f, ldr.x), fmaxf(0.0f, ldr.y), fmaxf(0.0f, ldr.z));
+  }
+  float c[3] = { rt_powf(ldr.x, invGamma), rt_powf(ldr.y, invGamma), rt_powf(ldr.z, invGamma) };
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+  {
+    float v = c[k];
+    if (v < 0.0f) v = 0.0f;
+    if (v > 1.0f) v = 1.0f;
+    rgb[3 * i + k] = (uint8_t)(v * 255.0f);
+  }
+}
+
+} // namespace
+
+int ensure_wavefront(rtc_context* ctx, uint64_t capacity)
+{
+  WavefrontBuffers& wf = ctx->wf;
+  if (wf.capacity >= capacity) return 0;
+  if (wf.base) { RTC_CUDA(cudaStreamSynchronize(ctx->stream)); RTC_CUDA(cudaFree(wf.base)); wf = WavefrontBuffers(); }
+  // one allocation, carved into 256-byte aligned SoA arrays
+  auto align = [](uint64_t v) { return (v + 255u) & ~(uint64_t)255u; };
+  const uint64_t n = capacity;
+  uint64_t off = 0;
+  const uint64_t oRayOrg = off; off += align(16 * n);
+  const uint64_t oRayDir = off; off += align(16 * n);
+  const uint64_t oHit = off; off += align(16 * n);
+  const uint64_t oHitInst = off; off += align(4 * n);
+  const uint64_t oThroughput = off; off += align(16 * n);
+  const uint64_t oRadiance = off; off += align(16 * n);
+  const uint64_t oMisc = off; off += align(16 * n);
+  const uint64_t oAbs = off; off += align(64 * n);
+  const uint64_t oSOrg = off; off += align(16 * n);
+  const uint64_t oSDir = off; off += align(16 * n);
+  const uint64_t oSCon = off; off += align(16 * n);
+  const uint64_t oQA = off; off += align(4 * n);
+  const uint64_t oQB = off; off += align(4 * n);
+  const uint64_t oQS = off; off += align(4 * n);
+  const uint64_t oCnt = off; off += align(4 * 256);
+  void* base = nullptr;
+  RTC_CUDA(cudaMalloc(&base, off));
+  char* b = static_cast<char*>(base);
+  wf.base = base; wf.capacity = capacity;
+  wf.rayOrg = (float4*)(b + oRayOrg); wf.rayDir = (float4*)(b + oRayDir); wf.hit = (float4*)(b + oHit); wf.hitInst = (uint32_t*)(b + oHitInst);
+  wf.throughput = (float4*)(b + oThroughput); wf.radiance = (float4*)(b + oRadiance); wf.misc = (uint4*)(b + oMisc); wf.absStack = (float4*)(b + oAbs);
+  wf.shadowOrg = (float4*)(b + oSOrg); wf.shadowDir = (float4*)(b + oSDir); wf.shadowContrib = (float4*)(b + oSCon);
+  wf.queueA = (uint32_t*)(b + oQA); wf.queueB = (uint32_t*)(b + oQB); wf.shadowQueue = (uint32_t*)(b + oQS); wf.counters = (uint32_t*)(b + oCnt);
+  return 0;
+}
+
+namespace {
+
+// sums the per-depth queue counts of one batch into the 64-bit statistics
+__global__ void k_stats(const uint32_t* __restrict__ counters, int maxDepth, uint32_t numPaths, uint64_t* __restrict__ stats)
+{
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+  {
+    uint64_t rad = 0, sh = 0;
+    for (int d = 0; d < maxDepth; ++d) { rad += counters[d]; sh += counters[64 + d]; }
+    stats[0] += rad; stats[1] += sh; stats[2] += counters[0];
+  }
+}
+
+} // namespace
+
+int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uint32_t h, int raygen, int miss, int iterFirst, int iterCount)
+{
+  if (sys.topObject == 0) RTC_FAIL("SystemData.topObject is null (call rtc_ias_build first)");
+  const SceneRecord* scene = nullptr;
+  for (const SceneRecord* s : ctx->scenes) if ((uint64_t)(uintptr_t)s->d_desc == sys.topObject) scene = s;
+  if (!scene) RTC_FAIL("SystemData.topObject was not returned by rtc_ias_build on this context");
+  const int maxDepth = sys.pathLengths.y;
+  if (maxDepth > 63) RTC_FAIL("pathLengths.y > 63 is not supported");
+  const uint64_t pixels = (uint64_t)w * h;
+  if (pixels == 0 || iterCount <= 0) return 0;
+  // iterations in flight per batch: keep the wavefront around 8M paths
+  uint64_t perBatch = (8u << 20) / pixels; if (perBatch < 1) perBatch = 1; if (perBatch > (uint64_t)iterCount) perBatch = (uint64_t)iterCount;
+  if (pixels * perBatch > 0x7fffffffull) RTC_FAIL("launch too large");
+  if (int rc = ensure_wavefront(ctx, pixels * perBatch)) return rc;
+
+  const int gridShade = ctx->numSMs * 8;
+  for (int done = 0; done < iterCount; done += (int)perBatch)
+  {
+    const int batch = (iterCount - done < (int)perBatch) ? iterCount - done : (int)perBatch;
+    WfArgs a;
+    a.wf = ctx->wf; a.sys = sys; a.launchWidth = w; a.launchHeight = h; a.raygen = raygen; a.miss = miss;
+    a.iterFirst = iterFirst + done; a.iterCount = batch; a.numPaths = (uint32_t)(pixels * (uint64_t)batch);
+    uint32_t* cnt = ctx->wf.counters;
+    RTC_CUDA(cudaMemsetAsync(cnt, 0, 4 * 256, ctx->stream));
+    k_generate<<<gridShade, kBlock, 0, ctx->stream>>>(a, ctx->wf.queueA, cnt + 0);
+    ctx->kernelLaunches++;
+    uint32_t* qIn = ctx->wf.queueA; uint32_t* qOut = ctx->wf.queueB;
+    for (int d = 0; d < maxDepth; ++d)
+    {
+      if (int rc = launch_extend(ctx, &scene->desc, ctx->wf, qIn, cnt + d)) return rc;
+      k_shade<<<gridShade, kBlock, 0, ctx->stream>>>(a, scene->desc, qIn, cnt + d, qOut, cnt + d + 1, ctx->wf.shadowQueue, cnt + 64 + d);
+      ctx->kernelLaunches++;
+      if (sys.numLights > 0) { if (int rc = launch_connect(ctx, &scene->desc, ctx->wf, cnt + 64 + d)) return rc; }
+      uint32_t* t = qIn; qIn = qOut; qOut = t;
+    }
+    k_accumulate<<<(unsigned)((pixels + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(a);
+    k_stats<<<1, 32, 0, ctx->stream>>>(cnt, maxDepth, a.numPaths, ctx->d_stats);
+    ctx->kernelLaunches += 2;
+    RTC_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int launch_generate_primary(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uint32_t h, int iteration, rtc_ray* rays)
+{
+  const uint64_t n = (uint64_t)w * h;
+  if (n == 0) return 0;
+  k_generate_primary<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(sys, w, h, iteration, reinterpret_cast<float4*>(rays));
+  ctx->kernelLaunches++;
+  RTC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_composite(rtc_context* ctx, const rt_CompositorData& args)
+{
+  if (args.launchWidth <= 0 || args.resolution.y <= 0) return 0;
+  dim3 grid((unsigned)((args.launchWidth + kBlock - 1) / kBlock), (unsigned)args.resolution.y);
+  k_composite<<<grid, kBlock, 0, ctx->stream>>>(args);
+  ctx->kernelLaunches++;
+  RTC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_tonemap(rtc_context* ctx, const rt_TonemapperParams& p, const float4* rgba, uint8_t* rgb, uint64_t n)
+{
+  if (n == 0) return 0;
+  k_tonemap<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(p, rgba, rgb, n);
+  ctx->kernelLaunches++;
+  RTC_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,133 @@
+// rtc_internal.h -- structures shared by the host side of librtcore and its sm_100a kernels.
+//
+// HBM layout of one scene (everything the traversal touches is 16-byte addressable so every
+// fetch is one LDG.128):
+//   nodes      uint4[5] per wide node (80 B): 8 children, quantised boxes           -> Node8 below
+//   tris       float4[3] per triangle (48 B): v0.xyz|prim id, v1.xyz|0, v2.xyz|0    (leaf order)
+//   instances  float4[4] per instance (64 B): world->object rows 0..2, {root node, -, -, -}
+//   tlasLeaves uint32 per instance-level leaf slot -> instance id
+//   shading tables (used by shade only): objectToWorld float4[3], rt_GeometryInstanceData per instance
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "rtc_core.h"
+
+// 8-wide node with child boxes quantised to 8 bits per plane on a per-node power-of-two grid
+// (after Ylitie, Karras, Laine, "Efficient Incoherent Ray Traversal on GPUs Through Compressed
+// Wide BVHs", HPG 2017).  Child i occupies slot i; slots are assigned by octant so that
+// slot ^ (7 ^ rayOctant) is a front-to-back priority.
+//   empty slot : imask bit clear, meta == 0
+//   inner child: imask bit set; its node is childBase + popc(imask & ((1 << slot) - 1))
+//   leaf child : imask bit clear, meta = (count << 5) | offset; primitives triBase + offset .. + count - 1
+struct Node8
+{
+  float    px, py, pz;
+  uint8_t  ex, ey, ez;      // biased exponents: grid step = 2^(e - 127)
+  uint8_t  imask;
+  uint32_t childBase;
+  uint32_t triBase;
+  uint8_t  meta[8];
+  uint8_t  qlox[8], qloy[8];
+  uint8_t  qloz[8], qhix[8];
+  uint8_t  qhiy[8], qhiz[8];
+};
+static_assert(sizeof(Node8) == 80, "wide node is 80 bytes");
+
+// Device-visible scene descriptor; SystemData::topObject points at one of these (in device memory).
+struct SceneDesc
+{
+  const uint4*    nodes;
+  const float4*   tris;
+  const float4*   instances;
+  const uint32_t* tlasLeaves;
+  const float4*   objectToWorld;
+  const rt_GeometryInstanceData* geomInst;
+  uint32_t        tlasRoot;
+  uint32_t        numInstances;
+  uint32_t        numNodes;
+  uint32_t        numTris;
+};
+
+// Host-side result of a BVH build over generic primitive boxes.
+struct WideBvh
+{
+  std::vector<Node8>    nodes;      // nodes[0] is the root
+  std::vector<uint32_t> primOrder;  // leaf order -> input primitive index
+  float lo[3], hi[3];               // bounds of everything
+};
+
+struct PrimBox { float lo[3], hi[3]; };
+
+// bvh_build_host.cpp: binned-SAH binary build, greedy collapse to 8-wide, octant slot assignment, quantisation.
+void build_wide_bvh_host(const PrimBox* prims, uint32_t numPrims, WideBvh& out);
+
+struct GasRecord
+{
+  uint32_t nodeOffset = 0, numNodes = 0;   // into the context-wide staging arrays
+  uint32_t triOffset = 0, numTris = 0;
+  float    lo[3], hi[3];
+  uint64_t attributes = 0, indices = 0;
+  uint32_t strideBytes = 0, numVerts = 0;
+};
+
+struct SceneRecord
+{
+  SceneDesc desc{};          // host copy
+  SceneDesc* d_desc = nullptr;
+  void *d_nodes = nullptr, *d_tris = nullptr, *d_instances = nullptr, *d_tlasLeaves = nullptr, *d_o2w = nullptr, *d_geomInst = nullptr;
+  uint32_t numTlasLeaves = 0;
+};
+
+// Wavefront state of one launch batch (device pointers, SoA, sized for `capacity` paths).
+struct WavefrontBuffers
+{
+  uint64_t capacity = 0;
+  float4 *rayOrg = nullptr, *rayDir = nullptr;     // per path: next radiance ray (org.xyz,tmin) (dir.xyz,tmax)
+  float4 *hit = nullptr;                           // per path: t,u,v,prim bits
+  uint32_t *hitInst = nullptr;                     // per path
+  float4 *throughput = nullptr;                    // per path: T.xyz, pdf
+  float4 *radiance = nullptr;                      // per path: L.xyz, flags bits
+  uint4  *misc = nullptr;                          // per path: seed, depth, stackIdx, pixel index
+  float4 *absStack = nullptr;                      // per path x 4: nested-volume stack
+  float4 *shadowOrg = nullptr, *shadowDir = nullptr, *shadowContrib = nullptr;  // per path
+  uint32_t *queueA = nullptr, *queueB = nullptr, *shadowQueue = nullptr;
+  uint32_t *counters = nullptr;                    // [0..63] extend counts per depth, [64..127] shadow counts per depth, 128.. stats
+  void* base = nullptr;
+};
+
+struct rtc_context
+{
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int numSMs = 0;
+  std::vector<GasRecord> gas;
+  std::vector<Node8>  stagingNodes;   // all GAS nodes, concatenated (indices absolute)
+  std::vector<float4> stagingTris;
+  std::vector<SceneRecord*> scenes;
+  WavefrontBuffers wf;
+  uint64_t* d_stats = nullptr;        // device counters: radiance rays, shadow rays, path samples
+  uint64_t kernelLaunches = 0;
+  double lastTraceMs = 0.0;
+  cudaEvent_t evA = nullptr, evB = nullptr;
+};
+
+// error plumbing (rtc_api.cpp)
+int rtc_set_error(const char* file, int line, const char* call, int code, const char* text);
+#define RTC_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return rtc_set_error(__FILE__, __LINE__, #call, (int)e_, cudaGetErrorString(e_)); } while (0)
+#define RTC_FAIL(text) return rtc_set_error(__FILE__, __LINE__, __func__, -1, text)
+
+// kernel launchers (kernels_trace.cu / kernels_shade.cu); all enqueue on ctx->stream
+int launch_trace_closest(rtc_context* ctx, const SceneDesc* d_scene, const rtc_ray* rays, uint64_t n, rtc_hit* hits);
+int launch_trace_any(rtc_context* ctx, const SceneDesc* d_scene, const rtc_ray* rays, uint64_t n, uint32_t* occluded);
+int launch_extend(rtc_context* ctx, const SceneDesc* d_scene, const WavefrontBuffers& wf, const uint32_t* queue, const uint32_t* count);
+int launch_connect(rtc_context* ctx, const SceneDesc* d_scene, const WavefrontBuffers& wf, const uint32_t* count);
+int launch_generate_primary(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uint32_t h, int iteration, rtc_ray* rays);
+int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uint32_t h, int raygen, int miss, int iterFirst, int iterCount);
+int launch_composite(rtc_context* ctx, const rt_CompositorData& args);
+int launch_tonemap(rtc_context* ctx, const rt_TonemapperParams& p, const float4* rgba, uint8_t* rgb, uint64_t n);
+int ensure_wavefront(rtc_context* ctx, uint64_t capacity);
