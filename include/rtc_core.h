@@ -62,16 +62,23 @@ typedef struct {
   double   lastTraceMs;      /* device time of the last rtc_trace_* call (CUDA events on the context stream) */
 } rtc_stats;
 
-/* BVH statistics and raw arrays, so the CPU oracle can walk the identical tree and count
- * the nodes / triangles / instances each ray touches (the algorithmic-bytes figure). */
+/* BVH statistics of a built scene. */
 typedef struct {
-  uint32_t numNodes;         /* 80 B wide nodes (all GAS + the instance level) */
-  uint32_t numTris;          /* 48 B triangle records */
+  uint64_t numNodes;         /* 80 B wide nodes: every distinct GAS referenced + the instance level */
+  uint64_t numTris;          /* 48 B triangle records of every distinct GAS referenced */
   uint32_t numInstances;
-  uint32_t numTlasLeaves;
-  uint32_t tlasRoot;
+  uint32_t numTlasNodes;
+  uint32_t numGas;           /* distinct GAS referenced */
   uint32_t reserved;
+  double   gasBuildMs;       /* sum of the build times of the referenced GAS */
+  double   iasBuildMs;
 } rtc_scene_info;
+
+/* Work one traversal did, summed over a ray set (the algorithmic-bytes figure of DESIGN.md):
+ * wide nodes popped (80 B each), triangles tested (48 B each), instances entered (64 B each). */
+typedef struct {
+  uint64_t nodes, tris, instances, rays;
+} rtc_trace_counts;
 
 enum { RTC_RAYGEN_FULL_FRAME = 0,      /* __raygen__path_tracer            (raygeneration.cu:167) */
        RTC_RAYGEN_LOCAL_COPY = 1 };    /* __raygen__path_tracer_local_copy (raygeneration.cu:259) */
@@ -89,12 +96,23 @@ int rtc_synchronize(rtc_context* ctx);
 /* The context's stream as a cudaStream_t value (for callers that enqueue their own work, e.g. NCCL). */
 uint64_t rtc_context_stream(rtc_context* ctx);
 
+/* Device enumeration and peer-to-peer plumbing of the multi-GPU strategies
+ * (cuDeviceGetCount / cuDeviceGetName, Raytracer.cpp:53-64; cuDeviceCanAccessPeer / cuCtxEnablePeerAccess,
+ * Raytracer.cpp:127-132; cuMemcpyPeerAsync, DeviceMultiGPULocalCopy.cpp:289-295). */
+int rtc_device_count(int* count);
+int rtc_device_name(int deviceOrdinal, char* name, int length);
+int rtc_peer_can_access(int deviceOrdinal, int peerOrdinal, int* canAccess);
+int rtc_peer_enable(rtc_context* ctx, rtc_context* peer);      /* ctx may then dereference peer's allocations */
+int rtc_peer_disable(rtc_context* ctx, rtc_context* peer);
+/* dst (on dstCtx) <- src (on srcCtx): waits for srcCtx's stream, then copies asynchronously on dstCtx's stream. */
+int rtc_memcpy_peer(rtc_context* dstCtx, uint64_t dst, rtc_context* srcCtx, uint64_t src, uint64_t bytes);
+
 int rtc_malloc(rtc_context* ctx, uint64_t bytes, uint64_t* dptr);
 int rtc_free(rtc_context* ctx, uint64_t dptr);
 int rtc_upload(rtc_context* ctx, uint64_t dst, const void* src, uint64_t bytes);     /* async on the context stream */
 int rtc_download(rtc_context* ctx, void* dst, uint64_t src, uint64_t bytes);         /* async on the context stream */
 int rtc_memset(rtc_context* ctx, uint64_t dst, int value, uint64_t bytes);
-int rtc_host_alloc(rtc_context* ctx, uint64_t bytes, void** ptr);                    /* pinned */
+int rtc_host_alloc(rtc_context* ctx, uint64_t bytes, void** ptr);                    /* pinned, portable, device-mapped (UVA: same pointer on every GPU) */
 int rtc_host_free(rtc_context* ctx, void* ptr);
 
 /* attributes: device pointer to vertex records, position = 3 floats at offset 0, strideBytes apart
@@ -103,11 +121,10 @@ int rtc_gas_build(rtc_context* ctx, uint64_t attributes, uint32_t strideBytes, u
                   uint64_t indices, uint32_t numTris, uint32_t buildFlags, uint32_t* gas);
 /* Builds the instance level, the per-instance tables and returns SystemData::topObject. */
 int rtc_ias_build(rtc_context* ctx, const rtc_instance_desc* instances, uint32_t numInstances, uint64_t* topObject);
-/* Per-instance material switch (Device::updateMaterial's hit-record update, Device.cpp:1112-1167). */
 int rtc_scene_info_get(rtc_context* ctx, uint64_t topObject, rtc_scene_info* info);
-/* Copies the raw BVH out: nodes (80 B each), tris (48 B each), instances (64 B each: 3x4 inverse + root),
- * tlasLeaves (uint32 instance ids).  Any pointer may be NULL. */
-int rtc_scene_export(rtc_context* ctx, uint64_t topObject, void* nodes, void* tris, void* instances, void* tlasLeaves);
+/* Frees one scene (the instance level and its tables; GAS stay alive until rtc_gas_destroy / context destroy). */
+int rtc_scene_destroy(rtc_context* ctx, uint64_t topObject);
+int rtc_gas_destroy(rtc_context* ctx, uint32_t gas);
 /* Copies out the 3x4 world->object matrix of one instance. */
 int rtc_instance_inverse(rtc_context* ctx, uint64_t topObject, uint32_t instance, float out[12]);
 
@@ -120,9 +137,36 @@ int rtc_instance_inverse(rtc_context* ctx, uint64_t topObject, uint32_t instance
 int rtc_launch(rtc_context* ctx, const rt_SystemData* sys, uint32_t launchWidth, uint32_t launchHeight,
                int raygen, int miss, int iterationFirst, int iterationCount);
 
+/* rtc_launch with the accumulation index decoupled from the seed index: iteration b of the call draws its seeds from
+ * iterationFirst + b and is blended into the frame as sample number accumulationFirst + b (running average weight
+ * 1 / (accumulationFirst + b + 1)).  rtc_launch == rtc_launch_ex with accumulationFirst = iterationFirst.  Used by the
+ * sample-range partition across GPUs (each GPU averages its own disjoint iteration indices from zero).
+ * countWork != 0 additionally accumulates the traversal work counters read by rtc_launch_counts_get (slower; for
+ * the algorithmic-bytes figure only, never for a timed run). */
+int rtc_launch_ex(rtc_context* ctx, const rt_SystemData* sys, uint32_t launchWidth, uint32_t launchHeight,
+                  int raygen, int miss, int iterationFirst, int iterationCount, int accumulationFirst, int countWork);
+/* Work counters of the launches made with countWork since the last reset: [0] extend (radiance rays), [1] connect (shadow rays). */
+int rtc_launch_counts_get(rtc_context* ctx, rtc_trace_counts out[2]);
+int rtc_launch_counts_reset(rtc_context* ctx);
+
+/* Device-side timing on the context stream (CUDA events). */
+int rtc_timer_start(rtc_context* ctx);
+int rtc_timer_stop(rtc_context* ctx, float* milliseconds);     /* synchronises the stream */
+/* Per-kernel-class timing: while enabled every launch of the wavefront is bracketed by an event pair. */
+enum { RTC_KERNEL_GENERATE = 0, RTC_KERNEL_EXTEND = 1, RTC_KERNEL_SHADE = 2, RTC_KERNEL_CONNECT = 3,
+       RTC_KERNEL_ACCUMULATE = 4, RTC_KERNEL_OTHER = 5, RTC_NUM_KERNEL_CLASSES = 6 };
+typedef struct {
+  double   ms[RTC_NUM_KERNEL_CLASSES];        /* summed device time per class */
+  uint64_t launches[RTC_NUM_KERNEL_CLASSES];
+} rtc_profile;
+int rtc_profile_enable(rtc_context* ctx, int enable);          /* enabling resets the accumulated profile */
+int rtc_profile_get(rtc_context* ctx, rtc_profile* out);        /* synchronises the stream */
+
 /* Ray queries against a built scene; rays/hits/occluded are device pointers.  occluded: one uint32 per ray. */
 int rtc_trace_closest(rtc_context* ctx, uint64_t topObject, uint64_t rays, uint64_t numRays, uint64_t hits);
 int rtc_trace_any(rtc_context* ctx, uint64_t topObject, uint64_t rays, uint64_t numRays, uint64_t occluded);
+/* Same traversal as rtc_trace_closest (anyHit = 0) / rtc_trace_any (anyHit = 1) with work counters; synchronous. */
+int rtc_trace_count(rtc_context* ctx, uint64_t topObject, uint64_t rays, uint64_t numRays, int anyHit, rtc_trace_counts* out);
 /* Primary rays of one iteration, one rtc_ray per launch index (skipped indices get tmax = -1). */
 int rtc_generate_primary(rtc_context* ctx, const rt_SystemData* sys, uint32_t launchWidth, uint32_t launchHeight,
                          int iteration, uint64_t rays);

@@ -1,0 +1,232 @@
+"""ctypes binding of the scalar CPU oracle (oracle/rt_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this module;
+nothing under tweeker_raytracer_b200/ does.  See oracle/rt_oracle.h for what each function restates.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+_LIB = os.path.join(_HERE, "_build", "liborc.so")
+
+
+def build(force=False):
+    """Compiles the oracle with gcc (seconds)."""
+    src = os.path.join(_HERE, "rt_oracle.c")
+    deps = [src, os.path.join(_HERE, "rt_oracle.h"), os.path.join(_ROOT, "include", "rtigo3_abi.h"),
+            os.path.join(_ROOT, "include", "rt_portable_math.h")]
+    if not force and os.path.exists(_LIB) and all(os.path.getmtime(_LIB) >= os.path.getmtime(d) for d in deps):
+        return _LIB
+    os.makedirs(os.path.dirname(_LIB), exist_ok=True)
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-mfma", "-fPIC", "-shared", "-I" + os.path.join(_ROOT, "include"),
+                           "-I" + _HERE, "-o", _LIB, src, "-lm", "-lpthread"])
+    return _LIB
+
+
+class Float3(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
+
+
+class Int2(C.Structure):
+    _fields_ = [("x", C.c_int), ("y", C.c_int)]
+
+
+class SystemData(C.Structure):
+    """rt_SystemData (include/rtigo3_abi.h), 192 bytes."""
+    _fields_ = [("rect", C.c_int * 4), ("topObject", C.c_uint64), ("outputBuffer", C.c_uint64), ("tileBuffer", C.c_uint64),
+                ("texelBuffer", C.c_uint64), ("cameraDefinitions", C.c_uint64), ("lightDefinitions", C.c_uint64),
+                ("materialDefinitions", C.c_uint64), ("envTexture", C.c_uint64), ("envCDF_U", C.c_uint64), ("envCDF_V", C.c_uint64),
+                ("resolution", Int2), ("tileSize", Int2), ("tileShift", Int2), ("pathLengths", Int2),
+                ("deviceCount", C.c_int), ("deviceIndex", C.c_int), ("distribution", C.c_int), ("iterationIndex", C.c_int),
+                ("samplesSqrt", C.c_int), ("sceneEpsilon", C.c_float), ("clockScale", C.c_float), ("lensShader", C.c_int),
+                ("numCameras", C.c_int), ("numMaterials", C.c_int), ("numLights", C.c_int), ("envWidth", C.c_uint),
+                ("envHeight", C.c_uint), ("envIntegral", C.c_float), ("envRotation", C.c_float), ("_pad", C.c_int)]
+
+
+assert C.sizeof(SystemData) == 192
+
+
+class CompositorData(C.Structure):
+    _fields_ = [("outputBuffer", C.c_uint64), ("tileBuffer", C.c_uint64), ("resolution", Int2), ("tileSize", Int2),
+                ("tileShift", Int2), ("launchWidth", C.c_int), ("deviceCount", C.c_int), ("deviceIndex", C.c_int), ("_pad", C.c_int)]
+
+
+assert C.sizeof(CompositorData) == 56
+
+
+class TonemapperParams(C.Structure):
+    _fields_ = [("gamma", C.c_float), ("colorBalance", C.c_float * 3), ("whitePoint", C.c_float), ("burnHighlights", C.c_float),
+                ("crushBlacks", C.c_float), ("saturation", C.c_float), ("brightness", C.c_float)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("radianceRays", C.c_uint64), ("shadowRays", C.c_uint64), ("pathSamples", C.c_uint64),
+                ("nodesVisited", C.c_uint64), ("trisTested", C.c_uint64), ("instancesEntered", C.c_uint64)]
+
+
+RAY_DTYPE = np.dtype([("ox", "f4"), ("oy", "f4"), ("oz", "f4"), ("tmin", "f4"), ("dx", "f4"), ("dy", "f4"), ("dz", "f4"), ("tmax", "f4")])
+HIT_DTYPE = np.dtype([("t", "f4"), ("u", "f4"), ("v", "f4"), ("inst", "u4"), ("prim", "u4")])
+ATTR_DTYPE = np.dtype([("vertex", "f4", 3), ("tangent", "f4", 3), ("normal", "f4", 3), ("texcoord", "f4", 3)])
+MATERIAL_DTYPE = np.dtype([("textureAlbedo", "u8"), ("textureCutout", "u8"), ("roughness", "f4", 2), ("indexBSDF", "i4"),
+                           ("albedo", "f4", 3), ("absorption", "f4", 3), ("ior", "f4"), ("flags", "u4"), ("pad0", "i4")])
+LIGHT_DTYPE = np.dtype([("type", "i4"), ("position", "f4", 3), ("vecU", "f4", 3), ("vecV", "f4", 3), ("normal", "f4", 3),
+                        ("area", "f4"), ("emission", "f4", 3), ("unused", "f4", 3)])
+CAMERA_DTYPE = np.dtype([("P", "f4", 3), ("U", "f4", 3), ("V", "f4", 3), ("W", "f4", 3)])
+assert ATTR_DTYPE.itemsize == 48 and MATERIAL_DTYPE.itemsize == 64 and LIGHT_DTYPE.itemsize == 80 and CAMERA_DTYPE.itemsize == 48
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB)
+        L.orc_scene_create.restype = C.c_void_p
+        L.orc_scene_destroy.argtypes = [C.c_void_p]
+        L.orc_scene_add_geometry.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        L.orc_scene_add_instance.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orc_scene_set_materials.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_scene_set_lights.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_scene_set_camera.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_scene_set_env.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float]
+        L.orc_scene_commit.argtypes = [C.c_void_p]
+        L.orc_scene_get_inverse.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_trace_any.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_generate_primary.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+        L.orc_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_path_radiance.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_composite.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_tonemap.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.orc_tea4.argtypes = [C.c_uint32, C.c_uint32]
+        L.orc_tea4.restype = C.c_uint32
+        L.orc_rng.argtypes = [C.POINTER(C.c_uint32)]
+        L.orc_rng.restype = C.c_float
+        L.orc_online_cores.restype = C.c_int
+        L.orc_uses_libm.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Scene:
+    """One oracle scene: geometries, instances, materials, lights, camera, optional environment."""
+
+    def __init__(self):
+        self.L = lib()
+        self.h = C.c_void_p(self.L.orc_scene_create())
+        self.num_instances = 0
+
+    def close(self):
+        if self.h:
+            self.L.orc_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_geometry(self, attrs, indices):
+        attrs = np.ascontiguousarray(attrs, dtype=ATTR_DTYPE)
+        indices = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+        return self.L.orc_scene_add_geometry(self.h, _ptr(attrs), len(attrs), _ptr(indices), len(indices) // 3)
+
+    def add_instance(self, transform, geometry, material, light=-1):
+        t = np.ascontiguousarray(transform, dtype=np.float32).reshape(12)
+        self.num_instances += 1
+        return self.L.orc_scene_add_instance(self.h, _ptr(t), int(geometry), int(material), int(light))
+
+    def set_materials(self, materials):
+        m = np.ascontiguousarray(materials, dtype=MATERIAL_DTYPE)
+        self.L.orc_scene_set_materials(self.h, _ptr(m), len(m))
+
+    def set_lights(self, lights):
+        l = np.ascontiguousarray(lights, dtype=LIGHT_DTYPE)
+        self.L.orc_scene_set_lights(self.h, _ptr(l), len(l))
+
+    def set_camera(self, camera):
+        c = np.ascontiguousarray(camera, dtype=CAMERA_DTYPE).reshape(1)
+        self.L.orc_scene_set_camera(self.h, _ptr(c))
+
+    def set_env(self, rgba, cdf_u, cdf_v, integral):
+        rgba = np.ascontiguousarray(rgba, dtype=np.float32)
+        h, w = rgba.shape[0], rgba.shape[1]
+        cu = np.ascontiguousarray(cdf_u, dtype=np.float32)
+        cv = np.ascontiguousarray(cdf_v, dtype=np.float32)
+        self.L.orc_scene_set_env(self.h, _ptr(rgba), w, h, _ptr(cu), _ptr(cv), C.c_float(integral))
+
+    def commit(self):
+        self.L.orc_scene_commit(self.h)
+
+    def inverse(self, instance):
+        out = np.zeros(12, dtype=np.float32)
+        self.L.orc_scene_get_inverse(self.h, int(instance), _ptr(out))
+        return out
+
+    def trace_closest(self, rays, brute_force=False, stats=None):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.zeros(len(rays), dtype=HIT_DTYPE)
+        self.L.orc_trace_closest(self.h, _ptr(rays), len(rays), 1 if brute_force else 0, _ptr(hits), C.byref(stats) if stats is not None else None)
+        return hits
+
+    def trace_any(self, rays, brute_force=False, stats=None):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        occ = np.zeros(len(rays), dtype=np.uint8)
+        self.L.orc_trace_any(self.h, _ptr(rays), len(rays), 1 if brute_force else 0, _ptr(occ), C.byref(stats) if stats is not None else None)
+        return occ
+
+    def generate_primary(self, sys, launch_width, launch_height, iteration):
+        rays = np.zeros(launch_width * launch_height, dtype=RAY_DTYPE)
+        self.L.orc_generate_primary(self.h, C.byref(sys), launch_width, launch_height, iteration, _ptr(rays))
+        return rays
+
+    def render(self, sys, miss, launch_width, launch_height, local_copy=False, iter_first=0, iter_count=1, row_step=1, row_offset=0,
+               threads=0, buffer=None, stats=None):
+        if buffer is None:
+            n = launch_width * launch_height if local_copy else sys.resolution.x * sys.resolution.y
+            buffer = np.zeros((n, 4), dtype=np.float32)
+        self.L.orc_render(self.h, C.byref(sys), miss, launch_width, launch_height, 1 if local_copy else 0, iter_first, iter_count,
+                          row_step, row_offset, threads, _ptr(buffer), C.byref(stats) if stats is not None else None)
+        return buffer
+
+    def path_radiance(self, sys, miss, launch_width, launch_xy, iteration, stats=None):
+        xy = np.ascontiguousarray(launch_xy, dtype=np.uint32).reshape(-1, 2)
+        out = np.zeros((len(xy), 3), dtype=np.float32)
+        self.L.orc_path_radiance(self.h, C.byref(sys), miss, launch_width, _ptr(xy), len(xy), iteration, _ptr(out),
+                                 C.byref(stats) if stats is not None else None)
+        return out
+
+
+def tea4(v0, v1):
+    return lib().orc_tea4(v0 & 0xffffffff, v1 & 0xffffffff)
+
+
+def rng_sequence(seed, n):
+    s = C.c_uint32(seed)
+    return [lib().orc_rng(C.byref(s)) for _ in range(n)], s.value
+
+
+def composite(args, tile, out):
+    lib().orc_composite(C.byref(args), _ptr(tile), _ptr(out))
+
+
+def tonemap(params, rgba):
+    rgba = np.ascontiguousarray(rgba, dtype=np.float32).reshape(-1, 4)
+    out = np.zeros((len(rgba), 3), dtype=np.uint8)
+    lib().orc_tonemap(C.byref(params), _ptr(rgba), _ptr(out), len(rgba))
+    return out
+
+
+def online_cores():
+    return lib().orc_online_cores()

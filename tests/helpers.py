@@ -1,0 +1,105 @@
+"""Shared helpers of the test-suite: scene files in temp dirs, App -> oracle scene conversion, ray sets."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import orc  # noqa: E402  (test infrastructure)
+
+SCENES = os.path.join(ROOT, "scenes")
+
+
+def system_text(name, **overrides):
+    """Reads scenes/system_<name>.txt and replaces/appends `keyword value` lines."""
+    with open(os.path.join(SCENES, "system_%s.txt" % name)) as f:
+        lines = f.read().splitlines()
+    out = []
+    seen = set()
+    for line in lines:
+        key = line.split()[0] if line.split() else ""
+        if key in overrides:
+            out.append("%s %s" % (key, overrides[key]))
+            seen.add(key)
+        else:
+            out.append(line)
+    for k, v in overrides.items():
+        if k not in seen:
+            out.append("%s %s" % (k, v))
+    return "\n".join(out) + "\n"
+
+
+def write_system(tmpdir, name, **overrides):
+    path = os.path.join(str(tmpdir), "system_%s.txt" % name)
+    with open(path, "w") as f:
+        f.write(system_text(name, **overrides))
+    return path
+
+
+def scene_path(name):
+    return os.path.join(SCENES, "scene_%s.txt" % name)
+
+
+def oracle_scene(app):
+    """Feeds the scene an App loaded (geometries, flattened instances, materials, lights, camera, environment) to the oracle."""
+    s = orc.Scene()
+    for g in range(app.info.numGeometries):
+        attrs, idx = app.geometry(g)
+        s.add_geometry(attrs, idx)
+    for i in range(app.info.numInstances):
+        t, g, m, l = app.instance(i)
+        s.add_instance(t, g, m, l)
+    s.set_materials(app.materials())
+    s.set_lights(app.lights())
+    s.set_camera(app.camera())
+    env = app.environment()
+    if env is not None:
+        s.set_env(env[0], env[1], env[2], env[3])
+    s.commit()
+    return s
+
+
+def oracle_sys(app, device_index=0):
+    """SystemData in the oracle's ctypes type, copied field by field from the host's."""
+    src = app.system_data(device_index)
+    dst = orc.SystemData()
+    for name, _ in orc.SystemData._fields_:
+        v = getattr(src, name)
+        if name in ("resolution", "tileSize", "tileShift", "pathLengths"):
+            getattr(dst, name).x, getattr(dst, name).y = v.x, v.y
+        elif name == "rect":
+            for k in range(4):
+                dst.rect[k] = v[k]
+        else:
+            setattr(dst, name, v)
+    return dst
+
+
+def random_rays(n, seed, lo=(-1.2, -0.2, -1.2), hi=(1.2, 2.2, 1.2), tmin=5e-5, tmax=1e27):
+    """Incoherent rays: origins uniform in a box, directions uniform on the sphere."""
+    rng = np.random.default_rng(seed)
+    rays = np.zeros(n, dtype=orc.RAY_DTYPE)
+    o = rng.uniform(lo, hi, size=(n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["ox"], rays["oy"], rays["oz"] = o[:, 0], o[:, 1], o[:, 2]
+    rays["dx"], rays["dy"], rays["dz"] = d[:, 0], d[:, 1], d[:, 2]
+    rays["tmin"] = tmin
+    rays["tmax"] = tmax
+    return rays
+
+
+def hits_equal(a, b):
+    """Bit-exact comparison of two hit arrays (t, u, v as raw bits; instance and primitive ids)."""
+    return (np.array_equal(a["inst"], b["inst"]) and np.array_equal(a["prim"], b["prim"])
+            and np.array_equal(a["t"].view(np.uint32), b["t"].view(np.uint32))
+            and np.array_equal(a["u"].view(np.uint32), b["u"].view(np.uint32))
+            and np.array_equal(a["v"].view(np.uint32), b["v"].view(np.uint32)))
+
+
+def psnr(a, b, peak=1.0):
+    mse = float(np.mean((np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)) ** 2))
+    return 99.0 if mse == 0 else 10.0 * np.log10(peak * peak / mse)

@@ -24,6 +24,7 @@ struct WfArgs
   uint32_t launchWidth, launchHeight;
   int raygen, miss;
   int iterFirst, iterCount;
+  int accumFirst;          // sample number of the batch's first iteration in the running average
   uint32_t numPaths;
 };
 
@@ -313,7 +314,7 @@ k_accumulate(const __grid_constant__ WfArgs a)
     const float4 L = a.wf.radiance[(size_t)b * pixelsPerIter + idx];
     float3 r = f3(L.x, L.y, L.z);
     if (isnan(r.x) || isnan(r.y) || isnan(r.z)) continue;
-    const int it = a.iterFirst + b;
+    const int it = a.accumFirst + b;
     if (0 < it)
     {
       const float t = 1.0f / (float)(it + 1);
@@ -451,7 +452,8 @@ __global__ void k_stats(const uint32_t* __restrict__ counters, int maxDepth, uin
 
 } // namespace
 
-int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uint32_t h, int raygen, int miss, int iterFirst, int iterCount)
+int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uint32_t h, int raygen, int miss, int iterFirst, int iterCount,
+                     int accumFirst, bool countWork)
 {
   if (sys.topObject == 0) RTC_FAIL("SystemData.topObject is null (call rtc_ias_build first)");
   const SceneRecord* scene = nullptr;
@@ -472,21 +474,27 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
     const int batch = (iterCount - done < (int)perBatch) ? iterCount - done : (int)perBatch;
     WfArgs a;
     a.wf = ctx->wf; a.sys = sys; a.launchWidth = w; a.launchHeight = h; a.raygen = raygen; a.miss = miss;
-    a.iterFirst = iterFirst + done; a.iterCount = batch; a.numPaths = (uint32_t)(pixels * (uint64_t)batch);
+    a.iterFirst = iterFirst + done; a.iterCount = batch; a.accumFirst = accumFirst + done; a.numPaths = (uint32_t)(pixels * (uint64_t)batch);
     uint32_t* cnt = ctx->wf.counters;
     RTC_CUDA(cudaMemsetAsync(cnt, 0, 4 * 256, ctx->stream));
+    if (int rc = profile_begin(ctx, RTC_KERNEL_GENERATE)) return rc;
     k_generate<<<gridShade, kBlock, 0, ctx->stream>>>(a, ctx->wf.queueA, cnt + 0);
     ctx->kernelLaunches++;
+    if (int rc = profile_end(ctx)) return rc;
     uint32_t* qIn = ctx->wf.queueA; uint32_t* qOut = ctx->wf.queueB;
     for (int d = 0; d < maxDepth; ++d)
     {
-      if (int rc = launch_extend(ctx, &scene->desc, ctx->wf, qIn, cnt + d)) return rc;
+      if (int rc = launch_extend(ctx, &scene->desc, ctx->wf, qIn, cnt + d, countWork)) return rc;
+      if (int rc = profile_begin(ctx, RTC_KERNEL_SHADE)) return rc;
       k_shade<<<gridShade, kBlock, 0, ctx->stream>>>(a, scene->desc, qIn, cnt + d, qOut, cnt + d + 1, ctx->wf.shadowQueue, cnt + 64 + d);
       ctx->kernelLaunches++;
-      if (sys.numLights > 0) { if (int rc = launch_connect(ctx, &scene->desc, ctx->wf, cnt + 64 + d)) return rc; }
+      if (int rc = profile_end(ctx)) return rc;
+      if (sys.numLights > 0) { if (int rc = launch_connect(ctx, &scene->desc, ctx->wf, cnt + 64 + d, countWork)) return rc; }
       uint32_t* t = qIn; qIn = qOut; qOut = t;
     }
+    if (int rc = profile_begin(ctx, RTC_KERNEL_ACCUMULATE)) return rc;
     k_accumulate<<<(unsigned)((pixels + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(a);
+    if (int rc = profile_end(ctx)) return rc;
     k_stats<<<1, 32, 0, ctx->stream>>>(cnt, maxDepth, a.numPaths, ctx->d_stats);
     ctx->kernelLaunches += 2;
     RTC_CUDA(cudaGetLastError());

@@ -1,0 +1,659 @@
+// rtc_api.cpp -- the C ABI of librtcore (include/rtc_core.h): contexts, memory, acceleration-structure
+// builds, launches.  This file replaces the OptiX host calls of apps/rtigo3/src/Device.cpp (see the table
+// at the top of rtc_core.h); there is no CPU rendering path here: every entry point that produces
+// rays, hits or pixels ends in a kernel launch on the context's stream.
+#include "rtc_internal.h"
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <set>
+
+namespace {
+
+thread_local std::string g_lastError;
+
+double now_ms()
+{
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// World->object matrix of an instance.  DEFINED here (OptiX computed it inside optixAccelBuild,
+// Device.cpp:1478, read back by closesthit.cu:49-52): adjugate / determinant of the upper 3x3 in double,
+// rounded once to float; translation -(Minv * t) in double.  The oracle states the same definition.
+void invert_3x4(const float m[12], float out[12])
+{
+  const double a = m[0], b = m[1], c = m[2],  tx = m[3];
+  const double d = m[4], e = m[5], f = m[6],  ty = m[7];
+  const double g = m[8], h = m[9], i = m[10], tz = m[11];
+  const double c00 = e * i - f * h, c01 = c * h - b * i, c02 = b * f - c * e;
+  const double c10 = f * g - d * i, c11 = a * i - c * g, c12 = c * d - a * f;
+  const double c20 = d * h - e * g, c21 = b * g - a * h, c22 = a * e - b * d;
+  const double det = a * c00 + b * c10 + c * c20;
+  const double r = 1.0 / det;
+  const double i00 = c00 * r, i01 = c01 * r, i02 = c02 * r;
+  const double i10 = c10 * r, i11 = c11 * r, i12 = c12 * r;
+  const double i20 = c20 * r, i21 = c21 * r, i22 = c22 * r;
+  out[0] = (float)i00; out[1] = (float)i01; out[2]  = (float)i02; out[3]  = (float)(-(i00 * tx + i01 * ty + i02 * tz));
+  out[4] = (float)i10; out[5] = (float)i11; out[6]  = (float)i12; out[7]  = (float)(-(i10 * tx + i11 * ty + i12 * tz));
+  out[8] = (float)i20; out[9] = (float)i21; out[10] = (float)i22; out[11] = (float)(-(i20 * tx + i21 * ty + i22 * tz));
+}
+
+SceneRecord* find_scene(rtc_context* ctx, uint64_t topObject)
+{
+  for (SceneRecord* s : ctx->scenes) if ((uint64_t)(uintptr_t)s->d_desc == topObject) return s;
+  return nullptr;
+}
+
+void free_scene(SceneRecord* s)
+{
+  cudaFree(s->d_desc); cudaFree(s->d_tlasNodes); cudaFree(s->d_instances); cudaFree(s->d_tlasLeaves); cudaFree(s->d_o2w); cudaFree(s->d_geomInst);
+  delete s;
+}
+
+} // namespace
+
+int rtc_set_error(const char* file, int line, const char* call, int code, const char* text)
+{
+  char buf[1024];
+  std::snprintf(buf, sizeof(buf), "ERROR: %s(%d): %s (%d) %s", file, line, call, code, text ? text : "");
+  g_lastError = buf;
+  return code ? code : -1;
+}
+
+static int take_event(rtc_context* ctx, cudaEvent_t* e)
+{
+  if (!ctx->eventPool.empty()) { *e = ctx->eventPool.back(); ctx->eventPool.pop_back(); return 0; }
+  RTC_CUDA(cudaEventCreate(e));
+  return 0;
+}
+
+int profile_begin(rtc_context* ctx, int cls)
+{
+  if (!ctx->profiling) return 0;
+  // bound the number of pending events: resolve (synchronise) every 4096 launches
+  if (ctx->spans.size() >= 4096)
+  {
+    RTC_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (rtc_context::ProfileSpan& sp : ctx->spans)
+    {
+      float ms = 0.0f;
+      RTC_CUDA(cudaEventElapsedTime(&ms, sp.a, sp.b));
+      ctx->profile.ms[sp.cls] += ms; ctx->profile.launches[sp.cls] += 1;
+      ctx->eventPool.push_back(sp.a); ctx->eventPool.push_back(sp.b);
+    }
+    ctx->spans.clear();
+  }
+  rtc_context::ProfileSpan sp; sp.cls = cls;
+  if (int rc = take_event(ctx, &sp.a)) return rc;
+  if (int rc = take_event(ctx, &sp.b)) return rc;
+  RTC_CUDA(cudaEventRecord(sp.a, ctx->stream));
+  ctx->spans.push_back(sp);
+  return 0;
+}
+
+int profile_end(rtc_context* ctx)
+{
+  if (!ctx->profiling) return 0;
+  RTC_CUDA(cudaEventRecord(ctx->spans.back().b, ctx->stream));
+  return 0;
+}
+
+extern "C" {
+
+int rtc_version(void) { return 100; }
+
+const char* rtc_last_error(void) { return g_lastError.c_str(); }
+
+int rtc_context_create(int deviceOrdinal, rtc_context** out)
+{
+  if (!out) RTC_FAIL("out is null");
+  *out = nullptr;
+  int count = 0;
+  RTC_CUDA(cudaGetDeviceCount(&count));
+  if (deviceOrdinal < 0 || deviceOrdinal >= count) RTC_FAIL("device ordinal out of range (no CUDA device, no rendering: this core has no CPU path)");
+  RTC_CUDA(cudaSetDevice(deviceOrdinal));
+  rtc_context* ctx = new rtc_context();
+  ctx->device = deviceOrdinal;
+  cudaDeviceProp prop;
+  RTC_CUDA(cudaGetDeviceProperties(&prop, deviceOrdinal));
+  ctx->numSMs = prop.multiProcessorCount;
+  RTC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  RTC_CUDA(cudaEventCreate(&ctx->evA));
+  RTC_CUDA(cudaEventCreate(&ctx->evB));
+  RTC_CUDA(cudaEventCreate(&ctx->evTimerA));
+  RTC_CUDA(cudaEventCreate(&ctx->evTimerB));
+  RTC_CUDA(cudaMalloc(&ctx->d_stats, 8 * sizeof(uint64_t)));
+  RTC_CUDA(cudaMemset(ctx->d_stats, 0, 8 * sizeof(uint64_t)));
+  RTC_CUDA(cudaMalloc(&ctx->d_launchCounts, 8 * sizeof(unsigned long long)));
+  RTC_CUDA(cudaMemset(ctx->d_launchCounts, 0, 8 * sizeof(unsigned long long)));
+  *out = ctx;
+  return 0;
+}
+
+int rtc_context_destroy(rtc_context* ctx)
+{
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (SceneRecord* s : ctx->scenes) free_scene(s);
+  for (GasRecord& g : ctx->gas) { cudaFree(g.d_nodes); cudaFree(g.d_tris); }
+  if (ctx->wf.base) cudaFree(ctx->wf.base);
+  cudaFree(ctx->d_stats);
+  cudaFree(ctx->d_launchCounts);
+  for (rtc_context::ProfileSpan& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+  for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
+  cudaEventDestroy(ctx->evA); cudaEventDestroy(ctx->evB);
+  cudaEventDestroy(ctx->evTimerA); cudaEventDestroy(ctx->evTimerB);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return 0;
+}
+
+int rtc_synchronize(rtc_context* ctx)
+{
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  RTC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+uint64_t rtc_context_stream(rtc_context* ctx) { return (uint64_t)(uintptr_t)ctx->stream; }
+
+int rtc_device_count(int* count)
+{
+  if (!count) RTC_FAIL("count is null");
+  *count = 0;
+  RTC_CUDA(cudaGetDeviceCount(count));
+  return 0;
+}
+
+int rtc_device_name(int deviceOrdinal, char* name, int length)
+{
+  if (!name || length <= 0) RTC_FAIL("bad name buffer");
+  cudaDeviceProp prop;
+  RTC_CUDA(cudaGetDeviceProperties(&prop, deviceOrdinal));
+  std::snprintf(name, (size_t)length, "%s", prop.name);
+  return 0;
+}
+
+int rtc_peer_can_access(int deviceOrdinal, int peerOrdinal, int* canAccess)
+{
+  if (!canAccess) RTC_FAIL("canAccess is null");
+  if (deviceOrdinal == peerOrdinal) { *canAccess = 1; return 0; }
+  RTC_CUDA(cudaDeviceCanAccessPeer(canAccess, deviceOrdinal, peerOrdinal));
+  return 0;
+}
+
+int rtc_peer_enable(rtc_context* ctx, rtc_context* peer)
+{
+  if (ctx->device == peer->device) return 0;
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+  RTC_CUDA(e);
+  return 0;
+}
+
+int rtc_peer_disable(rtc_context* ctx, rtc_context* peer)
+{
+  if (ctx->device == peer->device) return 0;
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  const cudaError_t e = cudaDeviceDisablePeerAccess(peer->device);
+  if (e == cudaErrorPeerAccessNotEnabled) { cudaGetLastError(); return 0; }
+  RTC_CUDA(e);
+  return 0;
+}
+
+int rtc_memcpy_peer(rtc_context* dstCtx, uint64_t dst, rtc_context* srcCtx, uint64_t src, uint64_t bytes)
+{
+  RTC_CUDA(cudaSetDevice(srcCtx->device));
+  RTC_CUDA(cudaStreamSynchronize(srcCtx->stream));
+  RTC_CUDA(cudaSetDevice(dstCtx->device));
+  if (bytes == 0) return 0;
+  if (dstCtx->device == srcCtx->device)
+    RTC_CUDA(cudaMemcpyAsync((void*)(uintptr_t)dst, (const void*)(uintptr_t)src, bytes, cudaMemcpyDeviceToDevice, dstCtx->stream));
+  else
+    RTC_CUDA(cudaMemcpyPeerAsync((void*)(uintptr_t)dst, dstCtx->device, (const void*)(uintptr_t)src, srcCtx->device, bytes, dstCtx->stream));
+  return 0;
+}
+
+int rtc_malloc(rtc_context* ctx, uint64_t bytes, uint64_t* dptr)
+{
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  void* p = nullptr;
+  RTC_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
+  *dptr = (uint64_t)(uintptr_t)p;
+  return 0;
+}
+
+int rtc_free(rtc_context* ctx, uint64_t dptr)
+{
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  RTC_CUDA(cudaStreamSynchronize(ctx->stream));
+  RTC_CUDA(cudaFree((void*)(uintptr_t)dptr));
+  return 0;
+}
+
+int rtc_upload(rtc_context* ctx, uint64_t dst, const void* src, uint64_t bytes)
+{
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  if (bytes) RTC_CUDA(cudaMemcpyAsync((void*)(uintptr_t)dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+int rtc_download(rtc_context* ctx, void* dst, uint64_t src, uint64_t bytes)
+{
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  if (bytes) RTC_CUDA(cudaMemcpyAsync(dst, (const void*)(uintptr_t)src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+
+int rtc_memset(rtc_context* ctx, uint64_t dst, int value, uint64_t bytes)
+{
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  if (bytes) RTC_CUDA(cudaMemsetAsync((void*)(uintptr_t)dst, value, bytes, ctx->stream));
+  return 0;
+}
+
+int rtc_host_alloc(rtc_context* ctx, uint64_t bytes, void** ptr)
+{
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  RTC_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped));
+  return 0;
+}
+
+int rtc_host_free(rtc_context* ctx, void* ptr)
+{
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  RTC_CUDA(cudaFreeHost(ptr));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Geometry acceleration structure (replaces optixAccelBuild over OPTIX_BUILD_INPUT_TYPE_TRIANGLES,
+// Device.cpp:1362-1405: vertex stride sizeof(TriangleAttributes), uint3 indices, flags NONE).
+// ------------------------------------------------------------------------------------------------
+int rtc_gas_build(rtc_context* ctx, uint64_t attributes, uint32_t strideBytes, uint32_t numVerts,
+                  uint64_t indices, uint32_t numTris, uint32_t buildFlags, uint32_t* gas)
+{
+  if (!gas) RTC_FAIL("gas is null");
+  if (strideBytes < 12 || (strideBytes & 3u)) RTC_FAIL("vertex stride must be a multiple of 4 and at least 12");
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  const double t0 = now_ms();
+  GasRecord rec;
+  rec.attributes = attributes; rec.indices = indices; rec.strideBytes = strideBytes; rec.numVerts = numVerts; rec.numTris = numTris;
+
+  int builder = (int)buildFlags;
+  if (builder == RTC_BUILD_DEFAULT) builder = (numTris > kGpuBuildThreshold) ? RTC_BUILD_GPU_LBVH : RTC_BUILD_HOST_SAH;
+  rec.builder = builder;
+
+  if (builder == RTC_BUILD_GPU_LBVH && numTris > 0)
+  {
+    if (int rc = build_gas_gpu(ctx, rec)) return rc;
+  }
+  else
+  {
+    // host quality build: fetch positions and indices, bin-SAH, collapse, quantise, upload
+    std::vector<uint8_t> verts((size_t)numVerts * strideBytes);
+    std::vector<uint32_t> idx((size_t)numTris * 3u);
+    RTC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!verts.empty()) RTC_CUDA(cudaMemcpy(verts.data(), (const void*)(uintptr_t)attributes, verts.size(), cudaMemcpyDeviceToHost));
+    if (!idx.empty()) RTC_CUDA(cudaMemcpy(idx.data(), (const void*)(uintptr_t)indices, idx.size() * 4u, cudaMemcpyDeviceToHost));
+    std::vector<PrimBox> boxes(numTris);
+    auto vertex = [&](uint32_t i) { return reinterpret_cast<const float*>(verts.data() + (size_t)i * strideBytes); };
+    for (uint32_t t = 0; t < numTris; ++t)
+    {
+      PrimBox& b = boxes[t];
+      for (int k = 0; k < 3; ++k) { b.lo[k] = std::numeric_limits<float>::infinity(); b.hi[k] = -b.lo[k]; }
+      for (int c = 0; c < 3; ++c)
+      {
+        const uint32_t vi = idx[3u * t + c];
+        if (vi >= numVerts) RTC_FAIL("triangle index out of range");
+        const float* p = vertex(vi);
+        for (int k = 0; k < 3; ++k) { b.lo[k] = std::fmin(b.lo[k], p[k]); b.hi[k] = std::fmax(b.hi[k], p[k]); }
+      }
+    }
+    WideBvh bvh;
+    build_wide_bvh_host(boxes.data(), numTris, bvh);
+    std::vector<float4> tris((size_t)numTris * 3u);
+    for (uint32_t s = 0; s < numTris; ++s)
+    {
+      const uint32_t prim = bvh.primOrder[s];
+      for (int c = 0; c < 3; ++c)
+      {
+        const float* p = vertex(idx[3u * prim + c]);
+        float w = 0.0f;
+        if (c == 0) std::memcpy(&w, &prim, 4);
+        tris[3u * (size_t)s + c] = make_float4(p[0], p[1], p[2], w);
+      }
+    }
+    rec.numNodes = (uint32_t)bvh.nodes.size();
+    for (int k = 0; k < 3; ++k) { rec.lo[k] = bvh.lo[k]; rec.hi[k] = bvh.hi[k]; }
+    RTC_CUDA(cudaMalloc(&rec.d_nodes, bvh.nodes.size() * sizeof(Node8)));
+    RTC_CUDA(cudaMemcpy(rec.d_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(Node8), cudaMemcpyHostToDevice));
+    RTC_CUDA(cudaMalloc(&rec.d_tris, tris.empty() ? 16 : tris.size() * sizeof(float4)));
+    if (!tris.empty()) RTC_CUDA(cudaMemcpy(rec.d_tris, tris.data(), tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  }
+  rec.buildMs = now_ms() - t0;
+  ctx->gas.push_back(rec);
+  *gas = (uint32_t)(ctx->gas.size() - 1);
+  return 0;
+}
+
+int rtc_gas_destroy(rtc_context* ctx, uint32_t gas)
+{
+  if (gas >= ctx->gas.size()) RTC_FAIL("bad gas handle");
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  RTC_CUDA(cudaStreamSynchronize(ctx->stream));
+  GasRecord& g = ctx->gas[gas];
+  cudaFree(g.d_nodes); cudaFree(g.d_tris);
+  g.d_nodes = nullptr; g.d_tris = nullptr; g.numNodes = 0; g.numTris = 0;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Instance level (replaces createInstance + optixAccelBuild INSTANCES + createHitGroupRecords,
+// Device.cpp:1427-1532).  Single-level instancing, as the reference's pipeline (Device.cpp:560).
+// ------------------------------------------------------------------------------------------------
+int rtc_ias_build(rtc_context* ctx, const rtc_instance_desc* instances, uint32_t numInstances, uint64_t* topObject)
+{
+  if (!topObject) RTC_FAIL("topObject is null");
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  const double t0 = now_ms();
+  std::vector<PrimBox> boxes(numInstances);
+  std::vector<float4> inst((size_t)numInstances * 4u), o2w((size_t)numInstances * 3u);
+  std::vector<rt_GeometryInstanceData> gi(numInstances);
+  SceneRecord* rec = new SceneRecord();
+  rec->inverses.resize((size_t)numInstances * 12u);
+  std::set<uint32_t> distinct;
+  for (uint32_t i = 0; i < numInstances; ++i)
+  {
+    const rtc_instance_desc& d = instances[i];
+    if (d.instanceId != i) { delete rec; RTC_FAIL("instanceId must equal the array position"); }
+    if (d.gas >= ctx->gas.size() || ctx->gas[d.gas].d_nodes == nullptr) { delete rec; RTC_FAIL("bad gas handle in instance"); }
+    const GasRecord& g = ctx->gas[d.gas];
+    distinct.insert(d.gas);
+    float* inv = &rec->inverses[(size_t)i * 12u];
+    invert_3x4(d.transform, inv);
+    for (int r = 0; r < 3; ++r)
+    {
+      inst[4u * i + r] = make_float4(inv[4 * r], inv[4 * r + 1], inv[4 * r + 2], inv[4 * r + 3]);
+      o2w[3u * i + r] = make_float4(d.transform[4 * r], d.transform[4 * r + 1], d.transform[4 * r + 2], d.transform[4 * r + 3]);
+    }
+    const uint64_t np = (uint64_t)(uintptr_t)g.d_nodes, tp = (uint64_t)(uintptr_t)g.d_tris;
+    const uint32_t w[4] = { (uint32_t)np, (uint32_t)(np >> 32), (uint32_t)tp, (uint32_t)(tp >> 32) };
+    std::memcpy(&inst[4u * i + 3], w, 16);
+    gi[i].attributes = g.attributes; gi[i].indices = g.indices; gi[i].materialIndex = d.materialIndex; gi[i].lightIndex = d.lightIndex;
+
+    // world bounds of the transformed GAS box, padded: the object-space ray is a ROUNDED transform of the
+    // world ray, so a hit found in object space may lie a few ulps outside the exact world-space box
+    PrimBox& b = boxes[i];
+    for (int k = 0; k < 3; ++k) { b.lo[k] = std::numeric_limits<float>::infinity(); b.hi[k] = -b.lo[k]; }
+    const double ext = std::fabs((double)g.hi[0] - g.lo[0]) + std::fabs((double)g.hi[1] - g.lo[1]) + std::fabs((double)g.hi[2] - g.lo[2]);
+    for (int corner = 0; corner < 8; ++corner)
+    {
+      const double x = (corner & 1) ? g.hi[0] : g.lo[0], y = (corner & 2) ? g.hi[1] : g.lo[1], z = (corner & 4) ? g.hi[2] : g.lo[2];
+      for (int r = 0; r < 3; ++r)
+      {
+        const float* m = &d.transform[4 * r];
+        const double wv = m[0] * x + m[1] * y + m[2] * z + m[3];
+        const double scale = std::fabs((double)m[0]) + std::fabs((double)m[1]) + std::fabs((double)m[2]);
+        const double pad = (std::fabs(wv) + ext * scale) * 1.0e-5;
+        const float lo = std::nextafterf((float)(wv - pad), -std::numeric_limits<float>::infinity());
+        const float hi = std::nextafterf((float)(wv + pad), std::numeric_limits<float>::infinity());
+        b.lo[r] = std::fmin(b.lo[r], lo); b.hi[r] = std::fmax(b.hi[r], hi);
+      }
+    }
+    if (g.numTris == 0) { for (int k = 0; k < 3; ++k) { b.lo[k] = 0.0f; b.hi[k] = 0.0f; } }
+  }
+  WideBvh bvh;
+  build_wide_bvh_host(boxes.data(), numInstances, bvh);
+
+  auto upload = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t e = cudaMalloc(dst, bytes ? bytes : 16);
+    if (e != cudaSuccess) return e;
+    return bytes ? cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
+  };
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = upload(&rec->d_tlasNodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(Node8));
+  if (e == cudaSuccess) e = upload(&rec->d_tlasLeaves, bvh.primOrder.data(), bvh.primOrder.size() * 4u);
+  if (e == cudaSuccess) e = upload(&rec->d_instances, inst.data(), inst.size() * sizeof(float4));
+  if (e == cudaSuccess) e = upload(&rec->d_o2w, o2w.data(), o2w.size() * sizeof(float4));
+  if (e == cudaSuccess) e = upload(&rec->d_geomInst, gi.data(), gi.size() * sizeof(rt_GeometryInstanceData));
+  rec->desc.tlasNodes = (const uint4*)rec->d_tlasNodes;
+  rec->desc.tlasLeaves = (const uint32_t*)rec->d_tlasLeaves;
+  rec->desc.instances = (const float4*)rec->d_instances;
+  rec->desc.objectToWorld = (const float4*)rec->d_o2w;
+  rec->desc.geomInst = (const rt_GeometryInstanceData*)rec->d_geomInst;
+  rec->desc.numInstances = numInstances;
+  rec->desc.numTlasNodes = (uint32_t)bvh.nodes.size();
+  rec->desc.numTlasLeaves = (uint32_t)bvh.primOrder.size();
+  if (e == cudaSuccess) e = upload((void**)&rec->d_desc, &rec->desc, sizeof(SceneDesc));
+  if (e != cudaSuccess) { free_scene(rec); return rtc_set_error(__FILE__, __LINE__, "rtc_ias_build upload", (int)e, cudaGetErrorString(e)); }
+  rec->totalNodes = bvh.nodes.size(); rec->totalTris = 0; rec->gasBuildMs = 0.0; rec->numGas = (uint32_t)distinct.size();
+  for (uint32_t g : distinct) { rec->totalNodes += ctx->gas[g].numNodes; rec->totalTris += ctx->gas[g].numTris; rec->gasBuildMs += ctx->gas[g].buildMs; }
+  rec->iasBuildMs = now_ms() - t0;
+  ctx->scenes.push_back(rec);
+  *topObject = (uint64_t)(uintptr_t)rec->d_desc;
+  return 0;
+}
+
+int rtc_scene_info_get(rtc_context* ctx, uint64_t topObject, rtc_scene_info* info)
+{
+  SceneRecord* s = find_scene(ctx, topObject);
+  if (!s) RTC_FAIL("unknown topObject");
+  std::memset(info, 0, sizeof(*info));
+  info->numNodes = s->totalNodes; info->numTris = s->totalTris; info->numInstances = s->desc.numInstances;
+  info->numTlasNodes = s->desc.numTlasNodes; info->numGas = s->numGas; info->gasBuildMs = s->gasBuildMs; info->iasBuildMs = s->iasBuildMs;
+  return 0;
+}
+
+int rtc_scene_destroy(rtc_context* ctx, uint64_t topObject)
+{
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  for (size_t i = 0; i < ctx->scenes.size(); ++i)
+    if ((uint64_t)(uintptr_t)ctx->scenes[i]->d_desc == topObject)
+    {
+      RTC_CUDA(cudaStreamSynchronize(ctx->stream));
+      free_scene(ctx->scenes[i]);
+      ctx->scenes.erase(ctx->scenes.begin() + (long)i);
+      return 0;
+    }
+  RTC_FAIL("unknown topObject");
+}
+
+int rtc_instance_inverse(rtc_context* ctx, uint64_t topObject, uint32_t instance, float out[12])
+{
+  SceneRecord* s = find_scene(ctx, topObject);
+  if (!s) RTC_FAIL("unknown topObject");
+  if (instance >= s->desc.numInstances) RTC_FAIL("instance out of range");
+  std::memcpy(out, &s->inverses[(size_t)instance * 12u], 48);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Launches
+// ------------------------------------------------------------------------------------------------
+int rtc_launch(rtc_context* ctx, const rt_SystemData* sys, uint32_t launchWidth, uint32_t launchHeight,
+               int raygen, int miss, int iterationFirst, int iterationCount)
+{
+  if (!sys) RTC_FAIL("sys is null");
+  if (raygen != RTC_RAYGEN_FULL_FRAME && raygen != RTC_RAYGEN_LOCAL_COPY) RTC_FAIL("bad raygen selector");
+  if (miss < RT_MISS_NULL || miss > RT_MISS_SPHERE) RTC_FAIL("bad miss selector");
+  if (miss == RT_MISS_SPHERE && (sys->envTexture == 0 || sys->envCDF_U == 0 || sys->envCDF_V == 0)) RTC_FAIL("miss 2 needs envTexture/envCDF_U/envCDF_V");
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  return launch_wavefront(ctx, *sys, launchWidth, launchHeight, raygen, miss, iterationFirst, iterationCount, iterationFirst, false);
+}
+
+int rtc_launch_ex(rtc_context* ctx, const rt_SystemData* sys, uint32_t launchWidth, uint32_t launchHeight,
+                  int raygen, int miss, int iterationFirst, int iterationCount, int accumulationFirst, int countWork)
+{
+  if (!sys) RTC_FAIL("sys is null");
+  if (raygen != RTC_RAYGEN_FULL_FRAME && raygen != RTC_RAYGEN_LOCAL_COPY) RTC_FAIL("bad raygen selector");
+  if (miss < RT_MISS_NULL || miss > RT_MISS_SPHERE) RTC_FAIL("bad miss selector");
+  if (miss == RT_MISS_SPHERE && (sys->envTexture == 0 || sys->envCDF_U == 0 || sys->envCDF_V == 0)) RTC_FAIL("miss 2 needs envTexture/envCDF_U/envCDF_V");
+  if (accumulationFirst < 0) RTC_FAIL("accumulationFirst < 0");
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  return launch_wavefront(ctx, *sys, launchWidth, launchHeight, raygen, miss, iterationFirst, iterationCount, accumulationFirst, countWork != 0);
+}
+
+int rtc_launch_counts_get(rtc_context* ctx, rtc_trace_counts out[2])
+{
+  if (!out) RTC_FAIL("out is null");
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  unsigned long long h[8];
+  RTC_CUDA(cudaMemcpyAsync(h, ctx->d_launchCounts, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  RTC_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < 2; ++k) { out[k].nodes = h[4 * k]; out[k].tris = h[4 * k + 1]; out[k].instances = h[4 * k + 2]; out[k].rays = h[4 * k + 3]; }
+  return 0;
+}
+
+int rtc_launch_counts_reset(rtc_context* ctx)
+{
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  RTC_CUDA(cudaMemsetAsync(ctx->d_launchCounts, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  return 0;
+}
+
+int rtc_timer_start(rtc_context* ctx)
+{
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  RTC_CUDA(cudaEventRecord(ctx->evTimerA, ctx->stream));
+  return 0;
+}
+
+int rtc_timer_stop(rtc_context* ctx, float* milliseconds)
+{
+  if (!milliseconds) RTC_FAIL("milliseconds is null");
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  RTC_CUDA(cudaEventRecord(ctx->evTimerB, ctx->stream));
+  RTC_CUDA(cudaEventSynchronize(ctx->evTimerB));
+  RTC_CUDA(cudaEventElapsedTime(milliseconds, ctx->evTimerA, ctx->evTimerB));
+  return 0;
+}
+
+static int profile_resolve(rtc_context* ctx)
+{
+  RTC_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (rtc_context::ProfileSpan& sp : ctx->spans)
+  {
+    float ms = 0.0f;
+    RTC_CUDA(cudaEventElapsedTime(&ms, sp.a, sp.b));
+    ctx->profile.ms[sp.cls] += ms;
+    ctx->profile.launches[sp.cls] += 1;
+    ctx->eventPool.push_back(sp.a); ctx->eventPool.push_back(sp.b);
+  }
+  ctx->spans.clear();
+  return 0;
+}
+
+int rtc_profile_enable(rtc_context* ctx, int enable)
+{
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  if (int rc = profile_resolve(ctx)) return rc;
+  if (enable) std::memset(&ctx->profile, 0, sizeof(ctx->profile));
+  ctx->profiling = enable != 0;
+  return 0;
+}
+
+int rtc_profile_get(rtc_context* ctx, rtc_profile* out)
+{
+  if (!out) RTC_FAIL("out is null");
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  if (int rc = profile_resolve(ctx)) return rc;
+  *out = ctx->profile;
+  return 0;
+}
+
+int rtc_trace_closest(rtc_context* ctx, uint64_t topObject, uint64_t rays, uint64_t numRays, uint64_t hits)
+{
+  SceneRecord* s = find_scene(ctx, topObject);
+  if (!s) RTC_FAIL("unknown topObject");
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  RTC_CUDA(cudaEventRecord(ctx->evA, ctx->stream));
+  if (int rc = launch_trace_closest(ctx, &s->desc, (const rtc_ray*)(uintptr_t)rays, numRays, (rtc_hit*)(uintptr_t)hits)) return rc;
+  RTC_CUDA(cudaEventRecord(ctx->evB, ctx->stream));
+  ctx->traceTimed = true;
+  return 0;
+}
+
+int rtc_trace_any(rtc_context* ctx, uint64_t topObject, uint64_t rays, uint64_t numRays, uint64_t occluded)
+{
+  SceneRecord* s = find_scene(ctx, topObject);
+  if (!s) RTC_FAIL("unknown topObject");
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  RTC_CUDA(cudaEventRecord(ctx->evA, ctx->stream));
+  if (int rc = launch_trace_any(ctx, &s->desc, (const rtc_ray*)(uintptr_t)rays, numRays, (uint32_t*)(uintptr_t)occluded)) return rc;
+  RTC_CUDA(cudaEventRecord(ctx->evB, ctx->stream));
+  ctx->traceTimed = true;
+  return 0;
+}
+
+int rtc_trace_count(rtc_context* ctx, uint64_t topObject, uint64_t rays, uint64_t numRays, int anyHit, rtc_trace_counts* out)
+{
+  SceneRecord* s = find_scene(ctx, topObject);
+  if (!s) RTC_FAIL("unknown topObject");
+  if (!out) RTC_FAIL("out is null");
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(ctx->d_stats + 4);
+  RTC_CUDA(cudaMemsetAsync(d, 0, 4 * sizeof(uint64_t), ctx->stream));
+  if (int rc = launch_trace_count(ctx, &s->desc, (const rtc_ray*)(uintptr_t)rays, numRays, anyHit, d)) return rc;
+  uint64_t h[4];
+  RTC_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  RTC_CUDA(cudaStreamSynchronize(ctx->stream));
+  out->nodes = h[0]; out->tris = h[1]; out->instances = h[2]; out->rays = h[3];
+  return 0;
+}
+
+int rtc_generate_primary(rtc_context* ctx, const rt_SystemData* sys, uint32_t launchWidth, uint32_t launchHeight,
+                         int iteration, uint64_t rays)
+{
+  if (!sys) RTC_FAIL("sys is null");
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  return launch_generate_primary(ctx, *sys, launchWidth, launchHeight, iteration, (rtc_ray*)(uintptr_t)rays);
+}
+
+int rtc_composite(rtc_context* ctx, const rt_CompositorData* args)
+{
+  if (!args) RTC_FAIL("args is null");
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  return launch_composite(ctx, *args);
+}
+
+int rtc_tonemap(rtc_context* ctx, const rt_TonemapperParams* params, uint64_t rgba, uint64_t rgb8, uint64_t numPixels)
+{
+  if (!params) RTC_FAIL("params is null");
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  return launch_tonemap(ctx, *params, (const float4*)(uintptr_t)rgba, (uint8_t*)(uintptr_t)rgb8, numPixels);
+}
+
+int rtc_stats_get(rtc_context* ctx, rtc_stats* out)
+{
+  if (!out) RTC_FAIL("out is null");
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  uint64_t h[4];
+  RTC_CUDA(cudaMemcpyAsync(h, ctx->d_stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  RTC_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->traceTimed)
+  {
+    float ms = 0.0f;
+    RTC_CUDA(cudaEventElapsedTime(&ms, ctx->evA, ctx->evB));
+    ctx->lastTraceMs = ms;
+  }
+  out->radianceRays = h[0]; out->shadowRays = h[1]; out->pathSamples = h[2];
+  out->kernelLaunches = ctx->kernelLaunches; out->lastTraceMs = ctx->lastTraceMs;
+  return 0;
+}
+
+int rtc_stats_reset(rtc_context* ctx)
+{
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  RTC_CUDA(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(uint64_t), ctx->stream));
+  ctx->kernelLaunches = 0;
+  return 0;
+}
+
+} // extern "C"

@@ -2,11 +2,14 @@
 //
 // HBM layout of one scene (everything the traversal touches is 16-byte addressable so every
 // fetch is one LDG.128):
-//   nodes      uint4[5] per wide node (80 B): 8 children, quantised boxes           -> Node8 below
-//   tris       float4[3] per triangle (48 B): v0.xyz|prim id, v1.xyz|0, v2.xyz|0    (leaf order)
-//   instances  float4[4] per instance (64 B): world->object rows 0..2, {root node, -, -, -}
-//   tlasLeaves uint32 per instance-level leaf slot -> instance id
+//   per GAS    nodes  uint4[5] per wide node (80 B): 8 children, quantised boxes    -> Node8 below (root = node 0)
+//              tris   float4[3] per triangle (48 B): v0.xyz|prim id, v1.xyz|0, v2.xyz|0   (leaf order)
+//   per scene  tlasNodes  the same 80 B nodes over instance bounds (root = node 0)
+//              tlasLeaves uint32 per instance-level leaf slot -> instance id
+//              instances  float4[4] per instance (64 B): world->object rows 0..2, {GAS nodes ptr, GAS tris ptr}
 //   shading tables (used by shade only): objectToWorld float4[3], rt_GeometryInstanceData per instance
+// Node and triangle indices are relative to their own GAS, so a GAS is built once (on the host or by the
+// GPU builder, straight into device memory) and shared by any number of instances and scenes.
 #pragma once
 
 #include <cstdint>
@@ -41,16 +44,15 @@ static_assert(sizeof(Node8) == 80, "wide node is 80 bytes");
 // Device-visible scene descriptor; SystemData::topObject points at one of these (in device memory).
 struct SceneDesc
 {
-  const uint4*    nodes;
-  const float4*   tris;
-  const float4*   instances;
+  const uint4*    tlasNodes;
   const uint32_t* tlasLeaves;
+  const float4*   instances;
   const float4*   objectToWorld;
   const rt_GeometryInstanceData* geomInst;
-  uint32_t        tlasRoot;
   uint32_t        numInstances;
-  uint32_t        numNodes;
-  uint32_t        numTris;
+  uint32_t        numTlasNodes;
+  uint32_t        numTlasLeaves;
+  uint32_t        pad0;
 };
 
 // Host-side result of a BVH build over generic primitive boxes.
@@ -68,19 +70,25 @@ void build_wide_bvh_host(const PrimBox* prims, uint32_t numPrims, WideBvh& out);
 
 struct GasRecord
 {
-  uint32_t nodeOffset = 0, numNodes = 0;   // into the context-wide staging arrays
-  uint32_t triOffset = 0, numTris = 0;
-  float    lo[3], hi[3];
-  uint64_t attributes = 0, indices = 0;
+  void*    d_nodes = nullptr;              // Node8[numNodes]
+  void*    d_tris = nullptr;               // float4[3 * numTris]
+  uint32_t numNodes = 0, numTris = 0;
+  float    lo[3] = { 0, 0, 0 }, hi[3] = { 0, 0, 0 };
+  uint64_t attributes = 0, indices = 0;    // caller-owned inputs (kept for the per-instance shading table)
   uint32_t strideBytes = 0, numVerts = 0;
+  double   buildMs = 0.0;
+  int      builder = 0;                    // RTC_BUILD_HOST_SAH or RTC_BUILD_GPU_LBVH
 };
 
 struct SceneRecord
 {
   SceneDesc desc{};          // host copy
   SceneDesc* d_desc = nullptr;
-  void *d_nodes = nullptr, *d_tris = nullptr, *d_instances = nullptr, *d_tlasLeaves = nullptr, *d_o2w = nullptr, *d_geomInst = nullptr;
-  uint32_t numTlasLeaves = 0;
+  void *d_tlasNodes = nullptr, *d_instances = nullptr, *d_tlasLeaves = nullptr, *d_o2w = nullptr, *d_geomInst = nullptr;
+  std::vector<float> inverses;             // 12 floats per instance (host copy of the world->object matrices)
+  uint64_t totalNodes = 0, totalTris = 0;  // unique GAS nodes / triangles referenced + instance level
+  uint32_t numGas = 0;
+  double   gasBuildMs = 0.0, iasBuildMs = 0.0;
 };
 
 // Wavefront state of one launch batch (device pointers, SoA, sized for `capacity` paths).
@@ -106,15 +114,31 @@ struct rtc_context
   cudaStream_t stream = nullptr;
   int numSMs = 0;
   std::vector<GasRecord> gas;
-  std::vector<Node8>  stagingNodes;   // all GAS nodes, concatenated (indices absolute)
-  std::vector<float4> stagingTris;
   std::vector<SceneRecord*> scenes;
   WavefrontBuffers wf;
   uint64_t* d_stats = nullptr;        // device counters: radiance rays, shadow rays, path samples
   uint64_t kernelLaunches = 0;
   double lastTraceMs = 0.0;
+  bool traceTimed = false;
   cudaEvent_t evA = nullptr, evB = nullptr;
+  cudaEvent_t evTimerA = nullptr, evTimerB = nullptr;
+  // per-kernel-class profile (rtc_profile_enable): pending event pairs are resolved at rtc_profile_get
+  bool profiling = false;
+  struct ProfileSpan { int cls; cudaEvent_t a, b; };
+  std::vector<ProfileSpan> spans;
+  std::vector<cudaEvent_t> eventPool;
+  rtc_profile profile{};
+  unsigned long long* d_launchCounts = nullptr;   // 2 x {nodes, tris, insts, rays}: extend, connect
 };
+
+// RAII-less helpers used by the launchers: bracket one kernel launch with an event pair when profiling is on
+int profile_begin(rtc_context* ctx, int cls);
+int profile_end(rtc_context* ctx);
+
+// RTC_BUILD_DEFAULT picks the GPU LBVH builder above this many triangles (host SAH quality below it)
+constexpr uint32_t kGpuBuildThreshold = 1u << 20;
+// bvh_build_gpu.cu: Morton LBVH on the device, straight into rec.d_nodes / rec.d_tris; fills numNodes, lo, hi
+int build_gas_gpu(rtc_context* ctx, GasRecord& rec);
 
 // error plumbing (rtc_api.cpp)
 int rtc_set_error(const char* file, int line, const char* call, int code, const char* text);
@@ -124,10 +148,13 @@ int rtc_set_error(const char* file, int line, const char* call, int code, const 
 // kernel launchers (kernels_trace.cu / kernels_shade.cu); all enqueue on ctx->stream
 int launch_trace_closest(rtc_context* ctx, const SceneDesc* d_scene, const rtc_ray* rays, uint64_t n, rtc_hit* hits);
 int launch_trace_any(rtc_context* ctx, const SceneDesc* d_scene, const rtc_ray* rays, uint64_t n, uint32_t* occluded);
-int launch_extend(rtc_context* ctx, const SceneDesc* d_scene, const WavefrontBuffers& wf, const uint32_t* queue, const uint32_t* count);
-int launch_connect(rtc_context* ctx, const SceneDesc* d_scene, const WavefrontBuffers& wf, const uint32_t* count);
+// counting variant: adds {nodes popped, triangles tested, instances entered, rays} to d_counts[0..3]
+int launch_trace_count(rtc_context* ctx, const SceneDesc* d_scene, const rtc_ray* rays, uint64_t n, int anyHit, unsigned long long* d_counts);
+int launch_extend(rtc_context* ctx, const SceneDesc* d_scene, const WavefrontBuffers& wf, const uint32_t* queue, const uint32_t* count, bool countWork);
+int launch_connect(rtc_context* ctx, const SceneDesc* d_scene, const WavefrontBuffers& wf, const uint32_t* count, bool countWork);
 int launch_generate_primary(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uint32_t h, int iteration, rtc_ray* rays);
-int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uint32_t h, int raygen, int miss, int iterFirst, int iterCount);
+int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uint32_t h, int raygen, int miss, int iterFirst, int iterCount,
+                     int accumFirst, bool countWork);
 int launch_composite(rtc_context* ctx, const rt_CompositorData& args);
 int launch_tonemap(rtc_context* ctx, const rt_TonemapperParams& p, const float4* rgba, uint8_t* rgb, uint64_t n);
 int ensure_wavefront(rtc_context* ctx, uint64_t capacity);

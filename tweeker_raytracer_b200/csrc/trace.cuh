@@ -143,11 +143,14 @@ __device__ __forceinline__ uint32_t node_test(const BoxRay& b, const uint4 n0, c
   return mask;
 }
 
+// Per-ray work counters of the counting variant (the algorithmic-bytes figure of DESIGN.md section 5).
+struct TraceCounts { uint32_t nodes, tris, insts; };
+
 // Closest hit (ANY = false) or first hit (ANY = true) of one ray against the two-level scene.
 // Closest hit: smallest t in (tmin, tmax), ties -> smaller (instance, primitive).
-template <bool ANY>
+template <bool ANY, bool COUNT = false>
 __device__ __forceinline__ bool trace_ray(const SceneDesc& sc, const float4 org, const float4 dir, TraceHit& hit,
-                                          uint32_t* __restrict__ counters = nullptr)
+                                          TraceCounts* counts = nullptr)
 {
   const float tmin = org.w;
   float tlimit = dir.w;               // current far bound (shrinks to the best t for closest hit)
@@ -162,8 +165,10 @@ __device__ __forceinline__ bool trace_ray(const SceneDesc& sc, const float4 org,
   BoxRay br;
   box_setup(br, org.x, org.y, org.z, dir.x, dir.y, dir.z);
   ObjRay orr;
+  const uint4*  nodes = sc.tlasNodes; // node array of the current level
+  const float4* tris = nullptr;       // triangle array of the current GAS
 
-  uint2 nodeGroup = make_uint2(sc.tlasRoot, 0x80000000u);
+  uint2 nodeGroup = make_uint2(0u, 0x80000000u);
   uint2 triGroup = make_uint2(0u, 0u);
 
   for (;;)
@@ -175,8 +180,9 @@ __device__ __forceinline__ bool trace_ray(const SceneDesc& sc, const float4 org,
       if (nodeGroup.y & 0xff000000u) { if (sp < RTC_STACK_SIZE) stack[sp++] = nodeGroup; }
       const uint32_t slot = (bit - 24u) ^ br.octinv;
       const uint32_t rel = (uint32_t)__popc(nodeGroup.y & 0xffu & ((1u << slot) - 1u));
-      const uint4* np = sc.nodes + (size_t)(nodeGroup.x + rel) * 5u;
+      const uint4* np = nodes + (size_t)(nodeGroup.x + rel) * 5u;
       const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+      if (COUNT) counts->nodes++;
       const uint32_t m = node_test(br, n0, n1, n2, n3, n4, tmin, tlimit);
       nodeGroup = make_uint2(n1.x, (m & 0xff000000u) | (n0.w >> 24));
       triGroup = make_uint2(n1.y, m & 0x00ffffffu);
@@ -199,6 +205,7 @@ __device__ __forceinline__ bool trace_ray(const SceneDesc& sc, const float4 org,
         if (nodeGroup.y & 0xff000000u) { if (sp < RTC_STACK_SIZE) stack[sp++] = nodeGroup; }
         const float4* ip = sc.instances + (size_t)inst * 4u;
         const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
+        if (COUNT) counts->insts++;
         orr.ox = __fmaf_rn(r0.x, org.x, __fmaf_rn(r0.y, org.y, __fmaf_rn(r0.z, org.z, r0.w)));
         orr.oy = __fmaf_rn(r1.x, org.x, __fmaf_rn(r1.y, org.y, __fmaf_rn(r1.z, org.z, r1.w)));
         orr.oz = __fmaf_rn(r2.x, org.x, __fmaf_rn(r2.y, org.y, __fmaf_rn(r2.z, org.z, r2.w)));
@@ -209,14 +216,17 @@ __device__ __forceinline__ bool trace_ray(const SceneDesc& sc, const float4 org,
         box_setup(br, orr.ox, orr.oy, orr.oz, orr.dx, orr.dy, orr.dz);
         curInst = inst;
         blasBase = sp;
-        nodeGroup = make_uint2(__float_as_uint(r3.x), 0x80000000u);
+        nodes = reinterpret_cast<const uint4*>(((unsigned long long)__float_as_uint(r3.y) << 32) | __float_as_uint(r3.x));
+        tris  = reinterpret_cast<const float4*>(((unsigned long long)__float_as_uint(r3.w) << 32) | __float_as_uint(r3.z));
+        nodeGroup = make_uint2(0u, 0x80000000u);
         triGroup = make_uint2(0u, 0u);
         break;
       }
       else
       {
-        const float4* tp = sc.tris + (size_t)(triGroup.x + idx) * 3u;
+        const float4* tp = tris + (size_t)(triGroup.x + idx) * 3u;
         const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+        if (COUNT) counts->tris++;
         float t, det, V, W;
         if (tri_test(orr, v0, v1, v2, t, det, V, W) && t > tmin)
         {
@@ -244,6 +254,7 @@ __device__ __forceinline__ bool trace_ray(const SceneDesc& sc, const float4 org,
       if (blasBase >= 0 && sp == blasBase)
       {
         blasBase = -1;   // leave the instance: back to the world-space ray
+        nodes = sc.tlasNodes;
         box_setup(br, org.x, org.y, org.z, dir.x, dir.y, dir.z);
       }
       if (sp == 0) break;

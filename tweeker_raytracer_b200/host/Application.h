@@ -1,0 +1,111 @@
+// Application.h -- rtigo3's Application (apps/rtigo3/inc/Application.h, src/Application.cpp) re-hosted headless:
+// system/scene description loaders (Application.cpp:1046-1299, :1397-1878), createLights (:572-677),
+// createCameras (:562-569), the strategy switch (:224-245), render/benchmark (:401-531) and screenshot (:2231-2340).
+// GLFW/ImGui/Rasterizer are out of scope; the loaders, index semantics and file formats are kept.
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "Camera.h"
+#include "EnvMap.h"
+#include "HostTypes.h"
+#include "Options.h"
+#include "Raytracer.h"
+#include "SceneGraph.h"
+
+// Flattened view of the loaded scene (the order Device::traverseNode visits it), used by tools and tests.
+struct FlatInstance { float transform[12]; int geometry; int material; int light; };
+
+class Application
+{
+public:
+  // hostOnly = true loads and flattens the scene without creating a Raytracer (no GPU needed; nothing can be rendered).
+  explicit Application(Options const& options, bool hostOnly = false);
+  ~Application();
+
+  bool isValid() const { return m_isValid; }
+  unsigned int render(const unsigned int count = 1);        // advances up to `count` iterations; returns iterations done
+  void benchmark();                                         // Application.cpp:491-531: all spp, fps print, tonemapped screenshot
+  bool screenshot(const bool tonemap, std::string* writtenPath = nullptr);
+  const float* getOutputBufferHost();                       // float4 rows bottom-up, resolution.x * resolution.y
+  void tonemapDevice(std::vector<unsigned char>& rgb);      // rtc_tonemap of the current frame (device 0)
+  void restartAccumulation();
+
+  // accessors
+  Raytracer* getRaytracer() { return m_raytracer.get(); }
+  int2 getResolution() const { return m_resolution; }
+  int getSamplesPerPixel() const { return m_samplesSqrt * m_samplesSqrt; }
+  int getMiss() const { return m_miss; }
+  int getLightMode() const { return m_light; }
+  int getDevicesMask() const { return m_devicesMask; }
+  std::string getPrefixScreenshot() const { return m_prefixScreenshot; }
+  void getMaterialDefinitions(std::vector<MaterialDefinition>& out) const;
+  void getSystemData(int deviceIndex, SystemData& out) const;
+  RendererStrategy getStrategy() const { return m_strategy; }
+  TonemapperGUI const& getTonemapper() const { return m_tonemapperGUI; }
+  DeviceState const& getState() const { return m_state; }
+  std::vector<MaterialGUI> const& getMaterialsGUI() const { return m_materialsGUI; }
+  std::vector<LightDefinition> const& getLights() const { return m_lights; }
+  std::vector<CameraDefinition> const& getCameras() const { return m_cameras; }
+  std::vector<std::shared_ptr<sg::Triangles>> const& getGeometries() const { return m_geometries; }
+  std::vector<FlatInstance> const& getFlatInstances() const { return m_flatInstances; }
+  EnvMap const* getEnvironment() const { return m_environmentMap.get(); }
+  double getLastBenchmarkSeconds() const { return m_benchmarkSeconds; }
+  std::string getLastError() const { return m_lastError; }
+  void setCompositeMode(int mode);
+
+private:
+  bool loadSystemDescription(std::string const& filename);
+  bool loadSceneDescription(std::string const& filename);
+  void createCameras();
+  void createLights();
+  void createPictures();
+  void appendInstance(std::shared_ptr<sg::Group>& group, std::shared_ptr<sg::Triangles> geometry, const float trafo[12],
+                      std::string const& reference, unsigned int& idInstance);
+  std::shared_ptr<sg::Triangles> cachedGeometry(std::string const& key, bool& created);
+  void flatten(std::shared_ptr<sg::Node> node, const float matrix[12], int material, int light);
+
+private:
+  bool m_isValid = false;
+  std::string m_lastError;
+
+  // system options (defaults: Application.cpp:55-120)
+  RendererStrategy m_strategy = RS_INTERACTIVE_SINGLE_GPU;
+  int   m_devicesMask = 255;
+  int   m_interop = 0;
+  bool  m_present = false;
+  int2  m_resolution = { 1, 1 };
+  int2  m_tileSize = { 8, 8 };
+  int   m_samplesSqrt = 1;
+  int   m_miss = 1;
+  std::string m_environment;
+  float m_environmentRotation = 0.0f;
+  float m_clockFactor = 1000.0f;
+  int   m_light = 0;
+  int2  m_pathLengths = { 0, 2 };
+  float m_epsilonFactor = 500.0f;
+  LensShader m_lensShader = LENS_SHADER_PINHOLE;
+  std::string m_prefixScreenshot = "./img";
+  TonemapperGUI m_tonemapperGUI;
+  int   m_compositeMode = 0;     // extension keyword "composite": 0 peer copies, 1 NCCL reduce (local-copy strategy)
+  int   m_batch = 1;             // extension keyword "batchIterations": iterations per enqueue in benchmark()
+
+  Camera m_camera;
+  DeviceState m_state;
+  std::unique_ptr<Raytracer> m_raytracer;
+
+  std::shared_ptr<sg::Group> m_scene;
+  unsigned int m_idGroup = 0, m_idInstance = 0, m_idGeometry = 0;
+  std::vector<std::shared_ptr<sg::Triangles>> m_geometries;
+  std::map<std::string, unsigned int> m_mapGeometries;
+  std::vector<MaterialGUI> m_materialsGUI;
+  std::map<std::string, int> m_mapMaterialReferences;
+  std::vector<CameraDefinition> m_cameras;
+  std::vector<LightDefinition> m_lights;
+  std::unique_ptr<EnvMap> m_environmentMap;
+  std::map<std::string, EnvMap*> m_mapPictures;
+  std::vector<FlatInstance> m_flatInstances;
+  double m_benchmarkSeconds = 0.0;
+};

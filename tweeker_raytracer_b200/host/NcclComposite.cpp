@@ -1,0 +1,47 @@
+#include "NcclComposite.h"
+
+#include <stdexcept>
+#include <vector>
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+struct NcclGroup
+{
+  std::vector<ncclComm_t> comms;
+  std::vector<int> ordinals;
+};
+
+static void check(ncclResult_t r, const char* what)
+{
+  if (r != ncclSuccess) throw std::runtime_error(std::string("ERROR: ") + what + ": " + ncclGetErrorString(r));
+}
+
+NcclGroup* ncclGroupCreate(int count, const int* ordinals)
+{
+  NcclGroup* g = new NcclGroup();
+  g->ordinals.assign(ordinals, ordinals + count);
+  g->comms.resize((size_t)count);
+  try { check(ncclCommInitAll(g->comms.data(), count, g->ordinals.data()), "ncclCommInitAll"); }
+  catch (...) { delete g; throw; }
+  return g;
+}
+
+void ncclGroupDestroy(NcclGroup* group)
+{
+  if (!group) return;
+  for (ncclComm_t c : group->comms) ncclCommDestroy(c);
+  delete group;
+}
+
+void ncclGroupReduceSum(NcclGroup* group, const uint64_t* src, uint64_t dstRoot, size_t count, const uint64_t* streams)
+{
+  check(ncclGroupStart(), "ncclGroupStart");
+  for (size_t i = 0; i < group->comms.size(); ++i)
+  {
+    cudaSetDevice(group->ordinals[i]);
+    check(ncclReduce((const void*)(uintptr_t)src[i], (void*)(uintptr_t)dstRoot, count, ncclFloat, ncclSum, 0, group->comms[i],
+                     (cudaStream_t)(uintptr_t)streams[i]), "ncclReduce");
+  }
+  check(ncclGroupEnd(), "ncclGroupEnd");
+}

@@ -1,0 +1,278 @@
+#include "Raytracer.h"
+
+#include <cstring>
+#include <iostream>
+
+#include "NcclComposite.h"
+
+Raytracer::Raytracer(RendererStrategy strategy, const int interop, const unsigned int tex, const unsigned int pbo)
+: m_strategy(strategy), m_interop(interop), m_tex(tex), m_pbo(pbo), m_isValid(false)
+, m_visibleDevices(0), m_deviceOGL(-1), m_activeDevicesMask(0), m_iterationIndex(0), m_samplesPerPixel(1)
+{
+  RTC_CHECK(rtc_device_count(&m_visibleDevices));
+  std::cout << "Raytracer() core version " << rtc_version() << ", " << m_visibleDevices << " visible CUDA device(s)" << std::endl;
+}
+
+Raytracer::~Raytracer()
+{
+  for (Device* device : m_activeDevices) delete device;
+}
+
+template <class DeviceType>
+void Raytracer::createDevices(const int devicesMask, const int miss, const bool onlyFirst)
+{
+  std::vector<int> ordinals;
+  for (int ordinal = 0; ordinal < m_visibleDevices && ordinal < 32; ++ordinal)
+  {
+    if (devicesMask & (1 << ordinal)) { ordinals.push_back(ordinal); if (onlyFirst) break; }
+  }
+  const int count = (int)ordinals.size();
+  for (int index = 0; index < count; ++index)
+  {
+    const int ordinal = ordinals[index];
+    m_activeDevices.push_back(new DeviceType(m_strategy, ordinal, index, count, miss, m_interop, m_tex, m_pbo));
+    m_activeDevicesMask |= (1u << ordinal);
+    char name[256] = "";
+    RTC_CHECK(rtc_device_name(ordinal, name, (int)sizeof(name)));
+    std::cout << "Raytracer() Using device " << ordinal << ": " << name << std::endl;
+  }
+  m_isValid = !m_activeDevices.empty();
+}
+
+// Peer-to-peer bit matrix and islands (Raytracer.cpp:109-234).  On an NVSwitch box all GPUs form one island.
+bool Raytracer::enablePeerAccess()
+{
+  const size_t n = m_activeDevices.size();
+  m_peerConnections.assign(n, 0u);
+  for (size_t i = 0; i < n; ++i)
+  {
+    m_peerConnections[i] |= (1u << i);
+    for (size_t j = 0; j < n; ++j)
+    {
+      if (i == j) continue;
+      int can = 0;
+      RTC_CHECK(rtc_peer_can_access(m_activeDevices[i]->m_ordinal, m_activeDevices[j]->m_ordinal, &can));
+      if (can)
+      {
+        RTC_CHECK(rtc_peer_enable(m_activeDevices[i]->getContext(), m_activeDevices[j]->getContext()));
+        m_peerConnections[i] |= (1u << j);
+      }
+    }
+  }
+  // islands: greedy grouping of devices which all see each other
+  m_peerIslands.clear();
+  std::vector<bool> placed(n, false);
+  for (size_t i = 0; i < n; ++i)
+  {
+    if (placed[i]) continue;
+    std::vector<int> island(1, (int)i);
+    placed[i] = true;
+    for (size_t j = i + 1; j < n; ++j)
+    {
+      if (placed[j]) continue;
+      bool all = true;
+      for (int k : island) all = all && (m_peerConnections[k] & (1u << j)) && (m_peerConnections[j] & (1u << k));
+      if (all) { island.push_back((int)j); placed[j] = true; }
+    }
+    m_peerIslands.push_back(island);
+  }
+  return m_peerIslands.size() <= 1;
+}
+
+void Raytracer::disablePeerAccess()
+{
+  const size_t n = m_activeDevices.size();
+  for (size_t i = 0; i < n && i < m_peerConnections.size(); ++i)
+    for (size_t j = 0; j < n; ++j)
+      if (i != j && (m_peerConnections[i] & (1u << j)))
+        RTC_CHECK(rtc_peer_disable(m_activeDevices[i]->getContext(), m_activeDevices[j]->getContext()));
+  m_peerConnections.clear();
+  m_peerIslands.clear();
+  for (size_t i = 0; i < n; ++i) m_peerIslands.push_back(std::vector<int>(1, (int)i));
+}
+
+void Raytracer::synchronize()
+{
+  for (Device* device : m_activeDevices) { device->activateContext(); device->synchronizeStream(); }
+}
+
+void Raytracer::initTextures(std::map<std::string, EnvMap*> const& mapOfPictures) { for (Device* d : m_activeDevices) d->initTextures(mapOfPictures); }
+void Raytracer::initCameras(std::vector<CameraDefinition> const& cameras) { for (Device* d : m_activeDevices) d->initCameras(cameras); }
+void Raytracer::initLights(std::vector<LightDefinition> const& lights) { for (Device* d : m_activeDevices) d->initLights(lights); }
+void Raytracer::initMaterials(std::vector<MaterialGUI> const& materialsGUI) { for (Device* d : m_activeDevices) d->initMaterials(materialsGUI); }
+void Raytracer::initScene(std::shared_ptr<sg::Group> root, const unsigned int numGeometries) { for (Device* d : m_activeDevices) d->initScene(root, numGeometries); }
+
+void Raytracer::initState(DeviceState const& state)
+{
+  m_samplesPerPixel = (unsigned int)(state.samplesSqrt * state.samplesSqrt);
+  for (Device* d : m_activeDevices) d->setState(state);
+}
+
+// Every update restarts the accumulation (Raytracer.cpp:331-367).
+void Raytracer::updateCamera(const int idCamera, CameraDefinition const& camera) { for (Device* d : m_activeDevices) d->updateCamera(idCamera, camera); m_iterationIndex = 0; }
+void Raytracer::updateLight(const int idLight, LightDefinition const& light) { for (Device* d : m_activeDevices) d->updateLight(idLight, light); m_iterationIndex = 0; }
+void Raytracer::updateMaterial(const int idMaterial, MaterialGUI const& src) { for (Device* d : m_activeDevices) d->updateMaterial(idMaterial, src); m_iterationIndex = 0; }
+void Raytracer::updateState(DeviceState const& state)
+{
+  m_samplesPerPixel = (unsigned int)(state.samplesSqrt * state.samplesSqrt);
+  for (Device* d : m_activeDevices) d->setState(state);
+  m_iterationIndex = 0;
+}
+
+unsigned int Raytracer::render(const unsigned int count) { return renderAll(count); }
+
+// All devices work on the same iteration indices; the first device called allocates shared buffers.
+unsigned int Raytracer::renderAll(const unsigned int count)
+{
+  if (m_iterationIndex < m_samplesPerPixel)
+  {
+    unsigned int n = m_samplesPerPixel - m_iterationIndex;
+    if (count < n) n = count;
+    void* buffer = nullptr;
+    for (Device* device : m_activeDevices) device->renderIterations(m_iterationIndex, n, &buffer);
+    m_iterationIndex += n;
+  }
+  return m_iterationIndex;
+}
+
+void Raytracer::getStats(rtc_stats& total)
+{
+  std::memset(&total, 0, sizeof(total));
+  for (Device* device : m_activeDevices)
+  {
+    rtc_stats s; device->getStats(s);
+    total.radianceRays += s.radianceRays; total.shadowRays += s.shadowRays; total.pathSamples += s.pathSamples;
+    total.kernelLaunches += s.kernelLaunches; total.lastTraceMs = s.lastTraceMs;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+RaytracerSingleGPU::RaytracerSingleGPU(const int devicesMask, const int miss, const int interop, const unsigned int tex, const unsigned int pbo)
+: Raytracer(RS_INTERACTIVE_SINGLE_GPU, interop, tex, pbo)
+{
+  createDevices<DeviceSingleGPU>(devicesMask, miss, true);
+}
+
+RaytracerMultiGPUZeroCopy::RaytracerMultiGPUZeroCopy(const int devicesMask, const int miss, const int interop, const unsigned int tex, const unsigned int pbo)
+: Raytracer(RS_INTERACTIVE_MULTI_GPU_ZERO_COPY, interop, tex, pbo)
+{
+  createDevices<DeviceMultiGPUZeroCopy>(devicesMask, miss, false);
+}
+
+const void* RaytracerMultiGPUZeroCopy::getOutputBufferHost()
+{
+  synchronize();
+  return m_activeDevices[0]->getOutputBufferHost();
+}
+
+RaytracerMultiGPUPeerAccess::RaytracerMultiGPUPeerAccess(const int devicesMask, const int miss, const int interop, const unsigned int tex, const unsigned int pbo)
+: Raytracer(RS_INTERACTIVE_MULTI_GPU_PEER_ACCESS, interop, tex, pbo)
+{
+  createDevices<DeviceMultiGPUPeerAccess>(devicesMask, miss, false);
+  // the shared frame lives on one device: every active device must reach it (RaytracerMultiGPUPeerAccess.cpp:79-84)
+  if (m_isValid && !enablePeerAccess())
+  {
+    std::cerr << "ERROR: RaytracerMultiGPUPeerAccess() the active devices do not form one peer-to-peer island." << std::endl;
+    m_isValid = false;
+  }
+}
+
+RaytracerMultiGPUPeerAccess::~RaytracerMultiGPUPeerAccess()
+{
+  try { synchronize(); disablePeerAccess(); } catch (std::exception const& e) { std::cerr << e.what() << std::endl; }
+}
+
+const void* RaytracerMultiGPUPeerAccess::getOutputBufferHost()
+{
+  synchronize();
+  return m_activeDevices[0]->getOutputBufferHost();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct RaytracerMultiGPULocalCopy::NcclState
+{
+  NcclGroup* group = nullptr;
+  std::vector<uint64_t> scatter;   // per device: full-resolution frame holding only that device's pixels
+  size_t pixels = 0;
+};
+
+RaytracerMultiGPULocalCopy::RaytracerMultiGPULocalCopy(const int devicesMask, const int miss, const int interop, const unsigned int tex, const unsigned int pbo)
+: Raytracer(RS_INTERACTIVE_MULTI_GPU_LOCAL_COPY, interop, tex, pbo)
+{
+  createDevices<DeviceMultiGPULocalCopy>(devicesMask, miss, false);
+  if (m_isValid) enablePeerAccess();   // peer copies fall back to staging through the host when this is not one island
+}
+
+RaytracerMultiGPULocalCopy::~RaytracerMultiGPULocalCopy()
+{
+  try
+  {
+    synchronize();
+    if (m_nccl)
+    {
+      for (size_t i = 0; i < m_nccl->scatter.size(); ++i) if (m_nccl->scatter[i]) RTC_CHECK_NO_THROW(rtc_free(m_activeDevices[i]->getContext(), m_nccl->scatter[i]));
+      ncclGroupDestroy(m_nccl->group);
+      delete m_nccl;
+    }
+    disablePeerAccess();
+  }
+  catch (std::exception const& e) { std::cerr << e.what() << std::endl; }
+}
+
+// The reference composites device 0 twice when no OpenGL device exists (RaytracerMultiGPULocalCopy.cpp:141-147);
+// the result is the same, so each device is composited once here.
+void RaytracerMultiGPULocalCopy::composite()
+{
+  if (m_compositeMode == COMPOSITE_NCCL_REDUCE && 1 < m_activeDevices.size()) { compositeNccl(); return; }
+  synchronize();
+  for (Device* device : m_activeDevices) m_activeDevices[0]->compositor(device);
+}
+
+// Every device scatters its own texel slab into a zeroed full-resolution frame (pixel ownership is disjoint), then
+// ONE ncclReduce(sum) over NVLink lands the complete frame on device 0: x + 0 + ... + 0 is exact, so the result is
+// bit-identical to the serial peer-copy compositor.
+void RaytracerMultiGPULocalCopy::compositeNccl()
+{
+  const size_t n = m_activeDevices.size();
+  DeviceMultiGPULocalCopy* root = static_cast<DeviceMultiGPULocalCopy*>(m_activeDevices[0]);
+  SystemData const& sys = root->getSystemData();
+  const size_t pixels = (size_t)sys.resolution.x * (size_t)sys.resolution.y;
+  if (!m_nccl)
+  {
+    m_nccl = new NcclState();
+    std::vector<int> ordinals;
+    for (Device* d : m_activeDevices) ordinals.push_back(d->m_ordinal);
+    m_nccl->group = ncclGroupCreate((int)n, ordinals.data());
+    m_nccl->scatter.assign(n, 0);
+  }
+  if (m_nccl->pixels != pixels)
+  {
+    for (size_t i = 0; i < n; ++i)
+    {
+      if (m_nccl->scatter[i]) RTC_CHECK(rtc_free(m_activeDevices[i]->getContext(), m_nccl->scatter[i]));
+      RTC_CHECK(rtc_malloc(m_activeDevices[i]->getContext(), sizeof(float4) * pixels, &m_nccl->scatter[i]));
+    }
+    m_nccl->pixels = pixels;
+  }
+  for (size_t i = 0; i < n; ++i)
+  {
+    DeviceMultiGPULocalCopy* d = static_cast<DeviceMultiGPULocalCopy*>(m_activeDevices[i]);
+    RTC_CHECK(rtc_memset(d->getContext(), m_nccl->scatter[i], 0, sizeof(float4) * pixels));
+    CompositorData args;
+    args.outputBuffer = m_nccl->scatter[i];
+    args.tileBuffer = d->getTexelBuffer();
+    args.resolution = sys.resolution; args.tileSize = sys.tileSize; args.tileShift = sys.tileShift;
+    args.launchWidth = d->getLaunchWidth(); args.deviceCount = (int)n; args.deviceIndex = d->m_index;
+    RTC_CHECK(rtc_composite(d->getContext(), &args));
+  }
+  std::vector<uint64_t> streams(n);
+  for (size_t i = 0; i < n; ++i) streams[i] = rtc_context_stream(m_activeDevices[i]->getContext());
+  ncclGroupReduceSum(m_nccl->group, m_nccl->scatter.data(), root->getOutputBuffer(), pixels * 4, streams.data());
+  synchronize();
+}
+
+const void* RaytracerMultiGPULocalCopy::getOutputBufferHost()
+{
+  composite();
+  return m_activeDevices[0]->getOutputBufferHost();
+}

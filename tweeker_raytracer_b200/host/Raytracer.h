@@ -1,0 +1,112 @@
+// Raytracer.h -- the strategy layer of rtigo3 (apps/rtigo3/inc/Raytracer.h:49-101 and the four derived
+// classes).  A Raytracer owns the active Devices (bits of devicesMask that exist), broadcasts init*/update*
+// to them, advances the iteration counter in render() and produces the final float4 frame.
+//   RaytracerSingleGPU            RaytracerSingleGPU.cpp:38-92
+//   RaytracerMultiGPUZeroCopy     RaytracerMultiGPUZeroCopy.cpp:38-129
+//   RaytracerMultiGPUPeerAccess   RaytracerMultiGPUPeerAccess.cpp:38-160
+//   RaytracerMultiGPULocalCopy    RaytracerMultiGPULocalCopy.cpp:38-173
+// B200 additions: render(count) enqueues several iterations at once, and the local-copy strategy can combine
+// the per-GPU results with one NCCL reduce over NVLink instead of N serial peer copies (setCompositeMode).
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "Devices.h"
+
+class Raytracer
+{
+public:
+  Raytracer(RendererStrategy strategy, const int interop, const unsigned int tex, const unsigned int pbo);
+  virtual ~Raytracer();
+
+  bool enablePeerAccess();    // fills m_peerConnections and m_peerIslands; false when more than one island exists
+  void disablePeerAccess();
+  void synchronize();
+
+  virtual void initTextures(std::map<std::string, EnvMap*> const& mapOfPictures);
+  virtual void initCameras(std::vector<CameraDefinition> const& cameras);
+  virtual void initLights(std::vector<LightDefinition> const& lights);
+  virtual void initMaterials(std::vector<MaterialGUI> const& materialsGUI);
+  virtual void initScene(std::shared_ptr<sg::Group> root, const unsigned int numGeometries);
+  virtual void initState(DeviceState const& state);
+
+  virtual void updateCamera(const int idCamera, CameraDefinition const& camera);
+  virtual void updateLight(const int idLight, LightDefinition const& light);
+  virtual void updateMaterial(const int idMaterial, MaterialGUI const& src);
+  virtual void updateState(DeviceState const& state);
+
+  virtual unsigned int render() = 0;                 // one iteration; returns the iterations done so far
+  virtual unsigned int render(const unsigned int count);   // up to `count` iterations in one enqueue
+  virtual void updateDisplayTexture() = 0;
+  virtual const void* getOutputBufferHost() = 0;
+
+  void getStats(rtc_stats& total);                   // summed over the active devices
+
+public:
+  RendererStrategy m_strategy;
+  int              m_interop;
+  unsigned int     m_tex;
+  unsigned int     m_pbo;
+  bool m_isValid;
+  int                  m_visibleDevices;
+  int                  m_deviceOGL;          // always -1 (headless)
+  unsigned int         m_activeDevicesMask;
+  std::vector<Device*> m_activeDevices;
+  unsigned int m_iterationIndex;
+  unsigned int m_samplesPerPixel;
+  std::vector<unsigned int>       m_peerConnections;
+  std::vector< std::vector<int> > m_peerIslands;
+
+protected:
+  template <class DeviceType> void createDevices(const int devicesMask, const int miss, const bool onlyFirst);
+  unsigned int renderAll(const unsigned int count);
+};
+
+class RaytracerSingleGPU : public Raytracer
+{
+public:
+  RaytracerSingleGPU(const int devicesMask, const int miss, const int interop, const unsigned int tex, const unsigned int pbo);
+  unsigned int render() override { return renderAll(1); }
+  void updateDisplayTexture() override { m_activeDevices[0]->updateDisplayTexture(); }
+  const void* getOutputBufferHost() override { return m_activeDevices[0]->getOutputBufferHost(); }
+};
+
+class RaytracerMultiGPUZeroCopy : public Raytracer
+{
+public:
+  RaytracerMultiGPUZeroCopy(const int devicesMask, const int miss, const int interop, const unsigned int tex, const unsigned int pbo);
+  unsigned int render() override { return renderAll(1); }
+  void updateDisplayTexture() override {}
+  const void* getOutputBufferHost() override;
+};
+
+class RaytracerMultiGPUPeerAccess : public Raytracer
+{
+public:
+  RaytracerMultiGPUPeerAccess(const int devicesMask, const int miss, const int interop, const unsigned int tex, const unsigned int pbo);
+  ~RaytracerMultiGPUPeerAccess() override;
+  unsigned int render() override { return renderAll(1); }
+  void updateDisplayTexture() override {}
+  const void* getOutputBufferHost() override;
+};
+
+enum CompositeMode { COMPOSITE_PEER_COPY = 0, COMPOSITE_NCCL_REDUCE = 1 };
+
+class RaytracerMultiGPULocalCopy : public Raytracer
+{
+public:
+  RaytracerMultiGPULocalCopy(const int devicesMask, const int miss, const int interop, const unsigned int tex, const unsigned int pbo);
+  ~RaytracerMultiGPULocalCopy() override;
+  unsigned int render() override { return renderAll(1); }
+  void updateDisplayTexture() override { composite(); }
+  const void* getOutputBufferHost() override;
+  void setCompositeMode(CompositeMode mode) { m_compositeMode = mode; }
+private:
+  void composite();
+  void compositeNccl();
+  CompositeMode m_compositeMode = COMPOSITE_PEER_COPY;
+  struct NcclState;
+  NcclState* m_nccl = nullptr;
+};

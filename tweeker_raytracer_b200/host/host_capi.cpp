@@ -1,0 +1,129 @@
+// host_capi.cpp -- flat C entry points over the C++ host classes, for tools and the Python test harness
+// (ctypes).  Nothing here computes pixels: rendering goes Application -> Raytracer -> Device -> librtcore.
+#include <cstring>
+#include <string>
+
+#include "Application.h"
+
+extern "C" {
+
+struct rth_info
+{
+  int resolutionX, resolutionY, samplesSqrt, miss, lightMode, strategy, numDevices;
+  int numGeometries, numInstances, numMaterials, numLights, hasEnvironment;
+};
+
+static std::string g_error;
+const char* rth_last_error(void) { return g_error.c_str(); }
+
+void* rth_app_create(const char* systemFile, const char* sceneFile, int hostOnly)
+{
+  Options options;
+  options.set(512, 512, 1, systemFile ? systemFile : "", sceneFile ? sceneFile : "");
+  Application* app = nullptr;
+  try { app = new Application(options, hostOnly != 0); }
+  catch (std::exception const& e) { g_error = e.what(); return nullptr; }
+  if (!app->isValid()) { g_error = app->getLastError(); delete app; return nullptr; }
+  return app;
+}
+
+void rth_app_destroy(void* h) { delete static_cast<Application*>(h); }
+
+int rth_app_info(void* h, rth_info* out)
+{
+  Application* app = static_cast<Application*>(h);
+  std::memset(out, 0, sizeof(*out));
+  out->resolutionX = app->getResolution().x; out->resolutionY = app->getResolution().y;
+  out->samplesSqrt = app->getState().samplesSqrt; out->miss = app->getMiss(); out->lightMode = app->getLightMode();
+  out->strategy = (int)app->getStrategy();
+  out->numDevices = app->getRaytracer() ? (int)app->getRaytracer()->m_activeDevices.size() : 0;
+  out->numGeometries = (int)app->getGeometries().size(); out->numInstances = (int)app->getFlatInstances().size();
+  out->numMaterials = (int)app->getMaterialsGUI().size(); out->numLights = (int)app->getLights().size();
+  out->hasEnvironment = app->getEnvironment() && app->getEnvironment()->getWidth() ? 1 : 0;
+  return 0;
+}
+
+int rth_app_geometry(void* h, int g, const rt_TriangleAttributes** attrs, unsigned int* numVerts, const unsigned int** indices, unsigned int* numTris)
+{
+  Application* app = static_cast<Application*>(h);
+  if (g < 0 || (size_t)g >= app->getGeometries().size()) return -1;
+  sg::Triangles const& t = *app->getGeometries()[g];
+  *attrs = t.getAttributes().data(); *numVerts = (unsigned int)t.getAttributes().size();
+  *indices = t.getIndices().data(); *numTris = (unsigned int)(t.getIndices().size() / 3);
+  return 0;
+}
+
+int rth_app_instance(void* h, int i, float transform[12], int* geometry, int* material, int* light)
+{
+  Application* app = static_cast<Application*>(h);
+  if (i < 0 || (size_t)i >= app->getFlatInstances().size()) return -1;
+  FlatInstance const& fi = app->getFlatInstances()[i];
+  std::memcpy(transform, fi.transform, sizeof(float) * 12);
+  *geometry = fi.geometry; *material = fi.material; *light = fi.light;
+  return 0;
+}
+
+int rth_app_materials(void* h, rt_MaterialDefinition* out)
+{
+  std::vector<MaterialDefinition> m;
+  static_cast<Application*>(h)->getMaterialDefinitions(m);
+  std::memcpy(out, m.data(), m.size() * sizeof(MaterialDefinition));
+  return (int)m.size();
+}
+
+int rth_app_lights(void* h, rt_LightDefinition* out)
+{
+  std::vector<LightDefinition> const& l = static_cast<Application*>(h)->getLights();
+  if (!l.empty()) std::memcpy(out, l.data(), l.size() * sizeof(LightDefinition));
+  return (int)l.size();
+}
+
+int rth_app_camera(void* h, rt_CameraDefinition* out) { *out = static_cast<Application*>(h)->getCameras()[0]; return 0; }
+
+int rth_app_system_data(void* h, int deviceIndex, rt_SystemData* out) { static_cast<Application*>(h)->getSystemData(deviceIndex, *out); return 0; }
+
+int rth_app_tonemapper(void* h, rt_TonemapperParams* out) { *out = static_cast<Application*>(h)->getTonemapper(); return 0; }
+
+int rth_app_environment(void* h, unsigned int* w, unsigned int* hgt, const float** texels, const float** cdfU, const float** cdfV, float* integral)
+{
+  EnvMap const* env = static_cast<Application*>(h)->getEnvironment();
+  if (!env || env->getWidth() == 0) return -1;
+  *w = env->getWidth(); *hgt = env->getHeight(); *texels = env->getTexels().data();
+  *cdfU = env->getCDF_U().data(); *cdfV = env->getCDF_V().data(); *integral = env->getIntegral();
+  return 0;
+}
+
+// --- device side (needs a GPU) ---
+unsigned int rth_app_render(void* h, unsigned int count) { return static_cast<Application*>(h)->render(count); }
+int rth_app_synchronize(void* h)
+{
+  try { static_cast<Application*>(h)->getRaytracer()->synchronize(); return 0; } catch (std::exception const& e) { g_error = e.what(); return -1; }
+}
+const float* rth_app_frame(void* h) { return static_cast<Application*>(h)->getOutputBufferHost(); }
+void rth_app_restart(void* h) { static_cast<Application*>(h)->restartAccumulation(); }
+void rth_app_set_composite(void* h, int mode) { static_cast<Application*>(h)->setCompositeMode(mode); }
+double rth_app_benchmark(void* h) { Application* app = static_cast<Application*>(h); app->benchmark(); return app->getLastBenchmarkSeconds(); }
+int rth_app_screenshot(void* h, int tonemap, char* path, int pathLen)
+{
+  std::string written;
+  const bool ok = static_cast<Application*>(h)->screenshot(tonemap != 0, &written);
+  if (path && pathLen > 0) std::snprintf(path, (size_t)pathLen, "%s", written.c_str());
+  return ok ? 0 : -1;
+}
+int rth_app_tonemap(void* h, unsigned char* rgb)
+{
+  try { std::vector<unsigned char> v; static_cast<Application*>(h)->tonemapDevice(v); std::memcpy(rgb, v.data(), v.size()); return 0; }
+  catch (std::exception const& e) { g_error = e.what(); return -1; }
+}
+rtc_context* rth_app_context(void* h, int deviceIndex)
+{
+  Raytracer* rt = static_cast<Application*>(h)->getRaytracer();
+  if (!rt || deviceIndex < 0 || (size_t)deviceIndex >= rt->m_activeDevices.size()) return nullptr;
+  return rt->m_activeDevices[deviceIndex]->getContext();
+}
+int rth_app_stats(void* h, rtc_stats* out)
+{
+  try { static_cast<Application*>(h)->getRaytracer()->getStats(*out); return 0; } catch (std::exception const& e) { g_error = e.what(); return -1; }
+}
+
+} // extern "C"
