@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- the headline measurement: 1080p samples/s (and Mrays/s) of the rtigo3 geometry scene.
+
+  python bench.py --gpus N --steps K --warmup W            the B200 core (this repository)
+  python bench.py --impl reference --gpus N ...            the scalar CPU restatement of the reference (oracle/), host cores
+
+A "step" renders `--spp-per-step` iterations (samples per pixel) of the 1920x1080 frame: generate -> [extend -> shade ->
+connect] x depth -> accumulate, i.e. one pass of the hot path over one batch of 1920*1080*spp path samples.
+
+  value     whole-job Msamples/s (pixel-samples per second / 1e6) with the scene resident in HBM, device-timed with CUDA
+            events on the launching stream, max over ranks.  N > 1: sample-range partition (each GPU renders its own
+            iteration indices over the full frame, scaling "weak") followed by ONE NCCL reduce of the accumulation
+            buffers, whose time is inside the timed region.
+  e2e       the same metric through the reference-facing classes (Application::render -> Raytracer -> Device ->
+            librtcore) with the camera uploaded from host memory and the float4 frame read back to host memory every step.
+  roofline  the extend (closest-hit traversal) kernel: algorithmic bytes (rays 48 B + nodes 80 B + triangles 48 B +
+            instance records 64 B, counted by a second, untimed pass with the same seeds) / its device time.
+  cpu_baseline  oracle/ (scalar C restatement, kind "port") on a bounded sample of the same workload, host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "rtigo3_geometry_1080p_samples_per_s"
+UNIT = "Msamples/s"
+WORKLOAD = "rtigo3 geometry scene (planes/boxes/spheres/tori, 5 BSDFs, constant env + 4x4 parallelogram light), 1920x1080, pathLengths 2 6"
+S_RAY, S_NODE, S_TRI, S_INST = 48, 80, 48, 64
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--spp-per-step", type=int, default=8)
+    ap.add_argument("--resolution", default="1920 1080")
+    ap.add_argument("--scene", default="rtigo3_geometry")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = threading.Event()
+        self.rows = []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, name in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def system_file(tmp, args, device_ordinal):
+    import helpers as H
+    return H.write_system(tmp, args.scene, resolution=args.resolution, samplesSqrt=128, devicesMask=1 << device_ordinal, strategy=0)
+
+
+def cpu_sample(args, threads, iterations=2, row_step=16, host_only_app=None):
+    """Oracle on rows y % row_step == 0 for `iterations` samples per pixel; returns (Msamples/s, seconds, description)."""
+    import helpers as H
+    from oracle import orc
+    from tweeker_raytracer_b200 import host
+    tmp = tempfile.mkdtemp()
+    app = host_only_app or host.App(system_file(tmp, args, 0), H.scene_path(args.scene), host_only=True)
+    ref = H.oracle_scene(app)
+    w, h = app.resolution
+    sysd = H.oracle_sys(app)
+    st = orc.Stats()
+    t0 = time.perf_counter()
+    ref.render(sysd, app.info.miss, w, h, iter_count=iterations, row_step=row_step, row_offset=0, threads=threads, stats=st)
+    dt = time.perf_counter() - t0
+    desc = "rows y%%%d==0 of %dx%d, %d spp = %d path samples (%d radiance + %d shadow rays) in %.2f s" % (
+        row_step, w, h, iterations, st.pathSamples, st.radianceRays, st.shadowRays, dt)
+    return st.pathSamples / dt / 1e6, dt, desc, (st.radianceRays + st.shadowRays) / dt / 1e6
+
+
+def run_reference(args, rank):
+    """The reference arm: the scalar CPU restatement (oracle/, kind "port") with every host thread, rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import orc
+    cores = orc.online_cores()
+    for _ in range(min(args.warmup, 1)):
+        cpu_sample(args, cores, iterations=1, row_step=64)
+    vals, secs, desc, mrays = [], 0.0, "", 0.0
+    for _ in range(args.steps):
+        v, dt, desc, mr = cpu_sample(args, cores, iterations=1, row_step=16)
+        vals.append(v)
+        secs += dt
+        mrays = mr
+    value = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "sample_per_step": desc},
+            "mrays_per_s": mrays,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": "each step: " + desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import helpers as H
+    from tweeker_raytracer_b200 import core, host
+
+    if core.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: " + core.lib().rtc_last_error().decode())
+    n = args.gpus
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(local_rank)
+    if world != n and world > 1:
+        n = world
+    S, K, W = args.spp_per_step, args.steps, args.warmup
+
+    tmp = tempfile.mkdtemp()
+    app = host.App(system_file(tmp, args, local_rank), H.scene_path(args.scene))
+    w, h = app.resolution
+    pixels = w * h
+    ctx = app.context(0)
+    app.render(1)                      # allocates the frame, warms the allocator
+    app.synchronize()
+    sysd = app.system_data(0)
+    info = ctx.scene_info(sysd.topObject)
+
+    # the accumulation buffer of the device-timed arm is a torch tensor so that torch.distributed (NCCL) can reduce it
+    frame = torch.zeros(pixels * 4, dtype=torch.float32, device="cuda")
+    sysd.outputBuffer = frame.data_ptr()
+
+    def step(s, count_work=False):
+        # sample-range partition: rank r of n renders iteration indices (s*n + r)*S .. +S as samples s*S.. of its own average
+        ctx.launch_ex(sysd, w, h, core.RAYGEN_FULL_FRAME, app.info.miss, (s * n + rank) * S, S, s * S, count_work)
+
+    def barrier():
+        torch.cuda.synchronize()
+        ctx.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for s in range(W):
+        step(s)
+    barrier()
+    ctx.stats_reset()
+    ctx.profile_enable(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.timer_start()
+    for s in range(W, W + K):
+        step(s)
+    steps_ms = ctx.timer_stop()
+    reduce_ms = 0.0
+    if dist is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        dist.reduce(frame, dst=0, op=dist.ReduceOp.SUM)      # NCCL over NVLink: the one exchange step of the path
+        if rank == 0:
+            frame.mul_(1.0 / n)
+        ev1.record()
+        torch.cuda.synchronize()
+        reduce_ms = ev0.elapsed_time(ev1)
+    barrier()
+    sampler.stop_flag.set()
+    sampler.join()
+    prof = ctx.profile()
+    ctx.profile_enable(False)
+    stats = ctx.stats()
+    total_ms = steps_ms + reduce_ms
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    rays = torch.tensor([float(stats.radianceRays + stats.shadowRays)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rays, op=dist.ReduceOp.SUM)
+    total_ms = float(t.item())
+    value = n * K * S * pixels / (total_ms * 1e-3) / 1e6
+    mrays = float(rays.item()) / (total_ms * 1e-3) / 1e6
+    launches = int(stats.kernelLaunches)
+
+    # ---- algorithmic bytes of the extend kernel: the same steps again, untimed, with work counters
+    ctx.launch_counts_reset()
+    for s in range(W, W + K):
+        step(s, count_work=True)
+    ext, con = ctx.launch_counts()
+    ext_bytes = ext.rays * S_RAY + ext.nodes * S_NODE + ext.tris * S_TRI + ext.instances * S_INST
+    con_bytes = con.rays * S_RAY + con.nodes * S_NODE + con.tris * S_TRI + con.instances * S_INST
+    ext_ms, ext_launches = prof["extend"]
+    con_ms, con_launches = prof["connect"]
+    peak, peak_src = measured_peak()
+    achieved = ext_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_extend<false> (closest-hit traversal of the radiance-ray queue)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": ext_bytes / max(ext_launches, 1),
+                "avg_launch_ms": ext_ms / max(ext_launches, 1), "launches": int(ext_launches),
+                "per_ray": {"nodes": ext.nodes / max(ext.rays, 1), "tris": ext.tris / max(ext.rays, 1), "instances": ext.instances / max(ext.rays, 1),
+                            "bytes": ext_bytes / max(ext.rays, 1)},
+                "extend_mrays_per_s": ext.rays / (ext_ms * 1e-3) / 1e6 if ext_ms > 0 else 0.0,
+                "connect": {"achieved": con_bytes / (con_ms * 1e-3) / 1e9 if con_ms > 0 else 0.0,
+                            "mrays_per_s": con.rays / (con_ms * 1e-3) / 1e6 if con_ms > 0 else 0.0,
+                            "bytes_per_ray": con_bytes / max(con.rays, 1)},
+                "kernel_share_of_step": {k: v[0] / max(sum(x[0] for x in prof.values()), 1e-9) for k, v in prof.items()},
+                "note": "BVH (%.1f MB) + triangles fit the 126 MB L2, so DRAM traffic is far below the algorithmic bytes; HBM peak is the contract's denominator"
+                        % ((info.numNodes * 80 + info.numTris * 48) / 1e6)}
+
+    # ---- end to end through Application::render with host buffers
+    app.restart()
+    cam = app.camera()
+    pinned = ctx.host_alloc(48)
+    import ctypes
+    ctypes.memmove(pinned, cam.ctypes.data, 48)
+    sys_host = app.system_data(0)
+    for _ in range(min(W, 3)):
+        app.render(S)
+        app.frame_view()
+    barrier()
+    t0 = time.perf_counter()
+    checksum = 0.0
+    for _ in range(K):
+        ctx.upload_async(sys_host.cameraDefinitions, pinned, 48)      # this step's camera, from pinned host memory
+        app.render(S)
+        fr = app.frame_view()                                         # device -> host read of the step's result
+        checksum += float(fr[0, 0, 0])
+    ctx.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = n * K * S * pixels / float(te.item()) / 1e6
+    ctx.host_free(pinned)
+
+    line = None
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "spp_per_step": S, "path_samples_per_step_per_gpu": S * pixels,
+                           "parallelism": "sample-range x%d + NCCL reduce" % n if n > 1 else "single GPU",
+                           "l2": "wavefront state per step (%.0f MB) exceeds L2 (126 MB); no explicit flush" % (S * pixels * 292 / 1e6),
+                           "triangles": int(info.numTris), "bvh_nodes": int(info.numNodes), "instances": int(info.numInstances)},
+                "mrays_per_s": mrays, "reduce_ms": reduce_ms,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 48 + 192, "d2h_bytes_per_step": pixels * 16},
+                "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline}
+        if n == 1 and not args.no_cpu_baseline:
+            from oracle import orc
+            cores = orc.online_cores()
+            v, dt, desc, mr = cpu_sample(args, cores, iterations=2, row_step=16)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "mrays_per_s": mr}
+        print(json.dumps(line), flush=True)
+    app.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

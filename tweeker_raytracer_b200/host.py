@@ -203,6 +203,15 @@ class App:
         w, h = self.resolution
         return _copy(p, np.float32, 4 * w * h).reshape(h, w, 4)
 
+    def frame_view(self):
+        """Like frame() but a zero-copy view of the host staging buffer (valid until the next frame call)."""
+        p = self.L.rth_app_frame(self.h)
+        if not p:
+            raise core.RtcError("getOutputBufferHost failed")
+        w, h = self.resolution
+        buf = (C.c_float * (4 * w * h)).from_address(p)
+        return np.frombuffer(buf, dtype=np.float32).reshape(h, w, 4)
+
     def restart(self):
         self.L.rth_app_restart(self.h)
 

@@ -44,6 +44,7 @@ Device::~Device()
   release(m_systemData.envCDF_U);
   release(m_systemData.envCDF_V);
   for (GeometryData& g : m_geometryData) { release(g.d_attributes); release(g.d_indices); }
+  if (m_bufferHost) { RTC_CHECK_NO_THROW(rtc_host_free(m_context, m_bufferHost)); m_bufferHost = nullptr; }
   RTC_CHECK_NO_THROW(rtc_context_destroy(m_context));
   m_context = nullptr;
 }
@@ -308,6 +309,19 @@ void Device::launch(const unsigned int launchWidth, const int raygen, const unsi
   m_systemData.iterationIndex = (int)iterationFirst;
   RTC_CHECK(rtc_launch(m_context, &m_systemData, launchWidth, (uint32_t)m_systemData.resolution.y, raygen, m_miss, (int)iterationFirst, (int)count));
   m_isDirtySystemData = false;
+}
+
+float4* Device::hostBuffer(size_t pixels)
+{
+  if (m_bufferHostPixels != pixels || m_bufferHost == nullptr)
+  {
+    if (m_bufferHost) { RTC_CHECK(rtc_synchronize(m_context)); RTC_CHECK(rtc_host_free(m_context, m_bufferHost)); m_bufferHost = nullptr; }
+    void* p = nullptr;
+    RTC_CHECK(rtc_host_alloc(m_context, sizeof(float4) * (pixels ? pixels : 1), &p));
+    m_bufferHost = static_cast<float4*>(p);
+    m_bufferHostPixels = pixels;
+  }
+  return m_bufferHost;
 }
 
 void Device::getStats(rtc_stats& stats) const { RTC_CHECK(rtc_stats_get(m_context, &stats)); }

@@ -90,5 +90,9 @@ protected:
   std::vector<GeometryData>      m_geometryData;   // indexed by sg::Triangles id
   std::vector<rtc_instance_desc> m_instances;
   std::vector<MaterialDefinition> m_materials;     // host mirror in device layout
-  std::vector<float4> m_bufferHost;
+  // host staging of the frame (the reference's std::vector<float4> m_bufferHost, DeviceSingleGPU.h:57), pinned so the
+  // device->host copy runs at full PCIe rate and asynchronously
+  float4* hostBuffer(size_t pixels);
+  float4* m_bufferHost = nullptr;
+  size_t  m_bufferHostPixels = 0;
 };

@@ -16,7 +16,7 @@ void DeviceSingleGPU::renderIterations(const unsigned int iterationFirst, const 
   if (m_isDirtyOutputBuffer)
   {
     synchronizeStream();
-    m_bufferHost.resize(framePixels(m_systemData));
+    hostBuffer(framePixels(m_systemData));
     if (m_systemData.outputBuffer) RTC_CHECK(rtc_free(m_context, m_systemData.outputBuffer));
     RTC_CHECK(rtc_malloc(m_context, sizeof(float4) * framePixels(m_systemData), &m_systemData.outputBuffer));
     RTC_CHECK(rtc_memset(m_context, m_systemData.outputBuffer, 0, sizeof(float4) * framePixels(m_systemData)));
@@ -28,11 +28,11 @@ void DeviceSingleGPU::renderIterations(const unsigned int iterationFirst, const 
 
 const void* DeviceSingleGPU::getOutputBufferHost()
 {
-  if (m_bufferHost.size() != framePixels(m_systemData)) m_bufferHost.resize(framePixels(m_systemData));
+  float4* host = hostBuffer(framePixels(m_systemData));
   if (m_systemData.outputBuffer)
-    RTC_CHECK(rtc_download(m_context, m_bufferHost.data(), m_systemData.outputBuffer, sizeof(float4) * framePixels(m_systemData)));
+    RTC_CHECK(rtc_download(m_context, host, m_systemData.outputBuffer, sizeof(float4) * framePixels(m_systemData)));
   synchronizeStream();
-  return m_bufferHost.data();
+  return host;
 }
 
 // ------------------------------------------------------------------ zero copy: every GPU accumulates into one pinned host buffer
@@ -97,7 +97,7 @@ void DeviceMultiGPUPeerAccess::renderIterations(const unsigned int iterationFirs
     MY_ASSERT(buffer != nullptr);
     if (*buffer == nullptr)
     {
-      m_bufferHost.resize(framePixels(m_systemData));
+      hostBuffer(framePixels(m_systemData));
       if (m_ownsSharedBuffer && m_systemData.outputBuffer) RTC_CHECK(rtc_free(m_context, m_systemData.outputBuffer));
       RTC_CHECK(rtc_malloc(m_context, sizeof(float4) * framePixels(m_systemData), &m_systemData.outputBuffer));
       RTC_CHECK(rtc_memset(m_context, m_systemData.outputBuffer, 0, sizeof(float4) * framePixels(m_systemData)));
@@ -118,10 +118,10 @@ void DeviceMultiGPUPeerAccess::renderIterations(const unsigned int iterationFirs
 const void* DeviceMultiGPUPeerAccess::getOutputBufferHost()
 {
   // only called on the owner, after Raytracer::synchronize() of all devices
-  if (m_bufferHost.size() != framePixels(m_systemData)) m_bufferHost.resize(framePixels(m_systemData));
-  RTC_CHECK(rtc_download(m_context, m_bufferHost.data(), m_systemData.outputBuffer, sizeof(float4) * framePixels(m_systemData)));
+  float4* host = hostBuffer(framePixels(m_systemData));
+  RTC_CHECK(rtc_download(m_context, host, m_systemData.outputBuffer, sizeof(float4) * framePixels(m_systemData)));
   synchronizeStream();
-  return m_bufferHost.data();
+  return host;
 }
 
 // ------------------------------------------------------------------ local copy: per-device texel slab, composited on the first device
@@ -152,7 +152,7 @@ void DeviceMultiGPULocalCopy::renderIterations(const unsigned int iterationFirst
     const size_t slab = sizeof(float4) * (size_t)m_launchWidth * (size_t)m_systemData.resolution.y;
     if (*buffer == nullptr)   // the device called first holds the full-resolution frame and the staging slab of the compositor
     {
-      m_bufferHost.resize(framePixels(m_systemData));
+      hostBuffer(framePixels(m_systemData));
       if (m_ownsSharedBuffer && m_systemData.outputBuffer) RTC_CHECK(rtc_free(m_context, m_systemData.outputBuffer));
       if (m_ownsSharedBuffer && m_systemData.tileBuffer) RTC_CHECK(rtc_free(m_context, m_systemData.tileBuffer));
       RTC_CHECK(rtc_malloc(m_context, sizeof(float4) * framePixels(m_systemData), &m_systemData.outputBuffer));
@@ -191,8 +191,8 @@ void DeviceMultiGPULocalCopy::compositor(Device* other)
 
 const void* DeviceMultiGPULocalCopy::getOutputBufferHost()
 {
-  if (m_bufferHost.size() != framePixels(m_systemData)) m_bufferHost.resize(framePixels(m_systemData));
-  RTC_CHECK(rtc_download(m_context, m_bufferHost.data(), m_systemData.outputBuffer, sizeof(float4) * framePixels(m_systemData)));
+  float4* host = hostBuffer(framePixels(m_systemData));
+  RTC_CHECK(rtc_download(m_context, host, m_systemData.outputBuffer, sizeof(float4) * framePixels(m_systemData)));
   synchronizeStream();
-  return m_bufferHost.data();
+  return host;
 }
