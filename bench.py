@@ -39,10 +39,10 @@ S_RAY, S_NODE, S_TRI, S_INST = 48, 80, 48, 64
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--spp-per-step", type=int, default=8)
+    ap.add_argument("--spp-per-step", type=int, default=16)
     ap.add_argument("--resolution", default="1920 1080")
     ap.add_argument("--scene", default="rtigo3_geometry")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -126,7 +126,7 @@ def run_reference(args, rank):
         cpu_sample(args, cores, iterations=1, row_step=64)
     vals, secs, desc, mrays = [], 0.0, "", 0.0
     for _ in range(args.steps):
-        v, dt, desc, mr = cpu_sample(args, cores, iterations=1, row_step=16)
+        v, dt, desc, mr = cpu_sample(args, cores, iterations=4, row_step=1)
         vals.append(v)
         secs += dt
         mrays = mr
@@ -297,7 +297,7 @@ def main():
         if n == 1 and not args.no_cpu_baseline:
             from oracle import orc
             cores = orc.online_cores()
-            v, dt, desc, mr = cpu_sample(args, cores, iterations=2, row_step=16)
+            v, dt, desc, mr = cpu_sample(args, cores, iterations=24, row_step=1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "mrays_per_s": mr}
         print(json.dumps(line), flush=True)
     app.close()
