@@ -11,20 +11,34 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-_LIB = os.path.join(_HERE, "_build", "liborc.so")
+_LIBS = {"pinned": os.path.join(_HERE, "_build", "liborc.so"), "libm": os.path.join(_HERE, "_build", "liborc_libm.so")}
+REF_LIB = os.path.join(_HERE, "_ref", "libref.so")
+REFERENCE_SHADERS = "/root/reference/apps/rtigo3/shaders"
 
 
-def build(force=False):
-    """Compiles the oracle with gcc (seconds)."""
+def build(variant="pinned", force=False):
+    """Compiles the oracle with gcc (seconds).  variant "pinned": transcendentals of include/rt_portable_math.h (what the
+    GPU kernels are compared with); "libm": libm transcendentals (what the host-compiled reference is compared with)."""
+    out = _LIBS[variant]
     src = os.path.join(_HERE, "rt_oracle.c")
     deps = [src, os.path.join(_HERE, "rt_oracle.h"), os.path.join(_ROOT, "include", "rtigo3_abi.h"),
             os.path.join(_ROOT, "include", "rt_portable_math.h")]
-    if not force and os.path.exists(_LIB) and all(os.path.getmtime(_LIB) >= os.path.getmtime(d) for d in deps):
-        return _LIB
-    os.makedirs(os.path.dirname(_LIB), exist_ok=True)
-    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-mfma", "-fPIC", "-shared", "-I" + os.path.join(_ROOT, "include"),
-                           "-I" + _HERE, "-o", _LIB, src, "-lm", "-lpthread"])
-    return _LIB
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = ["gcc", "-O2", "-ffp-contract=off", "-mfma", "-fPIC", "-shared", "-I" + os.path.join(_ROOT, "include"), "-I" + _HERE]
+    if variant == "libm":
+        cmd.append("-DRT_MATH_LIBM")
+    subprocess.check_call(cmd + ["-o", out, src, "-lm", "-lpthread"])
+    return out
+
+
+def build_reference():
+    """Compiles the reference's shader sources for the host (oracle/Makefile target `ref`).  Needs /root/reference; on a
+    machine without it the prebuilt oracle/_ref/libref.so is used as is.  Returns the library path or None."""
+    if os.path.isdir(REFERENCE_SHADERS):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+    return REF_LIB if os.path.exists(REF_LIB) else None
 
 
 class Float3(C.Structure):
@@ -78,14 +92,13 @@ LIGHT_DTYPE = np.dtype([("type", "i4"), ("position", "f4", 3), ("vecU", "f4", 3)
 CAMERA_DTYPE = np.dtype([("P", "f4", 3), ("U", "f4", 3), ("V", "f4", 3), ("W", "f4", 3)])
 assert ATTR_DTYPE.itemsize == 48 and MATERIAL_DTYPE.itemsize == 64 and LIGHT_DTYPE.itemsize == 80 and CAMERA_DTYPE.itemsize == 48
 
-_lib = None
+_loaded = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        build()
-        L = C.CDLL(_LIB)
+def lib(variant="pinned"):
+    if variant not in _loaded:
+        build(variant)
+        L = C.CDLL(_LIBS[variant], mode=C.RTLD_GLOBAL if variant == "libm" else C.RTLD_LOCAL)
         L.orc_scene_create.restype = C.c_void_p
         L.orc_scene_destroy.argtypes = [C.c_void_p]
         L.orc_scene_add_geometry.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
@@ -110,8 +123,8 @@ def lib():
         L.orc_rng.restype = C.c_float
         L.orc_online_cores.restype = C.c_int
         L.orc_uses_libm.restype = C.c_int
-        _lib = L
-    return _lib
+        _loaded[variant] = L
+    return _loaded[variant]
 
 
 def _ptr(a):
@@ -121,10 +134,12 @@ def _ptr(a):
 class Scene:
     """One oracle scene: geometries, instances, materials, lights, camera, optional environment."""
 
-    def __init__(self):
-        self.L = lib()
+    def __init__(self, variant="pinned"):
+        self.L = lib(variant)
+        self.variant = variant
         self.h = C.c_void_p(self.L.orc_scene_create())
         self.num_instances = 0
+        self.keep = {"geometries": [], "instances": []}   # host arrays the reference driver points into
 
     def close(self):
         if self.h:
@@ -140,23 +155,28 @@ class Scene:
     def add_geometry(self, attrs, indices):
         attrs = np.ascontiguousarray(attrs, dtype=ATTR_DTYPE)
         indices = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+        self.keep["geometries"].append((attrs, indices))
         return self.L.orc_scene_add_geometry(self.h, _ptr(attrs), len(attrs), _ptr(indices), len(indices) // 3)
 
     def add_instance(self, transform, geometry, material, light=-1):
         t = np.ascontiguousarray(transform, dtype=np.float32).reshape(12)
         self.num_instances += 1
+        self.keep["instances"].append((t.copy(), int(geometry), int(material), int(light)))
         return self.L.orc_scene_add_instance(self.h, _ptr(t), int(geometry), int(material), int(light))
 
     def set_materials(self, materials):
         m = np.ascontiguousarray(materials, dtype=MATERIAL_DTYPE)
+        self.keep["materials"] = m
         self.L.orc_scene_set_materials(self.h, _ptr(m), len(m))
 
     def set_lights(self, lights):
         l = np.ascontiguousarray(lights, dtype=LIGHT_DTYPE)
+        self.keep["lights"] = l
         self.L.orc_scene_set_lights(self.h, _ptr(l), len(l))
 
     def set_camera(self, camera):
         c = np.ascontiguousarray(camera, dtype=CAMERA_DTYPE).reshape(1)
+        self.keep["camera"] = c
         self.L.orc_scene_set_camera(self.h, _ptr(c))
 
     def set_env(self, rgba, cdf_u, cdf_v, integral):
@@ -164,6 +184,7 @@ class Scene:
         h, w = rgba.shape[0], rgba.shape[1]
         cu = np.ascontiguousarray(cdf_u, dtype=np.float32)
         cv = np.ascontiguousarray(cdf_v, dtype=np.float32)
+        self.keep["env"] = (rgba, cu, cv, float(integral))
         self.L.orc_scene_set_env(self.h, _ptr(rgba), w, h, _ptr(cu), _ptr(cv), C.c_float(integral))
 
     def commit(self):
@@ -206,6 +227,54 @@ class Scene:
         self.L.orc_path_radiance(self.h, C.byref(sys), miss, launch_width, _ptr(xy), len(xy), iteration, _ptr(out),
                                  C.byref(stats) if stats is not None else None)
         return out
+
+
+class Reference:
+    """The reference's own device programs, host-compiled (oracle/_ref/libref.so), driven one launch index at a time.
+    `scene` must be a committed Scene(variant="libm"): it serves optixTrace and keeps the arrays the programs read."""
+
+    def __init__(self, scene, miss):
+        if scene.variant != "libm":
+            raise ValueError("the reference driver links the libm oracle")
+        path = build_reference()
+        if path is None:
+            raise FileNotFoundError("oracle/_ref/libref.so is not built and /root/reference is absent")
+        self.scene = scene
+        R = C.CDLL(path)
+        R.ref_setup.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_float]
+        R.ref_render.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        R.ref_tea4.argtypes = [C.c_uint, C.c_uint]
+        R.ref_tea4.restype = C.c_uint
+        R.ref_rng.argtypes = [C.POINTER(C.c_uint)]
+        R.ref_rng.restype = C.c_float
+        self.R = R
+        k = scene.keep
+        n = len(k["instances"])
+        self.attr_ptrs = (C.c_void_p * n)(*[k["geometries"][g][0].ctypes.data for (_, g, _, _) in k["instances"]])
+        self.index_ptrs = (C.c_void_p * n)(*[k["geometries"][g][1].ctypes.data for (_, g, _, _) in k["instances"]])
+        self.mat = np.array([m for (_, _, m, _) in k["instances"]], dtype=np.int32)
+        self.light = np.array([l for (_, _, _, l) in k["instances"]], dtype=np.int32)
+        self.xf = np.concatenate([t for (t, _, _, _) in k["instances"]]).astype(np.float32) if n else np.zeros(0, np.float32)
+        env = k.get("env")
+        lights = k.get("lights")
+        R.ref_setup(scene.h, miss, n, self.attr_ptrs, self.index_ptrs, _ptr(self.mat), _ptr(self.light), _ptr(self.xf),
+                    _ptr(k["camera"]), _ptr(lights) if lights is not None and len(lights) else None, _ptr(k["materials"]),
+                    _ptr(env[0]) if env else None, env[0].shape[1] if env else 0, env[0].shape[0] if env else 0,
+                    _ptr(env[1]) if env else None, _ptr(env[2]) if env else None, C.c_float(env[3] if env else 1.0))
+
+    def render(self, sys, launch_width, launch_height, local_copy=False, iter_first=0, iter_count=1):
+        n = launch_width * launch_height if local_copy else sys.resolution.x * sys.resolution.y
+        buffer = np.zeros((n, 4), dtype=np.float32)
+        self.R.ref_render(C.byref(sys), launch_width, launch_height, 1 if local_copy else 0, iter_first, iter_count, _ptr(buffer))
+        return buffer
+
+    def tea4(self, a, b):
+        return self.R.ref_tea4(a & 0xffffffff, b & 0xffffffff)
+
+    def rng_sequence(self, seed, n):
+        s = C.c_uint(seed)
+        return [self.R.ref_rng(C.byref(s)) for _ in range(n)], s.value
 
 
 def tea4(v0, v1):

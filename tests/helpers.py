@@ -43,9 +43,9 @@ def scene_path(name):
     return os.path.join(SCENES, "scene_%s.txt" % name)
 
 
-def oracle_scene(app):
+def oracle_scene(app, variant="pinned"):
     """Feeds the scene an App loaded (geometries, flattened instances, materials, lights, camera, environment) to the oracle."""
-    s = orc.Scene()
+    s = orc.Scene(variant)
     for g in range(app.info.numGeometries):
         attrs, idx = app.geometry(g)
         s.add_geometry(attrs, idx)

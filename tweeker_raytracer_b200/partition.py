@@ -1,0 +1,42 @@
+"""Work partition of one render across GPUs (one process per GPU).  Pure index arithmetic, no device code.
+
+Two partitions of the same job:
+
+  * tile partition  -- the reference's strategies 1-3: a checkerboard of tileSize tiles, row yBlock rotated by the device
+    index (apps/rtigo3/shaders/raygeneration.cu:152-164); each device launches `launch_width` columns
+    (apps/rtigo3/src/DeviceMultiGPULocalCopy.cpp:91-93).  Seeds depend on the device layout.
+  * sample-range partition -- device r of n renders iteration indices (step*n + r)*spp .. +spp over the whole frame and
+    keeps its OWN running average (accumulation index counts from 0); the frame is the mean of the n averages, obtained
+    with one NCCL reduce(sum) and a scale by 1/n.  Seeds are the single-GPU ones.
+"""
+
+
+def tiled_launch_width(resolution_x, device_count, tile_size_x):
+    width = (resolution_x + device_count - 1) // device_count
+    mask = tile_size_x - 1
+    return (width + mask) & ~mask
+
+
+def tile_shift(tile_size):
+    shift = 0
+    while shift < 32 and (tile_size & (1 << shift)) == 0:
+        shift += 1
+    return shift
+
+
+def distribute(x, y, device_index, device_count, tile_size_x, tile_shift_x, tile_shift_y):
+    """Launch index (x, y) of one device -> pixel column (raygeneration.cu:152-164)."""
+    x_block = x >> tile_shift_x
+    y_block = y >> tile_shift_y
+    x_tile = x_block * device_count + ((device_index + y_block) % device_count)
+    return x_tile * tile_size_x + (x & (tile_size_x - 1))
+
+
+def sample_range(step, rank, world, spp_per_step):
+    """(first seed iteration, count, first accumulation index) of `rank` in `step`."""
+    return (step * world + rank) * spp_per_step, spp_per_step, step * spp_per_step
+
+
+def combine_scale(world):
+    """Factor applied after the sum-reduce of the per-rank running averages."""
+    return 1.0 / world
