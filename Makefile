@@ -9,6 +9,8 @@ INC       := -Iinclude -I$(CSRC)
 NVFLAGS   := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC $(INC)
 CXXFLAGS  := -O2 -std=c++17 -fPIC -ffp-contract=off $(INC) -I/usr/local/cuda/include -Wall
 
+# e.g. make TRACE_DEFS='-DRTC_TRACE_MIN_BLOCKS=5 -DRTC_FETCH_THRESHOLD=16' to explore the traversal kernel's tuning knobs
+TRACE_DEFS ?=
 CORE_OBJS := $(LIB)/kernels_trace.o $(LIB)/kernels_shade.o $(LIB)/bvh_build_gpu.o $(LIB)/rtc_api.o $(LIB)/bvh_build_host.o
 
 all: core host oracle
@@ -16,7 +18,7 @@ all: core host oracle
 core: $(LIB)/librtcore.so
 
 $(LIB)/kernels_trace.o: $(CSRC)/kernels_trace.cu $(CSRC)/trace.cuh $(CSRC)/rtc_internal.h include/rtc_core.h include/rtigo3_abi.h
-	$(NVCC) $(NVFLAGS) -c $< -o $@
+	$(NVCC) $(NVFLAGS) $(TRACE_DEFS) -c $< -o $@
 # shading: FMA contraction off, IEEE division/sqrt -- bit-exact against the scalar oracle
 $(LIB)/kernels_shade.o: $(CSRC)/kernels_shade.cu $(CSRC)/shade.cuh $(CSRC)/rtc_internal.h include/rtc_core.h include/rtigo3_abi.h include/rt_portable_math.h
 	$(NVCC) $(NVFLAGS) -fmad=false -prec-div=true -prec-sqrt=true -c $< -o $@

@@ -484,12 +484,12 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
     uint32_t* qIn = ctx->wf.queueA; uint32_t* qOut = ctx->wf.queueB;
     for (int d = 0; d < maxDepth; ++d)
     {
-      if (int rc = launch_extend(ctx, &scene->desc, ctx->wf, qIn, cnt + d, countWork)) return rc;
+      if (int rc = launch_extend(ctx, &scene->desc, ctx->wf, qIn, cnt + d, cnt + 128 + d, countWork)) return rc;
       if (int rc = profile_begin(ctx, RTC_KERNEL_SHADE)) return rc;
       k_shade<<<gridShade, kBlock, 0, ctx->stream>>>(a, scene->desc, qIn, cnt + d, qOut, cnt + d + 1, ctx->wf.shadowQueue, cnt + 64 + d);
       ctx->kernelLaunches++;
       if (int rc = profile_end(ctx)) return rc;
-      if (sys.numLights > 0) { if (int rc = launch_connect(ctx, &scene->desc, ctx->wf, cnt + 64 + d, countWork)) return rc; }
+      if (sys.numLights > 0) { if (int rc = launch_connect(ctx, &scene->desc, ctx->wf, cnt + 64 + d, cnt + 192 + d, countWork)) return rc; }
       uint32_t* t = qIn; qIn = qOut; qOut = t;
     }
     if (int rc = profile_begin(ctx, RTC_KERNEL_ACCUMULATE)) return rc;

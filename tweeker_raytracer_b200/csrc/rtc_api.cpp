@@ -128,6 +128,7 @@ int rtc_context_create(int deviceOrdinal, rtc_context** out)
   RTC_CUDA(cudaEventCreate(&ctx->evTimerB));
   RTC_CUDA(cudaMalloc(&ctx->d_stats, 8 * sizeof(uint64_t)));
   RTC_CUDA(cudaMemset(ctx->d_stats, 0, 8 * sizeof(uint64_t)));
+  RTC_CUDA(cudaMalloc(&ctx->d_cursor, 4 * sizeof(uint32_t)));
   RTC_CUDA(cudaMalloc(&ctx->d_launchCounts, 8 * sizeof(unsigned long long)));
   RTC_CUDA(cudaMemset(ctx->d_launchCounts, 0, 8 * sizeof(unsigned long long)));
   *out = ctx;
@@ -144,6 +145,7 @@ int rtc_context_destroy(rtc_context* ctx)
   if (ctx->wf.base) cudaFree(ctx->wf.base);
   cudaFree(ctx->d_stats);
   cudaFree(ctx->d_launchCounts);
+  cudaFree(ctx->d_cursor);
   for (rtc_context::ProfileSpan& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
   cudaEventDestroy(ctx->evA); cudaEventDestroy(ctx->evB);

@@ -104,7 +104,8 @@ struct WavefrontBuffers
   float4 *absStack = nullptr;                      // per path x 4: nested-volume stack
   float4 *shadowOrg = nullptr, *shadowDir = nullptr, *shadowContrib = nullptr;  // per path
   uint32_t *queueA = nullptr, *queueB = nullptr, *shadowQueue = nullptr;
-  uint32_t *counters = nullptr;                    // [0..63] extend counts per depth, [64..127] shadow counts per depth, 128.. stats
+  uint32_t *counters = nullptr;                    // [0..63] extend counts per depth, [64..127] shadow counts per depth,
+                                                   // [128..191] extend ray cursors, [192..255] connect ray cursors
   void* base = nullptr;
 };
 
@@ -129,6 +130,7 @@ struct rtc_context
   std::vector<cudaEvent_t> eventPool;
   rtc_profile profile{};
   unsigned long long* d_launchCounts = nullptr;   // 2 x {nodes, tris, insts, rays}: extend, connect
+  uint32_t* d_cursor = nullptr;                   // ray cursor of the query kernels (rtc_trace_*)
 };
 
 // RAII-less helpers used by the launchers: bracket one kernel launch with an event pair when profiling is on
@@ -150,8 +152,10 @@ int launch_trace_closest(rtc_context* ctx, const SceneDesc* d_scene, const rtc_r
 int launch_trace_any(rtc_context* ctx, const SceneDesc* d_scene, const rtc_ray* rays, uint64_t n, uint32_t* occluded);
 // counting variant: adds {nodes popped, triangles tested, instances entered, rays} to d_counts[0..3]
 int launch_trace_count(rtc_context* ctx, const SceneDesc* d_scene, const rtc_ray* rays, uint64_t n, int anyHit, unsigned long long* d_counts);
-int launch_extend(rtc_context* ctx, const SceneDesc* d_scene, const WavefrontBuffers& wf, const uint32_t* queue, const uint32_t* count, bool countWork);
-int launch_connect(rtc_context* ctx, const SceneDesc* d_scene, const WavefrontBuffers& wf, const uint32_t* count, bool countWork);
+// cursor: zero-initialised device counter the persistent warps hand rays out from (one per launch)
+int launch_extend(rtc_context* ctx, const SceneDesc* d_scene, const WavefrontBuffers& wf, const uint32_t* queue, const uint32_t* count,
+                  uint32_t* cursor, bool countWork);
+int launch_connect(rtc_context* ctx, const SceneDesc* d_scene, const WavefrontBuffers& wf, const uint32_t* count, uint32_t* cursor, bool countWork);
 int launch_generate_primary(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uint32_t h, int iteration, rtc_ray* rays);
 int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uint32_t h, int raygen, int miss, int iterFirst, int iterCount,
                      int accumFirst, bool countWork);

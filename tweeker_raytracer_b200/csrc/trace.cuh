@@ -12,7 +12,9 @@
 
 #include "rtc_internal.h"
 
-#define RTC_STACK_SIZE 40
+#ifndef RTC_FETCH_THRESHOLD
+#define RTC_FETCH_THRESHOLD 8     // refill a warp when at least this many lanes have finished their ray
+#endif
 
 struct TraceHit
 {
@@ -72,120 +74,164 @@ __device__ __forceinline__ bool tri_test(const ObjRay& r, const float4 v0, const
   return true;
 }
 
-// Per-space constants of the box test: t = q * adj + org per plane.
+// Per-space constants of the box test.
 struct BoxRay
 {
-  float idx, idy, idz;       // 1/d with |d| clamped to 2^-80
+  float idx, idy, idz;       // 1/d (approximate reciprocal; the box test only has to be conservative), |d| clamped to 2^-80
   float ox, oy, oz;          // origin
   uint32_t octinv;           // 7 ^ octant, octant bit2 = dx<0, bit1 = dy<0, bit0 = dz<0
 };
 
-__device__ __forceinline__ float safe_rcp(float d)
+__device__ __forceinline__ float fast_rcp(float d)
 {
   if (fabsf(d) < 0x1p-80f) d = copysignf(0x1p-80f, d);
-  return __fdiv_rn(1.0f, d);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return r;
 }
 
 __device__ __forceinline__ void box_setup(BoxRay& b, float ox, float oy, float oz, float dx, float dy, float dz)
 {
-  b.idx = safe_rcp(dx); b.idy = safe_rcp(dy); b.idz = safe_rcp(dz);
+  b.idx = fast_rcp(dx); b.idy = fast_rcp(dy); b.idz = fast_rcp(dz);
   b.ox = ox; b.oy = oy; b.oz = oz;
   const uint32_t oct = ((dx < 0.0f) ? 4u : 0u) | ((dy < 0.0f) ? 2u : 0u) | ((dz < 0.0f) ? 1u : 0u);
   b.octinv = 7u ^ oct;
 }
 
-__device__ __forceinline__ float byte_f(uint32_t w, int i) { return (float)((w >> (8 * i)) & 0xffu); }
+// 32768 + q as a float, q = byte i of w: one PRMT drops the byte into mantissa bits 8..15 of 0x47000000 (= 32768.0f),
+// which replaces the shift/mask/I2F triple of a plain conversion.  The plane parameter is then ONE fma:
+//   t = (32768 + q) * adj + (org - 32768 * adj),   adj = gridStep / d,  org = (p - o) / d.
+// The cancellation costs at most 2^-9 grid steps, an eighth of the 1/64 step slack the builder guarantees.
+__device__ __forceinline__ float quant_f(uint32_t w, uint32_t i) { return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7404u | (i << 4))); }
 
-// Tests the 8 quantised child boxes of one node; returns the hit mask:
-// bits 24..31 inner children at priority (slot ^ octinv), bits 0..23 leaf primitives (relative to triBase).
-__device__ __forceinline__ uint32_t node_test(const BoxRay& b, const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4,
-                                              float tmin, float tmax)
+// Tests the 8 quantised child boxes of one node.  Returns bit s set when the box in slot s is hit.
+__device__ __forceinline__ uint32_t node_test(const BoxRay& b, const uint4 n0, const uint4 n2, const uint4 n3, const uint4 n4,
+                                              float tmin, float tlimit)
 {
   const uint32_t e = n0.w;
-  const float sx = __uint_as_float((e & 0xffu) << 23), sy = __uint_as_float(((e >> 8) & 0xffu) << 23), sz = __uint_as_float(((e >> 16) & 0xffu) << 23);
-  const uint32_t imask = e >> 24;
-  const float adjx = sx * b.idx, adjy = sy * b.idy, adjz = sz * b.idz;
-  const float orgx = (__uint_as_float(n0.x) - b.ox) * b.idx;
-  const float orgy = (__uint_as_float(n0.y) - b.oy) * b.idy;
-  const float orgz = (__uint_as_float(n0.z) - b.oz) * b.idz;
+  const float adjx = __uint_as_float((e & 0xffu) << 23) * b.idx;
+  const float adjy = __uint_as_float(((e >> 8) & 0xffu) << 23) * b.idy;
+  const float adjz = __uint_as_float(((e >> 16) & 0xffu) << 23) * b.idz;
+  const float orgx = fmaf(-32768.0f, adjx, (__uint_as_float(n0.x) - b.ox) * b.idx);
+  const float orgy = fmaf(-32768.0f, adjy, (__uint_as_float(n0.y) - b.oy) * b.idy);
+  const float orgz = fmaf(-32768.0f, adjz, (__uint_as_float(n0.z) - b.oz) * b.idz);
   // near/far plane words per axis, selected by the direction sign
-  const bool nx = b.idx < 0.0f, ny = b.idy < 0.0f, nz = b.idz < 0.0f;
   // layout: n2 = qlox[0..3], qlox[4..7], qloy[0..3], qloy[4..7]; n3 = qloz, qhix; n4 = qhiy, qhiz
-  const uint32_t lox0 = n2.x, lox1 = n2.y, loy0 = n2.z, loy1 = n2.w;
-  const uint32_t loz0 = n3.x, loz1 = n3.y, hix0 = n3.z, hix1 = n3.w;
-  const uint32_t hiy0 = n4.x, hiy1 = n4.y, hiz0 = n4.z, hiz1 = n4.w;
-  const uint32_t nearx0 = nx ? hix0 : lox0, nearx1 = nx ? hix1 : lox1, farx0 = nx ? lox0 : hix0, farx1 = nx ? lox1 : hix1;
-  const uint32_t neary0 = ny ? hiy0 : loy0, neary1 = ny ? hiy1 : loy1, fary0 = ny ? loy0 : hiy0, fary1 = ny ? loy1 : hiy1;
-  const uint32_t nearz0 = nz ? hiz0 : loz0, nearz1 = nz ? hiz1 : loz1, farz0 = nz ? loz0 : hiz0, farz1 = nz ? loz1 : hiz1;
-  const uint32_t meta0 = n1.z, meta1 = n1.w;
-  const float tmaxPad = tmax * (1.0f + 0x1p-17f);
-  uint32_t mask = 0;
+  const bool nx = b.idx < 0.0f, ny = b.idy < 0.0f, nz = b.idz < 0.0f;
+  const uint32_t nearx[2] = { nx ? n3.z : n2.x, nx ? n3.w : n2.y }, farx[2] = { nx ? n2.x : n3.z, nx ? n2.y : n3.w };
+  const uint32_t neary[2] = { ny ? n4.x : n2.z, ny ? n4.y : n2.w }, fary[2] = { ny ? n2.z : n4.x, ny ? n2.w : n4.y };
+  const uint32_t nearz[2] = { nz ? n4.z : n3.x, nz ? n4.w : n3.y }, farz[2] = { nz ? n3.x : n4.z, nz ? n3.y : n4.w };
+  const float tlimitPad = tlimit * (1.0f + 0x1p-17f);
+  uint32_t hits = 0;
 #pragma unroll
   for (int s = 0; s < 8; ++s)
   {
-    const int i = s & 3;
-    const uint32_t wnx = (s < 4) ? nearx0 : nearx1, wfx = (s < 4) ? farx0 : farx1;
-    const uint32_t wny = (s < 4) ? neary0 : neary1, wfy = (s < 4) ? fary0 : fary1;
-    const uint32_t wnz = (s < 4) ? nearz0 : nearz1, wfz = (s < 4) ? farz0 : farz1;
-    const float t0x = fmaf(byte_f(wnx, i), adjx, orgx), t1x = fmaf(byte_f(wfx, i), adjx, orgx);
-    const float t0y = fmaf(byte_f(wny, i), adjy, orgy), t1y = fmaf(byte_f(wfy, i), adjy, orgy);
-    const float t0z = fmaf(byte_f(wnz, i), adjz, orgz), t1z = fmaf(byte_f(wfz, i), adjz, orgz);
-    const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
-    const float tf = fminf(fminf(t1x, t1y), t1z) * (1.0f + 0x1p-17f);
-    const uint32_t meta = (((s < 4) ? meta0 : meta1) >> (8 * i)) & 0xffu;
-    const bool inner = (imask >> s) & 1u;
-    if (tn <= fminf(tf, tmaxPad) && (inner || meta != 0u))
-    {
-      if (inner) mask |= 1u << (24u + ((uint32_t)s ^ b.octinv));
-      else       mask |= ((1u << (meta >> 5)) - 1u) << (meta & 31u);
-    }
+    const int h = s >> 2;
+    const uint32_t i = (uint32_t)(s & 3);
+    const float t0x = fmaf(quant_f(nearx[h], i), adjx, orgx), t1x = fmaf(quant_f(farx[h], i), adjx, orgx);
+    const float t0y = fmaf(quant_f(neary[h], i), adjy, orgy), t1y = fmaf(quant_f(fary[h], i), adjy, orgy);
+    const float t0z = fmaf(quant_f(nearz[h], i), adjz, orgz), t1z = fmaf(quant_f(farz[h], i), adjz, orgz);
+    const float tn = fmaxf(fmaxf(fmaxf(t0x, t0y), t0z), tmin);
+    const float tf = fminf(fminf(fminf(t1x, t1y), t1z) * (1.0f + 0x1p-17f), tlimitPad);
+    if (tn <= tf) hits |= 1u << s;
   }
-  return mask;
+  return hits;
+}
+
+// bit s of an 8-bit mask -> bit (s ^ x)
+__device__ __forceinline__ uint32_t xor_permute8(uint32_t h, uint32_t x)
+{
+  if (x & 1u) h = ((h & 0xAAu) >> 1) | ((h & 0x55u) << 1);
+  if (x & 2u) h = ((h & 0xCCu) >> 2) | ((h & 0x33u) << 2);
+  if (x & 4u) h = ((h & 0xF0u) >> 4) | ((h & 0x0Fu) << 4);
+  return h;
 }
 
 // Per-ray work counters of the counting variant (the algorithmic-bytes figure of DESIGN.md section 5).
 struct TraceCounts { uint32_t nodes, tris, insts; };
 
-// Closest hit (ANY = false) or first hit (ANY = true) of one ray against the two-level scene.
-// Closest hit: smallest t in (tmin, tmax), ties -> smaller (instance, primitive).
-template <bool ANY, bool COUNT = false>
-__device__ __forceinline__ bool trace_ray(const SceneDesc& sc, const float4 org, const float4 dir, TraceHit& hit,
-                                          TraceCounts* counts = nullptr)
+#define RTC_SM_STACK 8        // traversal stack entries per thread kept in shared memory
+#define RTC_LM_STACK 32       // overflow entries in local memory (never reached by the in-scope scenes)
+
+// One ray's traversal as a resumable state machine: begin() once, then step() until it returns false.
+// A step visits one wide node (or pops a postponed leaf group) and tests the triangles / enters the instance it yields.
+// Closest hit (ANY = false): smallest t in (tmin, tmax), ties -> smaller (instance, primitive).  ANY = true: first hit ends the ray.
+template <bool ANY, bool COUNT, int BLOCK>
+struct Traversal
 {
-  const float tmin = org.w;
-  float tlimit = dir.w;               // current far bound (shrinks to the best t for closest hit)
-  bool found = false;
-  hit.t = -1.0f; hit.u = 0.0f; hit.v = 0.0f; hit.inst = 0xffffffffu; hit.prim = 0xffffffffu;
-  if (!(tlimit > tmin)) return false;
-
-  uint2 stack[RTC_STACK_SIZE];
-  int sp = 0;
-  int blasBase = -1;                  // >= 0 while inside an instance: stack height at entry
-  uint32_t curInst = 0;
+  // world ray
+  float4 org, dir;
+  float tlimit;
+  bool found;
+  TraceHit hit;
+  // traversal state
+  uint2 nodeGroup, triGroup;
+  int sp, blasBase;
+  uint32_t curInst;
   BoxRay br;
-  box_setup(br, org.x, org.y, org.z, dir.x, dir.y, dir.z);
   ObjRay orr;
-  const uint4*  nodes = sc.tlasNodes; // node array of the current level
-  const float4* tris = nullptr;       // triangle array of the current GAS
+  const uint4*  nodes;
+  const float4* tris;
+  uint2* smStack;             // this thread's column of the shared stack: entry k at smStack[k * BLOCK]
+  uint2* lmStack;             // overflow entries (a local array owned by the caller)
+  TraceCounts counts;
 
-  uint2 nodeGroup = make_uint2(0u, 0x80000000u);
-  uint2 triGroup = make_uint2(0u, 0u);
-
-  for (;;)
+  __device__ __forceinline__ void push(uint2 v)
   {
+    if (sp < RTC_SM_STACK) smStack[sp * BLOCK] = v;
+    else if (sp < RTC_SM_STACK + RTC_LM_STACK) lmStack[sp - RTC_SM_STACK] = v;
+    ++sp;
+  }
+  __device__ __forceinline__ uint2 pop()
+  {
+    --sp;
+    return (sp < RTC_SM_STACK) ? smStack[sp * BLOCK] : lmStack[(sp - RTC_SM_STACK) & (RTC_LM_STACK - 1)];
+  }
+
+  // returns false when the ray interval is empty (nothing to traverse)
+  __device__ __forceinline__ bool begin(const SceneDesc& sc, const float4 o, const float4 d)
+  {
+    org = o; dir = d;
+    tlimit = d.w;
+    found = false;
+    hit.t = -1.0f; hit.u = 0.0f; hit.v = 0.0f; hit.inst = 0xffffffffu; hit.prim = 0xffffffffu;
+    if (COUNT) { counts.nodes = 0; counts.tris = 0; counts.insts = 0; }
+    if (!(tlimit > o.w)) return false;
+    sp = 0; blasBase = -1; curInst = 0;
+    box_setup(br, o.x, o.y, o.z, d.x, d.y, d.z);
+    nodes = sc.tlasNodes; tris = nullptr;
+    nodeGroup = make_uint2(0u, 0x80000000u);
+    triGroup = make_uint2(0u, 0u);
+    return true;
+  }
+
+  // returns true while the ray needs more steps
+  __device__ __forceinline__ bool step(const SceneDesc& sc)
+  {
+    const float tmin = org.w;
     if (nodeGroup.y & 0xff000000u)
     {
       const uint32_t bit = 31u - (uint32_t)__clz((int)nodeGroup.y);
       nodeGroup.y &= ~(1u << bit);
-      if (nodeGroup.y & 0xff000000u) { if (sp < RTC_STACK_SIZE) stack[sp++] = nodeGroup; }
+      if (nodeGroup.y & 0xff000000u) push(nodeGroup);
       const uint32_t slot = (bit - 24u) ^ br.octinv;
       const uint32_t rel = (uint32_t)__popc(nodeGroup.y & 0xffu & ((1u << slot) - 1u));
       const uint4* np = nodes + (size_t)(nodeGroup.x + rel) * 5u;
       const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-      if (COUNT) counts->nodes++;
-      const uint32_t m = node_test(br, n0, n1, n2, n3, n4, tmin, tlimit);
-      nodeGroup = make_uint2(n1.x, (m & 0xff000000u) | (n0.w >> 24));
-      triGroup = make_uint2(n1.y, m & 0x00ffffffu);
+      if (COUNT) counts.nodes++;
+      const uint32_t hits = node_test(br, n0, n2, n3, n4, tmin, tlimit);
+      const uint32_t imask = n0.w >> 24;
+      nodeGroup = make_uint2(n1.x, (xor_permute8(hits & imask, br.octinv) << 24) | imask);
+      // leaf children: meta = (count << 5) | first primitive (relative to triBase)
+      uint32_t leaf = hits & ~imask, primMask = 0u;
+      while (leaf)
+      {
+        const uint32_t s = (uint32_t)__ffs((int)leaf) - 1u;
+        leaf &= leaf - 1u;
+        const uint32_t meta = (((s < 4u) ? n1.z : n1.w) >> (8u * (s & 3u))) & 0xffu;
+        primMask |= ((1u << (meta >> 5)) - 1u) << (meta & 31u);
+      }
+      triGroup = make_uint2(n1.y, primMask);
     }
     else
     {
@@ -201,11 +247,11 @@ __device__ __forceinline__ bool trace_ray(const SceneDesc& sc, const float4 org,
       {
         // instance-level leaf: enter the instance
         const uint32_t inst = __ldg(sc.tlasLeaves + triGroup.x + idx);
-        if (triGroup.y) { if (sp < RTC_STACK_SIZE) stack[sp++] = triGroup; }
-        if (nodeGroup.y & 0xff000000u) { if (sp < RTC_STACK_SIZE) stack[sp++] = nodeGroup; }
+        if (triGroup.y) push(triGroup);
+        if (nodeGroup.y & 0xff000000u) push(nodeGroup);
         const float4* ip = sc.instances + (size_t)inst * 4u;
         const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
-        if (COUNT) counts->insts++;
+        if (COUNT) counts.insts++;
         orr.ox = __fmaf_rn(r0.x, org.x, __fmaf_rn(r0.y, org.y, __fmaf_rn(r0.z, org.z, r0.w)));
         orr.oy = __fmaf_rn(r1.x, org.x, __fmaf_rn(r1.y, org.y, __fmaf_rn(r1.z, org.z, r1.w)));
         orr.oz = __fmaf_rn(r2.x, org.x, __fmaf_rn(r2.y, org.y, __fmaf_rn(r2.z, org.z, r2.w)));
@@ -226,14 +272,14 @@ __device__ __forceinline__ bool trace_ray(const SceneDesc& sc, const float4 org,
       {
         const float4* tp = tris + (size_t)(triGroup.x + idx) * 3u;
         const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
-        if (COUNT) counts->tris++;
+        if (COUNT) counts.tris++;
         float t, det, V, W;
         if (tri_test(orr, v0, v1, v2, t, det, V, W) && t > tmin)
         {
           const uint32_t prim = __float_as_uint(v0.w);
           if (ANY)
           {
-            if (t < tlimit) { hit.t = t; hit.inst = curInst; hit.prim = prim; return true; }
+            if (t < tlimit) { hit.t = t; hit.inst = curInst; hit.prim = prim; found = true; return false; }
           }
           else
           {
@@ -257,9 +303,74 @@ __device__ __forceinline__ bool trace_ray(const SceneDesc& sc, const float4 org,
         nodes = sc.tlasNodes;
         box_setup(br, org.x, org.y, org.z, dir.x, dir.y, dir.z);
       }
-      if (sp == 0) break;
-      nodeGroup = stack[--sp];
+      if (sp == 0) return false;
+      nodeGroup = pop();
+    }
+    return true;
+  }
+};
+
+// Persistent-warp driver: every lane owns one ray at a time; lanes whose ray has finished take the next ray index from a
+// global cursor (one atomicAdd per warp and refill), so short rays do not leave their lanes idle while the longest ray of
+// the warp finishes.  Policy supplies load(i, org, dir) -> bool (false: skip this index) and store(i, traversal).
+template <bool ANY, bool COUNT, int BLOCK, class Policy>
+__device__ __forceinline__ void trace_stream(const SceneDesc& sc, uint32_t n, uint32_t* __restrict__ cursor, Policy& policy, uint2* smem,
+                                             unsigned long long* __restrict__ countsOut)
+{
+  Traversal<ANY, COUNT, BLOCK> tr;
+  uint2 overflow[RTC_LM_STACK];
+  tr.smStack = smem + threadIdx.x;
+  tr.lmStack = overflow;
+  const uint32_t lane = threadIdx.x & 31u;
+  bool active = false, exhausted = false;
+  uint32_t index = 0;
+  unsigned long long cNodes = 0, cTris = 0, cInsts = 0, cRays = 0;
+  for (;;)
+  {
+    const uint32_t idle = __ballot_sync(0xffffffffu, !active);
+    if (idle && !exhausted && (idle == 0xffffffffu || __popc(idle) >= RTC_FETCH_THRESHOLD))
+    {
+      const uint32_t want = (uint32_t)__popc(idle);
+      const uint32_t leader = (uint32_t)__ffs((int)idle) - 1u;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(cursor, want);
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (base + want >= n) exhausted = true;
+      if (!active)
+      {
+        index = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+        if (index < n)
+        {
+          float4 o, d;
+          if (policy.load(index, o, d))
+          {
+            if (tr.begin(sc, o, d)) active = true;
+            else { policy.store(index, tr); if (COUNT) cRays++; }
+          }
+        }
+      }
+    }
+    else if (idle == 0xffffffffu) break;      // nothing running and nothing left to fetch
+    if (active)
+    {
+      if (!tr.step(sc))
+      {
+        policy.store(index, tr);
+        if (COUNT) { cNodes += tr.counts.nodes; cTris += tr.counts.tris; cInsts += tr.counts.insts; cRays++; }
+        active = false;
+      }
     }
   }
-  return found;
+  if (COUNT)
+  {
+    for (int off = 16; off; off >>= 1)
+    {
+      cNodes += __shfl_down_sync(0xffffffffu, cNodes, off); cTris += __shfl_down_sync(0xffffffffu, cTris, off);
+      cInsts += __shfl_down_sync(0xffffffffu, cInsts, off); cRays += __shfl_down_sync(0xffffffffu, cRays, off);
+    }
+    if (lane == 0 && cRays)
+    {
+      atomicAdd(countsOut + 0, cNodes); atomicAdd(countsOut + 1, cTris); atomicAdd(countsOut + 2, cInsts); atomicAdd(countsOut + 3, cRays);
+    }
+  }
 }
