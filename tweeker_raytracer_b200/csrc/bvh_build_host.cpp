@@ -39,6 +39,7 @@ constexpr uint32_t kLeafMax = 3;    // a leaf child of a wide node carries 1..3 
 struct Builder
 {
   const PrimBox* prims;
+  uint32_t leafMax = kLeafMax;
   std::vector<uint32_t> order;
   std::vector<BinNode> nodes;
 
@@ -86,7 +87,7 @@ struct Builder
       }
     }
     // SAH termination for small leaves: intersecting `count` primitives vs. one more node level
-    if (count <= kLeafMax)
+    if (count <= leafMax)
     {
       const float leafCost = box.halfArea() * (float)count;
       if (bestAxis < 0 || bestCost + 1.2f * box.halfArea() >= leafCost) return idx;
@@ -252,4 +253,30 @@ void build_wide_bvh_host(const PrimBox* prims, uint32_t numPrims, WideBvh& out)
   out.nodes.emplace_back();
   Emitter em{ b.nodes, b.order, out };
   em.emit(0, root);
+}
+
+// Binned-SAH binary tree with single-primitive leaves; used by the GPU builder for the top levels over a cut of its
+// radix tree.  children[i] = (left, right), a negative value ~k means primitive k; node 0 is the root.
+void build_binary_sah_host(const PrimBox* prims, uint32_t numPrims, std::vector<int2>& children, std::vector<PrimBox>& boxes)
+{
+  Builder b; b.prims = prims; b.leafMax = 1;
+  b.order.resize(numPrims);
+  for (uint32_t i = 0; i < numPrims; ++i) b.order[i] = i;
+  b.nodes.reserve(2 * (size_t)numPrims);
+  b.build(0, numPrims);
+  // renumber: internal nodes get consecutive ids in creation order (the root was created first)
+  std::vector<int> id(b.nodes.size(), -1);
+  int next = 0;
+  for (size_t i = 0; i < b.nodes.size(); ++i) if (b.nodes[i].left >= 0) id[i] = next++;
+  children.assign((size_t)next, make_int2(0, 0));
+  boxes.assign((size_t)next, PrimBox());
+  auto ref = [&](int node) { return b.nodes[node].left >= 0 ? id[node] : ~(int)b.order[b.nodes[node].first]; };
+  for (size_t i = 0; i < b.nodes.size(); ++i)
+  {
+    if (b.nodes[i].left < 0) continue;
+    children[(size_t)id[i]] = make_int2(ref(b.nodes[i].left), ref(b.nodes[i].right));
+    PrimBox pb;
+    for (int k = 0; k < 3; ++k) { pb.lo[k] = b.nodes[i].box.lo[k]; pb.hi[k] = b.nodes[i].box.hi[k]; }
+    boxes[(size_t)id[i]] = pb;
+  }
 }

@@ -23,7 +23,8 @@ struct QueryClosest
   __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d) const { o = __ldg(rays + 2 * (size_t)i); d = __ldg(rays + 2 * (size_t)i + 1); return true; }
   template <class T> __device__ __forceinline__ void store(uint32_t i, const T& tr) const
   {
-    rtc_hit out; out.t = tr.hit.t; out.u = tr.hit.u; out.v = tr.hit.v; out.inst = tr.hit.inst; out.prim = tr.hit.prim;
+    const TraceHit h = tr.result();
+    rtc_hit out; out.t = h.t; out.u = h.u; out.v = h.v; out.inst = h.inst; out.prim = h.prim;
     hits[i] = out;
   }
 };
@@ -53,8 +54,9 @@ struct ExtendPaths
   __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d) { path = queue[i]; o = rayOrg[path]; d = rayDir[path]; return true; }
   template <class T> __device__ __forceinline__ void store(uint32_t, const T& tr) const
   {
-    hit[path] = make_float4(tr.hit.t, tr.hit.u, tr.hit.v, __uint_as_float(tr.hit.prim));
-    hitInst[path] = tr.hit.inst;
+    const TraceHit h = tr.result();
+    hit[path] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+    hitInst[path] = h.inst;
   }
 };
 

@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <set>
@@ -289,7 +290,17 @@ int rtc_gas_build(rtc_context* ctx, uint64_t attributes, uint32_t strideBytes, u
   rec.attributes = attributes; rec.indices = indices; rec.strideBytes = strideBytes; rec.numVerts = numVerts; rec.numTris = numTris;
 
   int builder = (int)buildFlags;
-  if (builder == RTC_BUILD_DEFAULT) builder = (numTris > kGpuBuildThreshold) ? RTC_BUILD_GPU_LBVH : RTC_BUILD_HOST_SAH;
+  if (builder == RTC_BUILD_DEFAULT)
+  {
+    builder = (numTris > kGpuBuildThreshold) ? RTC_BUILD_GPU_LBVH : RTC_BUILD_HOST_SAH;
+    // RTC_FORCE_BUILDER=gpu|host overrides the size rule (used by the tests to run whole scenes through either builder)
+    if (const char* force = std::getenv("RTC_FORCE_BUILDER"))
+    {
+      if (std::strcmp(force, "gpu") == 0) builder = RTC_BUILD_GPU_LBVH;
+      else if (std::strcmp(force, "host") == 0) builder = RTC_BUILD_HOST_SAH;
+    }
+  }
+  if (builder != RTC_BUILD_GPU_LBVH && builder != RTC_BUILD_HOST_SAH) RTC_FAIL("bad build flags");
   rec.builder = builder;
 
   if (builder == RTC_BUILD_GPU_LBVH && numTris > 0)

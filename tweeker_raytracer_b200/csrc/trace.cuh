@@ -163,7 +163,8 @@ struct Traversal
   float4 org, dir;
   float tlimit;
   bool found;
-  TraceHit hit;
+  TraceHit hit;               // u, v hold the un-normalised V, W until result() divides them by det (same operands, same bits)
+  float hitDet;
   // traversal state
   uint2 nodeGroup, triGroup;
   int sp, blasBase;
@@ -186,6 +187,13 @@ struct Traversal
   {
     --sp;
     return (sp < RTC_SM_STACK) ? smStack[sp * BLOCK] : lmStack[(sp - RTC_SM_STACK) & (RTC_LM_STACK - 1)];
+  }
+
+  __device__ __forceinline__ TraceHit result() const
+  {
+    TraceHit h = hit;
+    if (!ANY && found) { h.u = __fdiv_rn(hit.u, hitDet); h.v = __fdiv_rn(hit.v, hitDet); }
+    return h;
   }
 
   // returns false when the ray interval is empty (nothing to traverse)
@@ -288,7 +296,7 @@ struct Traversal
             if (better)
             {
               found = true; tlimit = t;
-              hit.t = t; hit.u = __fdiv_rn(V, det); hit.v = __fdiv_rn(W, det); hit.inst = curInst; hit.prim = prim;
+              hit.t = t; hit.u = V; hit.v = W; hitDet = det; hit.inst = curInst; hit.prim = prim;
             }
           }
         }
