@@ -34,6 +34,15 @@ METRIC = "rtigo3_geometry_1080p_samples_per_s"
 UNIT = "Msamples/s"
 WORKLOAD = "rtigo3 geometry scene (planes/boxes/spheres/tori, 5 BSDFs, constant env + 4x4 parallelogram light), 1920x1080, pathLengths 2 6"
 S_RAY, S_NODE, S_TRI, S_INST = 48, 80, 48, 64
+WORKLOADS = {
+    "rtigo3_geometry": WORKLOAD,
+    "rtigo3_cornell_box": "rtigo3 Cornell box (area light, mirror + glass spheres)",
+    "rtigo3_instances": "instanced stress scene: instances of a 50 000-triangle torus (two-level BVH), constant environment",
+}
+
+
+def workload(args):
+    return "%s, %s" % (WORKLOADS.get(args.scene, args.scene), args.resolution.replace(" ", "x"))
 
 
 def parse_args():
@@ -45,6 +54,7 @@ def parse_args():
     ap.add_argument("--spp-per-step", type=int, default=16)
     ap.add_argument("--resolution", default="1920 1080")
     ap.add_argument("--scene", default="rtigo3_geometry")
+    ap.add_argument("--instances", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -97,13 +107,26 @@ def system_file(tmp, args, device_ordinal):
     return H.write_system(tmp, args.scene, resolution=args.resolution, samplesSqrt=128, devicesMask=1 << device_ordinal, strategy=0)
 
 
+def scene_file(tmp, args):
+    """scenes/scene_<name>.txt; the instanced stress scene (config 4) is generated (tools/make_instances_scene.py)."""
+    import helpers as H
+    if args.scene == "rtigo3_instances":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import make_instances_scene
+        path = os.path.join(tmp, "scene_rtigo3_instances.txt")
+        if not os.path.exists(path):
+            make_instances_scene.write_scene(path, count=args.instances)
+        return path
+    return H.scene_path(args.scene)
+
+
 def cpu_sample(args, threads, iterations=2, row_step=16, host_only_app=None):
     """Oracle on rows y % row_step == 0 for `iterations` samples per pixel; returns (Msamples/s, seconds, description)."""
     import helpers as H
     from oracle import orc
     from tweeker_raytracer_b200 import host
     tmp = tempfile.mkdtemp()
-    app = host_only_app or host.App(system_file(tmp, args, 0), H.scene_path(args.scene), host_only=True)
+    app = host_only_app or host.App(system_file(tmp, args, 0), scene_file(tmp, args), host_only=True)
     ref = H.oracle_scene(app)
     w, h = app.resolution
     sysd = H.oracle_sys(app)
@@ -133,7 +156,7 @@ def run_reference(args, rank):
     value = sum(vals) / len(vals)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": WORKLOAD, "sample_per_step": desc},
+            "data": "synthetic", "config": {"workload": workload(args), "sample_per_step": desc},
             "mrays_per_s": mrays,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": "each step: " + desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -170,7 +193,7 @@ def main():
     S, K, W = args.spp_per_step, args.steps, args.warmup
 
     tmp = tempfile.mkdtemp()
-    app = host.App(system_file(tmp, args, local_rank), H.scene_path(args.scene))
+    app = host.App(system_file(tmp, args, local_rank), scene_file(tmp, args))
     w, h = app.resolution
     pixels = w * h
     ctx = app.context(0)
@@ -287,7 +310,7 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "spp_per_step": S, "path_samples_per_step_per_gpu": S * pixels,
+                "config": {"workload": workload(args), "spp_per_step": S, "path_samples_per_step_per_gpu": S * pixels,
                            "parallelism": "sample-range x%d + NCCL reduce" % n if n > 1 else "single GPU",
                            "l2": "wavefront state per step (%.0f MB) exceeds L2 (126 MB); no explicit flush" % (S * pixels * 292 / 1e6),
                            "triangles": int(info.numTris), "bvh_nodes": int(info.numNodes), "instances": int(info.numInstances)},
