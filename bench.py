@@ -219,6 +219,10 @@ def main():
 
     for s in range(W):
         step(s)
+    if dist is not None:       # warm the NCCL communicator up (connection set-up is not part of a render)
+        warm = torch.zeros(pixels * 4, dtype=torch.float32, device="cuda")
+        dist.reduce(warm, dst=0, op=dist.ReduceOp.SUM)
+        del warm
     barrier()
     ctx.stats_reset()
     ctx.profile_enable(True)
