@@ -29,7 +29,14 @@ struct ObjRay
   int   kx, ky, kz;
 };
 
-__device__ __forceinline__ float sel3(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
+// component k of (x, y, z) as two selects (a nested ternary compiles to divergent branches here)
+__device__ __forceinline__ float sel3(float x, float y, float z, int k)
+{
+  float r;
+  asm("{\n\t.reg .pred p1, p2;\n\tsetp.eq.s32 p1, %4, 1;\n\tsetp.eq.s32 p2, %4, 2;\n\tselp.f32 %0, %2, %1, p1;\n\tselp.f32 %0, %3, %0, p2;\n\t}"
+      : "=&f"(r) : "f"(x), "f"(y), "f"(z), "r"(k));
+  return r;
+}
 
 __device__ __forceinline__ void shear_setup(ObjRay& r)
 {
