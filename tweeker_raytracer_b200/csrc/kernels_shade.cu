@@ -16,6 +16,9 @@ namespace {
 
 constexpr int kBlock = 256;
 constexpr uint32_t kNoPixel = 0xffffffffu;
+// device counters of one batch: [0..63] extend counts per depth, [64..127] shadow counts, [128..191] extend cursors,
+// [192..255] connect cursors, [256 + 8 d + c] paths of shade class c at depth d
+constexpr uint32_t kNumCounters = 256 + 64 * 8;
 
 struct WfArgs
 {
@@ -28,17 +31,49 @@ struct WfArgs
   uint32_t numPaths;
 };
 
-// Appends `value` for every lane with pred set; returns nothing.  All 32 lanes must call it.
-__device__ __forceinline__ void warp_append(uint32_t* __restrict__ queue, uint32_t* __restrict__ counter, bool pred, uint32_t value)
+// Launch-index order of the wavefront: consecutive path ids cover 8x4 pixel tiles (a warp = one tile) instead of 32x1
+// row segments, which keeps the rays of a warp closer together.  Falls back to row-major when the launch does not tile.
+__device__ __forceinline__ void launch_xy(uint32_t idx, uint32_t w, uint32_t h, uint32_t& x, uint32_t& y)
 {
-  const uint32_t mask = __ballot_sync(0xffffffffu, pred);
-  if (mask == 0u) return;
-  const int lane = threadIdx.x & 31;
-  const int leader = __ffs((int)mask) - 1;
-  uint32_t base = 0;
-  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (pred) queue[base + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = value;
+  if (((w & 7u) | (h & 3u)) == 0u)
+  {
+    const uint32_t tile = idx >> 5, within = idx & 31u, tilesPerRow = w >> 3;
+    const uint32_t ty = tile / tilesPerRow, tx = tile - ty * tilesPerRow;
+    x = (tx << 3) + (within & 7u);
+    y = (ty << 2) + (within >> 3);
+  }
+  else
+  {
+    y = idx / w; x = idx - y * w;
+  }
+}
+
+// Queue append aggregated over the whole CTA: every thread offers (class, value), class < 0 meaning nothing.  Lanes of a
+// warp with the same class are found with one match.any, each warp reserves its run in a shared counter, ONE thread per
+// class reserves the CTA's run in the global counter, then every thread writes its slot.  A 256-thread CTA therefore
+// issues at most NCLS global atomics per 256 paths instead of one per warp and class, which matters because all of them
+// hit the same few addresses.  Must be called by all threads of the CTA (it synchronises).
+template <int NCLS>
+__device__ __forceinline__ void block_append(int cls, uint32_t value, uint32_t* __restrict__ const* queues, uint32_t* __restrict__ const* counters)
+{
+  __shared__ uint32_t sCount[NCLS], sBase[NCLS];
+  if (threadIdx.x < NCLS) sCount[threadIdx.x] = 0u;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t peers = __match_any_sync(0xffffffffu, cls);
+  uint32_t offset = 0;
+  if (cls >= 0)
+  {
+    const uint32_t leader = (uint32_t)__ffs((int)peers) - 1u;
+    if (lane == leader) offset = atomicAdd(&sCount[cls], (uint32_t)__popc(peers));
+  }
+  // peers of the same class share their leader's reservation
+  offset = __shfl_sync(0xffffffffu, offset, (cls >= 0) ? (uint32_t)__ffs((int)peers) - 1u : lane) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+  __syncthreads();
+  if (threadIdx.x < NCLS && sCount[threadIdx.x]) sBase[threadIdx.x] = atomicAdd(counters[threadIdx.x], sCount[threadIdx.x]);
+  __syncthreads();
+  if (cls >= 0) queues[cls][sBase[cls] + offset] = value;
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -54,7 +89,8 @@ k_generate(const __grid_constant__ WfArgs a, uint32_t* __restrict__ queue, uint3
     if (p < n)
     {
       const uint32_t it = p / pixelsPerIter, idx = p - it * pixelsPerIter;
-      const uint32_t y = idx / a.launchWidth, x = idx - y * a.launchWidth;
+      uint32_t x, y;
+      launch_xy(idx, a.launchWidth, a.launchHeight, x, y);
       uint32_t seed = 0, col = 0; float3 pos, wi;
       alive = start_path(a.sys, a.launchWidth, x, y, a.iterFirst + (int)it, seed, pos, wi, col);
       if (alive)
@@ -70,7 +106,7 @@ k_generate(const __grid_constant__ WfArgs a, uint32_t* __restrict__ queue, uint3
         a.wf.misc[p] = make_uint4(0u, 0u, 0u, kNoPixel);
       }
     }
-    warp_append(queue, count, alive, p);
+    { uint32_t* const q[1] = { queue }; uint32_t* const c[1] = { count }; block_append<1>(alive ? 0 : -1, p, q, c); }
   }
 }
 
@@ -84,6 +120,59 @@ __device__ __forceinline__ float3 xf_normal(const float4 r0, const float4 r1, co
 }
 __device__ __forceinline__ float3 ld3(const float* p) { return f3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); }
 
+// Surface classes of the shade stage.  After extend, k_bin sorts the live paths into one queue per class, and a
+// specialised instantiation of k_shade runs per class: a warp then executes ONE BSDF (or the miss program) instead of
+// serialising all of them, and each instantiation carries only its own code.
+enum : int { SHADE_MISS = 0, SHADE_BRDF_DIFFUSE = 1, SHADE_BRDF_SPECULAR = 2, SHADE_BSDF_SPECULAR = 3, SHADE_BRDF_GGX = 4, SHADE_BSDF_GGX = 5,
+             SHADE_OTHER = 6, SHADE_NUM_CLASSES = 7 };
+
+__global__ void __launch_bounds__(kBlock)
+k_bin(const __grid_constant__ WfArgs a, const SceneDesc sc, const uint32_t* __restrict__ queueIn, const uint32_t* __restrict__ countIn,
+      uint32_t* __restrict__ bins, uint32_t binStride, uint32_t* __restrict__ binCounts)
+{
+  const uint32_t n = *countIn;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const rt_MaterialDefinition* materials = reinterpret_cast<const rt_MaterialDefinition*>(a.sys.materialDefinitions);
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride)
+  {
+    const uint32_t i = base + threadIdx.x;
+    int cls = -1; uint32_t p = 0;
+    if (i < n)
+    {
+      p = queueIn[i];
+      const uint32_t inst = a.wf.hitInst[p];
+      if (inst == 0xffffffffu) cls = SHADE_MISS;
+      else
+      {
+        const int index = materials[sc.geomInst[inst].materialIndex].indexBSDF;
+        cls = (0 <= index && index < RT_NUM_BSDF_INDICES) ? 1 + index : SHADE_OTHER;
+      }
+    }
+    uint32_t* q[SHADE_NUM_CLASSES]; uint32_t* c[SHADE_NUM_CLASSES];
+#pragma unroll
+    for (int k = 0; k < SHADE_NUM_CLASSES; ++k) { q[k] = bins + (size_t)k * binStride; c[k] = binCounts + k; }
+    block_append<SHADE_NUM_CLASSES>(cls, p, q, c);
+  }
+}
+
+template <int CLASS> SD void bsdf_sample_class(const rt_MaterialDefinition& m, const State& st, Prd& prd)
+{
+  if (CLASS == SHADE_BRDF_DIFFUSE)        sample_brdf_diffuse(m, st, prd);
+  else if (CLASS == SHADE_BRDF_SPECULAR)  sample_brdf_specular(st, prd);
+  else if (CLASS == SHADE_BSDF_SPECULAR)  sample_bsdf_specular(m, st, prd);
+  else if (CLASS == SHADE_BRDF_GGX)       sample_brdf_ggx(m, st, prd);
+  else if (CLASS == SHADE_BSDF_GGX)       sample_bsdf_ggx(m, st, prd);
+  else                                    bsdf_sample(m, st, prd);
+}
+template <int CLASS> SD float4 bsdf_eval_class(const rt_MaterialDefinition& m, const State& st, const Prd& prd, float3 wiL)
+{
+  if (CLASS == SHADE_BRDF_DIFFUSE)  return eval_brdf_diffuse(st, wiL);
+  if (CLASS == SHADE_BRDF_GGX)      return eval_brdf_ggx(m, st, prd, wiL);
+  if (CLASS == SHADE_OTHER)         return bsdf_eval(m, st, prd, wiL);
+  return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+template <int CLASS>
 __global__ void __launch_bounds__(kBlock)
 k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
         const uint32_t* __restrict__ queueIn, const uint32_t* __restrict__ countIn,
@@ -136,7 +225,7 @@ k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
         if (RT_MATERIAL_STACK_FIRST <= stackIdx - 1) prd.ior.y = a.wf.absStack[(size_t)p * 4 + stackIdx - 1].w;
       }
 
-      if (hitInst == 0xffffffffu)
+      if (CLASS == SHADE_MISS)
       {
         miss_program(sys, a.miss, prd);
       }
@@ -201,10 +290,11 @@ k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
           const rt_MaterialDefinition material = reinterpret_cast<const rt_MaterialDefinition*>(sys.materialDefinitions)[gi.materialIndex];
           state.albedo = f3(material.albedo);
           prd.flags = (prd.flags & ~RT_FLAG_DIFFUSE) | RT_FLAG_HIT | material.flags;
-          bsdf_sample(material, state, prd);
+          bsdf_sample_class<CLASS>(material, state, prd);
 
           const int numLights = sys.numLights;
-          if ((prd.flags & RT_FLAG_DIFFUSE) && 0 < numLights)
+          // only the diffuse and glossy-reflection lobes ever set FLAG_DIFFUSE: the specular classes carry no NEE code
+          if ((CLASS == SHADE_BRDF_DIFFUSE || CLASS == SHADE_BRDF_GGX || CLASS == SHADE_OTHER) && (prd.flags & RT_FLAG_DIFFUSE) && 0 < numLights)
           {
             const float2 sample = rng2(prd.seed);
             LightSample ls; ls.pdf = 0.0f; ls.distance = 0.0f; ls.direction = f3(0.0f); ls.emission = f3(0.0f);
@@ -221,7 +311,7 @@ k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
             else                                light_env_constant(numLights, sample, ls);
             if (0.0f < ls.pdf)
             {
-              const float4 bp = bsdf_eval(material, state, prd, ls.direction);
+              const float4 bp = bsdf_eval_class<CLASS>(material, state, prd, ls.direction);
               const float3 f = f3(bp.x, bp.y, bp.z);
               if (0.0f < bp.w && !is_null(f))
               {
@@ -289,8 +379,8 @@ k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
         a.wf.misc[p] = misc;
       }
     }
-    warp_append(queueOut, countOut, continues, p);
-    warp_append(shadowQueue, shadowCount, shadow, p);
+    { uint32_t* const q[1] = { queueOut }; uint32_t* const c[1] = { countOut }; block_append<1>(continues ? 0 : -1, p, q, c); }
+    { uint32_t* const q[1] = { shadowQueue }; uint32_t* const c[1] = { shadowCount }; block_append<1>(shadow ? 0 : -1, p, q, c); }
   }
 }
 
@@ -303,9 +393,10 @@ k_accumulate(const __grid_constant__ WfArgs a)
   if (idx >= pixelsPerIter) return;
   const uint32_t col = a.wf.misc[idx].w;
   if (col == kNoPixel) return;
-  const uint32_t y = idx / a.launchWidth;
+  uint32_t x, y;
+  launch_xy(idx, a.launchWidth, a.launchHeight, x, y);
   float4* buffer; size_t index;
-  if (a.raygen == RTC_RAYGEN_LOCAL_COPY) { buffer = reinterpret_cast<float4*>(a.sys.texelBuffer); index = idx; }
+  if (a.raygen == RTC_RAYGEN_LOCAL_COPY) { buffer = reinterpret_cast<float4*>(a.sys.texelBuffer); index = (size_t)y * a.launchWidth + x; }
   else { buffer = reinterpret_cast<float4*>(a.sys.outputBuffer); index = (size_t)y * (size_t)a.sys.resolution.x + col; }
   float4 dst = buffer[index];
   bool wrote = false;
@@ -425,7 +516,8 @@ int ensure_wavefront(rtc_context* ctx, uint64_t capacity)
   const uint64_t oQA = off; off += align(4 * n);
   const uint64_t oQB = off; off += align(4 * n);
   const uint64_t oQS = off; off += align(4 * n);
-  const uint64_t oCnt = off; off += align(4 * 256);
+  const uint64_t oBins = off; off += align(4 * n) * SHADE_NUM_CLASSES;
+  const uint64_t oCnt = off; off += align(4 * kNumCounters);
   void* base = nullptr;
   RTC_CUDA(cudaMalloc(&base, off));
   char* b = static_cast<char*>(base);
@@ -434,6 +526,7 @@ int ensure_wavefront(rtc_context* ctx, uint64_t capacity)
   wf.throughput = (float4*)(b + oThroughput); wf.radiance = (float4*)(b + oRadiance); wf.misc = (uint4*)(b + oMisc); wf.absStack = (float4*)(b + oAbs);
   wf.shadowOrg = (float4*)(b + oSOrg); wf.shadowDir = (float4*)(b + oSDir); wf.shadowContrib = (float4*)(b + oSCon);
   wf.queueA = (uint32_t*)(b + oQA); wf.queueB = (uint32_t*)(b + oQB); wf.shadowQueue = (uint32_t*)(b + oQS); wf.counters = (uint32_t*)(b + oCnt);
+  wf.bins = (uint32_t*)(b + oBins); wf.binStride = (uint32_t)(align(4 * n) / 4);
   return 0;
 }
 
@@ -448,6 +541,29 @@ __global__ void k_stats(const uint32_t* __restrict__ counters, int maxDepth, uin
     for (int d = 0; d < maxDepth; ++d) { rad += counters[d]; sh += counters[64 + d]; }
     stats[0] += rad; stats[1] += sh; stats[2] += counters[0];
   }
+}
+
+} // namespace
+
+namespace {
+
+template <int CLASS>
+void launch_shade_class(rtc_context* ctx, int grid, const WfArgs& a, const SceneDesc& sc, uint32_t* bins, uint32_t binStride, uint32_t* binCounts,
+                        uint32_t* qOut, uint32_t* countOut, uint32_t* shadowQueue, uint32_t* shadowCount)
+{
+  k_shade<CLASS><<<grid, kBlock, 0, ctx->stream>>>(a, sc, bins + (size_t)CLASS * binStride, binCounts + CLASS, qOut, countOut, shadowQueue, shadowCount);
+}
+
+void launch_shade_classes(rtc_context* ctx, int grid, const WfArgs& a, const SceneDesc& sc, uint32_t* bins, uint32_t binStride, uint32_t* binCounts,
+                          uint32_t* qOut, uint32_t* countOut, uint32_t* shadowQueue, uint32_t* shadowCount)
+{
+  launch_shade_class<SHADE_MISS>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount);
+  launch_shade_class<SHADE_BRDF_DIFFUSE>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount);
+  launch_shade_class<SHADE_BRDF_SPECULAR>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount);
+  launch_shade_class<SHADE_BSDF_SPECULAR>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount);
+  launch_shade_class<SHADE_BRDF_GGX>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount);
+  launch_shade_class<SHADE_BSDF_GGX>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount);
+  launch_shade_class<SHADE_OTHER>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount);
 }
 
 } // namespace
@@ -476,7 +592,7 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
     a.wf = ctx->wf; a.sys = sys; a.launchWidth = w; a.launchHeight = h; a.raygen = raygen; a.miss = miss;
     a.iterFirst = iterFirst + done; a.iterCount = batch; a.accumFirst = accumFirst + done; a.numPaths = (uint32_t)(pixels * (uint64_t)batch);
     uint32_t* cnt = ctx->wf.counters;
-    RTC_CUDA(cudaMemsetAsync(cnt, 0, 4 * 256, ctx->stream));
+    RTC_CUDA(cudaMemsetAsync(cnt, 0, 4 * kNumCounters, ctx->stream));
     if (int rc = profile_begin(ctx, RTC_KERNEL_GENERATE)) return rc;
     k_generate<<<gridShade, kBlock, 0, ctx->stream>>>(a, ctx->wf.queueA, cnt + 0);
     ctx->kernelLaunches++;
@@ -486,8 +602,10 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
     {
       if (int rc = launch_extend(ctx, &scene->desc, ctx->wf, qIn, cnt + d, cnt + 128 + d, countWork)) return rc;
       if (int rc = profile_begin(ctx, RTC_KERNEL_SHADE)) return rc;
-      k_shade<<<gridShade, kBlock, 0, ctx->stream>>>(a, scene->desc, qIn, cnt + d, qOut, cnt + d + 1, ctx->wf.shadowQueue, cnt + 64 + d);
-      ctx->kernelLaunches++;
+      uint32_t* binCounts = cnt + 256 + d * 8;
+      k_bin<<<gridShade, kBlock, 0, ctx->stream>>>(a, scene->desc, qIn, cnt + d, ctx->wf.bins, ctx->wf.binStride, binCounts);
+      launch_shade_classes(ctx, gridShade, a, scene->desc, ctx->wf.bins, ctx->wf.binStride, binCounts, qOut, cnt + d + 1, ctx->wf.shadowQueue, cnt + 64 + d);
+      ctx->kernelLaunches += 1 + SHADE_NUM_CLASSES;
       if (int rc = profile_end(ctx)) return rc;
       if (sys.numLights > 0) { if (int rc = launch_connect(ctx, &scene->desc, ctx->wf, cnt + 64 + d, cnt + 192 + d, countWork)) return rc; }
       uint32_t* t = qIn; qIn = qOut; qOut = t;

@@ -104,6 +104,7 @@ struct WavefrontBuffers
   float4 *absStack = nullptr;                      // per path x 4: nested-volume stack
   float4 *shadowOrg = nullptr, *shadowDir = nullptr, *shadowContrib = nullptr;  // per path
   uint32_t *queueA = nullptr, *queueB = nullptr, *shadowQueue = nullptr;
+  uint32_t *bins = nullptr; uint32_t binStride = 0;  // per shade class: path ids binned after extend (class c at bins + c * binStride)
   uint32_t *counters = nullptr;                    // [0..63] extend counts per depth, [64..127] shadow counts per depth,
                                                    // [128..191] extend ray cursors, [192..255] connect ray cursors
   void* base = nullptr;
