@@ -94,6 +94,16 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
+def measured_traffic():
+    """DRAM bytes per extend launch from the committed ncu capture (profiles/extend_traffic_r1.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "extend_traffic_r1.json")) as f:
+            d = json.load(f)
+        return float(d["traffic_bytes_per_launch"]), d["source"]
+    except Exception:
+        return None, None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -270,8 +280,9 @@ def main():
     con_ms, con_launches = prof["connect"]
     peak, peak_src = measured_peak()
     achieved = ext_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_extend<false> (closest-hit traversal of the radiance-ray queue)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic, traffic_src = measured_traffic() if args.scene == "rtigo3_geometry" else (None, None)
+    roofline = {"bound": "hbm", "kernel": "k_trace<ANY=0, ExtendPaths> (closest-hit traversal of the radiance-ray queue)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": ext_bytes / max(ext_launches, 1),
                 "avg_launch_ms": ext_ms / max(ext_launches, 1), "launches": int(ext_launches),
                 "per_ray": {"nodes": ext.nodes / max(ext.rays, 1), "tris": ext.tris / max(ext.rays, 1), "instances": ext.instances / max(ext.rays, 1),
@@ -312,7 +323,7 @@ def main():
 
     line = None
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
+        line = {"metric": METRIC if args.scene == "rtigo3_geometry" else METRIC.replace("rtigo3_geometry", args.scene), "value": value, "unit": UNIT, "n_gpus": n, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload(args), "spp_per_step": S, "path_samples_per_step_per_gpu": S * pixels,
                            "parallelism": "sample-range x%d + NCCL reduce" % n if n > 1 else "single GPU",
