@@ -12,6 +12,8 @@
 // compacted with warp ballots (one atomicAdd per warp).
 #include "shade.cuh"
 
+#include <cstdlib>
+
 namespace {
 
 constexpr int kBlock = 256;
@@ -19,6 +21,7 @@ constexpr uint32_t kNoPixel = 0xffffffffu;
 // device counters of one batch: [0..63] extend counts per depth, [64..127] shadow counts, [128..191] extend cursors,
 // [192..255] connect cursors, [256 + 8 d + c] paths of shade class c at depth d
 constexpr uint32_t kNumCounters = 256 + 64 * 8;
+constexpr uint64_t kMaxPathsInFlight = 64ull << 20;   // 64 Mi paths x 320 B of wavefront state = 21 GB of the 180 GB HBM
 
 struct WfArgs
 {
@@ -579,8 +582,11 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
   if (maxDepth > 63) RTC_FAIL("pathLengths.y > 63 is not supported");
   const uint64_t pixels = (uint64_t)w * h;
   if (pixels == 0 || iterCount <= 0) return 0;
-  // iterations in flight per batch: keep the wavefront around 8M paths
-  uint64_t perBatch = (8u << 20) / pixels; if (perBatch < 1) perBatch = 1; if (perBatch > (uint64_t)iterCount) perBatch = (uint64_t)iterCount;
+  // iterations in flight per batch: up to kMaxPathsInFlight paths (deep bounces have few live paths, so the more
+  // iterations share a launch the smaller the tail of the persistent traversal kernels); RTC_MAX_PATHS overrides
+  uint64_t maxPaths = kMaxPathsInFlight;
+  if (const char* env = getenv("RTC_MAX_PATHS")) { const long long v = atoll(env); if (v > 0) maxPaths = (uint64_t)v; }
+  uint64_t perBatch = maxPaths / pixels; if (perBatch < 1) perBatch = 1; if (perBatch > (uint64_t)iterCount) perBatch = (uint64_t)iterCount;
   if (pixels * perBatch > 0x7fffffffull) RTC_FAIL("launch too large");
   if (int rc = ensure_wavefront(ctx, pixels * perBatch)) return rc;
 
