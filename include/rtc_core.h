@@ -60,6 +60,7 @@ typedef struct {
   uint64_t pathSamples;      /* paths started by generate */
   uint64_t kernelLaunches;   /* kernels of this library launched */
   double   lastTraceMs;      /* device time of the last rtc_trace_* call (CUDA events on the context stream) */
+  uint64_t stackOverflows;   /* rays whose traversal stack overflowed since the library was loaded; must be 0 */
 } rtc_stats;
 
 /* BVH statistics of a built scene. */

@@ -227,3 +227,21 @@ def test_radiance_hdr_file_round_trip(built, tmp_path):
     assert texels.shape == (4, 8, 4)
     assert np.allclose(texels[3, :, 0], 2.0) and np.allclose(texels[0, :, 2], 0.5) and np.allclose(texels[1], [0, 0, 0, 1])
     app.close()
+
+
+def test_save_system_description_round_trip(built, tmp_path):
+    app = load(tmp_path, name="rtigo3_geometry", resolution="320 180", envRotation=0.25, composite=1)
+    app.set_camera(0.6, 0.4, 35.0, 7.5, (0.5, 1.5, -0.25))
+    path = app.save_system(os.path.join(str(tmp_path), "saved_system.txt"))
+    assert path and os.path.exists(path)
+    text = open(path).read()
+    for line in ("strategy 0", "resolution 320 180", "samplesSqrt 16", "miss 1", "light 2", "pathLengths 2 6", "envRotation 0.25",
+                 "camera 0.6 0.4 35 7.5", "center 0.5 1.5 -0.25", "composite 1", "batchIterations 32"):
+        assert line in text, line
+    again = host.App(path, H.scene_path("rtigo3_geometry"), host_only=True)
+    a, b = app.system_data(), again.system_data()
+    assert bytes(a) == bytes(b)
+    assert app.camera().tobytes() == again.camera().tobytes()
+    assert bytes(app.tonemapper()) == bytes(again.tonemapper())
+    app.close()
+    again.close()

@@ -183,3 +183,24 @@ def test_update_restarts_accumulation(cuda_device, tmp_path):
         assert app.frame().tobytes() == first.tobytes()
     finally:
         app.close()
+
+
+def test_mutators_restart_and_match_oracle(cuda_device, tmp_path):
+    # updateCamera / updateMaterial / updateLight (Raytracer.cpp:331-367): each restarts the accumulation, and the frame
+    # rendered afterwards equals the oracle's frame of the modified scene
+    app = host.App(H.write_system(tmp_path, "rtigo3_cornell_box", resolution="96 96", samplesSqrt=2), H.scene_path("rtigo3_cornell_box"))
+    try:
+        app.render(4)
+        app.set_camera(0.7, 0.55, 50.0, 3.2, (0.0, 1.0, 0.0))
+        app.update_material(5, 3, (0.9, 0.6, 0.2), roughness=(0.3, 0.1))                                   # mirror sphere -> anisotropic GGX
+        app.update_material(6, 2, (1, 1, 1), absorption_color=(0.5, 0.8, 0.9), absorption_scale=2.0, ior=1.33)   # glass with absorption
+        app.update_light_emission(0, (4.0, 8.0, 12.0))
+        assert app.render(3) == 3
+        got = app.frame()
+        ref = H.oracle_scene(app)
+        want = ref.render(H.oracle_sys(app), app.info.miss, 96, 96, iter_count=3).reshape(96, 96, 4)
+        assert_frames_identical(got, want)
+        assert app.materials()["indexBSDF"][5] == 3 and abs(app.materials()["ior"][6] - 1.33) < 1e-6
+        assert app.stats().stackOverflows == 0
+    finally:
+        app.close()

@@ -33,7 +33,7 @@ SYMBOLS = [
 
 class Stats(C.Structure):
     _fields_ = [("radianceRays", C.c_uint64), ("shadowRays", C.c_uint64), ("pathSamples", C.c_uint64),
-                ("kernelLaunches", C.c_uint64), ("lastTraceMs", C.c_double)]
+                ("kernelLaunches", C.c_uint64), ("lastTraceMs", C.c_double), ("stackOverflows", C.c_uint64)]
 
 
 class SceneInfo(C.Structure):

@@ -155,3 +155,12 @@ int launch_connect(rtc_context* ctx, const SceneDesc* scene, const WavefrontBuff
   RTC_CUDA(cudaGetLastError());
   return profile_end(ctx);
 }
+
+int read_stack_overflows(rtc_context* ctx, uint64_t* out)
+{
+  unsigned int v = 0;
+  RTC_CUDA(cudaMemcpyFromSymbolAsync(&v, g_rtcStackOverflows, sizeof(v), 0, cudaMemcpyDeviceToHost, ctx->stream));
+  RTC_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = v;
+  return 0;
+}

@@ -658,7 +658,7 @@ int rtc_stats_get(rtc_context* ctx, rtc_stats* out)
   }
   out->radianceRays = h[0]; out->shadowRays = h[1]; out->pathSamples = h[2];
   out->kernelLaunches = ctx->kernelLaunches; out->lastTraceMs = ctx->lastTraceMs;
-  return 0;
+  return read_stack_overflows(ctx, &out->stackOverflows);
 }
 
 int rtc_stats_reset(rtc_context* ctx)

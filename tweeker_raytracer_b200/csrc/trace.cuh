@@ -160,6 +160,10 @@ struct TraceCounts { uint32_t nodes, tris, insts; };
 #define RTC_SM_STACK 8        // traversal stack entries per thread kept in shared memory
 #define RTC_LM_STACK 32       // overflow entries in local memory (never reached by the in-scope scenes)
 
+// Rays whose traversal stack ran out of its 40 entries (the dropped subtree may hide a hit).  Never non-zero for the 8-wide
+// trees this library builds; exported through rtc_stats so that a violation is loud instead of a silently wrong image.
+__device__ unsigned int g_rtcStackOverflows = 0;
+
 // One ray's traversal as a resumable state machine: begin() once, then step() until it returns false.
 // A step visits one wide node (or pops a postponed leaf group) and tests the triangles / enters the instance it yields.
 // Closest hit (ANY = false): smallest t in (tmin, tmax), ties -> smaller (instance, primitive).  ANY = true: first hit ends the ray.
@@ -188,6 +192,7 @@ struct Traversal
   {
     if (sp < RTC_SM_STACK) smStack[sp * BLOCK] = v;
     else if (sp < RTC_SM_STACK + RTC_LM_STACK) lmStack[sp - RTC_SM_STACK] = v;
+    else { atomicAdd(&g_rtcStackOverflows, 1u); return; }
     ++sp;
   }
   __device__ __forceinline__ uint2 pop()

@@ -57,7 +57,7 @@ assert C.sizeof(SystemData) == 192 and C.sizeof(CompositorData) == 56
 SYMBOLS = ["rth_last_error", "rth_app_create", "rth_app_destroy", "rth_app_info", "rth_app_geometry", "rth_app_instance",
            "rth_app_materials", "rth_app_lights", "rth_app_camera", "rth_app_system_data", "rth_app_tonemapper",
            "rth_app_environment", "rth_app_render", "rth_app_synchronize", "rth_app_frame", "rth_app_restart",
-           "rth_app_set_composite", "rth_app_benchmark", "rth_app_screenshot", "rth_app_tonemap", "rth_app_context", "rth_app_stats"]
+           "rth_app_set_composite", "rth_app_save_system", "rth_app_set_camera", "rth_app_update_material", "rth_app_update_light_emission", "rth_app_benchmark", "rth_app_screenshot", "rth_app_tonemap", "rth_app_context", "rth_app_stats"]
 
 _lib = None
 
@@ -90,6 +90,10 @@ def lib():
         L.rth_app_frame.restype = C.c_void_p
         L.rth_app_restart.argtypes = [C.c_void_p]
         L.rth_app_set_composite.argtypes = [C.c_void_p, C.c_int]
+        L.rth_app_save_system.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
+        L.rth_app_set_camera.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        L.rth_app_update_material.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int]
+        L.rth_app_update_light_emission.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.rth_app_benchmark.argtypes = [C.c_void_p]
         L.rth_app_benchmark.restype = C.c_double
         L.rth_app_screenshot.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
@@ -186,6 +190,28 @@ class App:
         W, H = w.value, h.value
         return (_copy(t.value, np.float32, 4 * W * H).reshape(H, W, 4), _copy(cu.value, np.float32, (W + 1) * H).reshape(H, W + 1),
                 _copy(cv.value, np.float32, H + 1), integral.value)
+
+    def save_system(self, filename=""):
+        """Application::saveSystemDescription: returns the path written."""
+        buf = C.create_string_buffer(1024)
+        rc = self.L.rth_app_save_system(self.h, os.fsencode(filename) if filename else None, buf, 1024)
+        return buf.value.decode() if rc == 0 else None
+
+    def set_camera(self, phi, theta, fov, distance, center):
+        c = np.asarray(center, dtype=np.float32)
+        self.L.rth_app_set_camera(self.h, phi, theta, fov, distance, c.ctypes.data_as(C.c_void_p))
+
+    def update_material(self, index, index_bsdf, albedo, roughness=(0.1, 0.1), absorption_color=(1, 1, 1), absorption_scale=0.0, ior=1.5, thinwalled=False):
+        a, r, c = (np.asarray(v, dtype=np.float32) for v in (albedo, roughness, absorption_color))
+        rc = self.L.rth_app_update_material(self.h, index, index_bsdf, a.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p),
+                                            c.ctypes.data_as(C.c_void_p), absorption_scale, ior, 1 if thinwalled else 0)
+        if rc != 0:
+            raise core.RtcError("updateMaterial(%d) failed" % index)
+
+    def update_light_emission(self, index, emission):
+        e = np.asarray(emission, dtype=np.float32)
+        if self.L.rth_app_update_light_emission(self.h, index, e.ctypes.data_as(C.c_void_p)) != 0:
+            raise core.RtcError("updateLight(%d) failed" % index)
 
     # ---- device side
     def render(self, count=1):

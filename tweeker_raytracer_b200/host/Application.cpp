@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
@@ -159,6 +160,75 @@ void Application::getSystemData(int deviceIndex, SystemData& out) const
   out.envRotation = m_state.envRotation; out.envIntegral = 1.0f;
   if (m_environmentMap && m_mapPictures.count("environment"))
   { out.envWidth = m_environmentMap->getWidth(); out.envHeight = m_environmentMap->getHeight(); out.envIntegral = m_environmentMap->getIntegral(); }
+}
+
+bool Application::saveSystemDescription(std::string const& filename, std::string* writtenPath)
+{
+  std::ostringstream d;
+  d << "strategy " << (int)m_strategy << '\n' << "devicesMask " << m_devicesMask << '\n' << "interop " << m_interop << '\n'
+    << "present " << (m_present ? "1" : "0") << '\n' << "resolution " << m_resolution.x << " " << m_resolution.y << '\n'
+    << "tileSize " << m_tileSize.x << " " << m_tileSize.y << '\n' << "samplesSqrt " << m_samplesSqrt << '\n' << "miss " << m_miss << '\n';
+  if (!m_environment.empty()) d << "envMap " << m_environment << '\n';
+  d << "envRotation " << m_environmentRotation << '\n' << "clockFactor " << m_clockFactor << '\n' << "light " << m_light << '\n'
+    << "pathLengths " << m_pathLengths.x << " " << m_pathLengths.y << '\n' << "epsilonFactor " << m_epsilonFactor << '\n'
+    << "lensShader " << (int)m_lensShader << '\n'
+    << "center " << m_camera.m_center.x << " " << m_camera.m_center.y << " " << m_camera.m_center.z << '\n'
+    << "camera " << m_camera.m_phi << " " << m_camera.m_theta << " " << m_camera.m_fov << " " << m_camera.m_distance << '\n';
+  if (!m_prefixScreenshot.empty()) d << "prefixScreenshot " << m_prefixScreenshot << '\n';
+  d << "gamma " << m_tonemapperGUI.gamma << '\n'
+    << "colorBalance " << m_tonemapperGUI.colorBalance[0] << " " << m_tonemapperGUI.colorBalance[1] << " " << m_tonemapperGUI.colorBalance[2] << '\n'
+    << "whitePoint " << m_tonemapperGUI.whitePoint << '\n' << "burnHighlights " << m_tonemapperGUI.burnHighlights << '\n'
+    << "crushBlacks " << m_tonemapperGUI.crushBlacks << '\n' << "saturation " << m_tonemapperGUI.saturation << '\n'
+    << "brightness " << m_tonemapperGUI.brightness << '\n';
+  if (m_compositeMode) d << "composite " << m_compositeMode << '\n';
+  if (m_batch != 1) d << "batchIterations " << m_batch << '\n';
+  std::string path = filename;
+  if (path.empty())
+  {
+    const std::time_t now = std::time(nullptr);
+    std::tm tmv; localtime_r(&now, &tmv);
+    std::ostringstream name; name << "system_rtigo3_" << std::put_time(&tmv, "%Y%m%d_%H%M%S") << ".txt";
+    path = name.str();
+  }
+  FILE* f = std::fopen(path.c_str(), "w");
+  if (!f) return false;
+  const std::string text = d.str();
+  const bool ok = std::fwrite(text.data(), 1, text.size(), f) == text.size();
+  std::fclose(f);
+  if (ok) std::cout << path << std::endl;
+  if (writtenPath) *writtenPath = ok ? path : std::string();
+  return ok;
+}
+
+void Application::setCamera(float phi, float theta, float fov, float distance, const float center[3])
+{
+  m_camera.m_phi = phi; m_camera.m_theta = theta; m_camera.m_fov = fov; m_camera.m_distance = distance;
+  m_camera.m_center = make_float3(center[0], center[1], center[2]);
+  m_camera.markDirty();
+  CameraDefinition camera;
+  if (m_camera.getFrustum(camera.P, camera.U, camera.V, camera.W))
+  {
+    m_cameras[0] = camera;
+    if (m_raytracer) m_raytracer->updateCamera(0, camera);
+  }
+}
+
+bool Application::updateMaterial(int index, MaterialGUI const& material)
+{
+  if (index < 0 || (size_t)index >= m_materialsGUI.size()) return false;
+  const std::string name = m_materialsGUI[index].name;
+  m_materialsGUI[index] = material;
+  m_materialsGUI[index].name = name;
+  if (m_raytracer) m_raytracer->updateMaterial(index, m_materialsGUI[index]);
+  return true;
+}
+
+bool Application::updateLightEmission(int index, const float emission[3])
+{
+  if (index < 0 || (size_t)index >= m_lights.size()) return false;
+  m_lights[index].emission = make_float3(emission[0], emission[1], emission[2]);
+  if (m_raytracer) m_raytracer->updateLight(index, m_lights[index]);
+  return true;
 }
 
 void Application::restartAccumulation() { if (m_raytracer) m_raytracer->updateState(m_state); }

@@ -32,6 +32,13 @@ public:
   const float* getOutputBufferHost();                       // float4 rows bottom-up, resolution.x * resolution.y
   void tonemapDevice(std::vector<unsigned char>& rgb);      // rtc_tonemap of the current frame (device 0)
   void restartAccumulation();
+  // Application::saveSystemDescription (Application.cpp:1302-1345, the 'S' key): writes the current system options in the
+  // system description format.  An empty filename yields "system_rtigo3_<date>_<time>.txt" like the reference.
+  bool saveSystemDescription(std::string const& filename = std::string(), std::string* writtenPath = nullptr);
+  // The GUI mutators of the reference (Application.cpp:410-417, :983, :1003): each restarts the accumulation.
+  void setCamera(float phi, float theta, float fov, float distance, const float center[3]);
+  bool updateMaterial(int index, MaterialGUI const& material);
+  bool updateLightEmission(int index, const float emission[3]);
 
   // accessors
   Raytracer* getRaytracer() { return m_raytracer.get(); }

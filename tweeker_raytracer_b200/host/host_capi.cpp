@@ -93,6 +93,37 @@ int rth_app_environment(void* h, unsigned int* w, unsigned int* hgt, const float
   return 0;
 }
 
+int rth_app_save_system(void* h, const char* filename, char* path, int pathLen)
+{
+  std::string written;
+  const bool ok = static_cast<Application*>(h)->saveSystemDescription(filename ? filename : "", &written);
+  if (path && pathLen > 0) std::snprintf(path, (size_t)pathLen, "%s", written.c_str());
+  return ok ? 0 : -1;
+}
+
+// mutators (valid in host-only mode too: they update the host scene; with devices they also restart the accumulation)
+void rth_app_set_camera(void* h, float phi, float theta, float fov, float distance, const float center[3])
+{
+  static_cast<Application*>(h)->setCamera(phi, theta, fov, distance, center);
+}
+
+int rth_app_update_material(void* h, int index, int indexBSDF, const float albedo[3], const float roughness[2], const float absorptionColor[3],
+                            float absorptionScale, float ior, int thinwalled)
+{
+  MaterialGUI m;
+  m.indexBSDF = static_cast<FunctionIndex>(indexBSDF);
+  m.albedo = make_float3(albedo[0], albedo[1], albedo[2]);
+  m.roughness = make_float2(roughness[0], roughness[1]);
+  m.absorptionColor = make_float3(absorptionColor[0], absorptionColor[1], absorptionColor[2]);
+  m.absorptionScale = absorptionScale; m.ior = ior; m.thinwalled = thinwalled != 0;
+  try { return static_cast<Application*>(h)->updateMaterial(index, m) ? 0 : -1; } catch (std::exception const& e) { g_error = e.what(); return -2; }
+}
+
+int rth_app_update_light_emission(void* h, int index, const float emission[3])
+{
+  try { return static_cast<Application*>(h)->updateLightEmission(index, emission) ? 0 : -1; } catch (std::exception const& e) { g_error = e.what(); return -2; }
+}
+
 // --- device side (needs a GPU) ---
 unsigned int rth_app_render(void* h, unsigned int count) { return static_cast<Application*>(h)->render(count); }
 int rth_app_synchronize(void* h)
