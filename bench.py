@@ -32,7 +32,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "rtigo3_geometry_1080p_samples_per_s"
 UNIT = "Msamples/s"
-WORKLOAD = "rtigo3 geometry scene (planes/boxes/spheres/tori, 5 BSDFs, constant env + 4x4 parallelogram light), 1920x1080, pathLengths 2 6"
+WORKLOAD = "rtigo3 geometry scene (planes/boxes/spheres/tori, 5 BSDFs, constant env + 4x4 parallelogram light), pathLengths 2 6"
 S_RAY, S_NODE, S_TRI, S_INST = 48, 80, 48, 64
 WORKLOADS = {
     "rtigo3_geometry": WORKLOAD,
@@ -79,7 +79,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05)
 
     def summary(self):
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
@@ -159,7 +159,7 @@ def run_reference(args, rank):
         cpu_sample(args, cores, iterations=1, row_step=64)
     vals, secs, desc, mrays = [], 0.0, "", 0.0
     for _ in range(args.steps):
-        v, dt, desc, mr = cpu_sample(args, cores, iterations=4, row_step=1)
+        v, dt, desc, mr = cpu_sample(args, cores, iterations=16, row_step=1)
         vals.append(v)
         secs += dt
         mrays = mr
@@ -335,7 +335,7 @@ def main():
         if n == 1 and not args.no_cpu_baseline:
             from oracle import orc
             cores = orc.online_cores()
-            v, dt, desc, mr = cpu_sample(args, cores, iterations=24, row_step=1)
+            v, dt, desc, mr = cpu_sample(args, cores, iterations=96, row_step=1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "mrays_per_s": mr}
         print(json.dumps(line), flush=True)
     app.close()
