@@ -55,8 +55,8 @@ struct ExtendPaths
   template <class T> __device__ __forceinline__ void store(uint32_t, const T& tr) const
   {
     const TraceHit h = tr.result();
-    hit[path] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
-    hitInst[path] = h.inst;
+    __stcs(hit + path, make_float4(h.t, h.u, h.v, __uint_as_float(h.prim)));
+    __stcs(hitInst + path, h.inst);
   }
 };
 
@@ -72,10 +72,10 @@ struct ConnectPaths
   {
     if (!tr.found)
     {
-      const float4 c = contrib[path];
-      float4 L = radiance[path];
+      const float4 c = __ldcs(contrib + path);
+      float4 L = __ldcs(radiance + path);
       L.x = __fadd_rn(L.x, c.x); L.y = __fadd_rn(L.y, c.y); L.z = __fadd_rn(L.z, c.z);
-      radiance[path] = L;
+      __stcs(radiance + path, L);
     }
   }
 };

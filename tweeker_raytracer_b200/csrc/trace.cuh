@@ -109,11 +109,20 @@ __device__ __forceinline__ void box_setup(BoxRay& b, float ox, float oy, float o
 // which replaces the shift/mask/I2F triple of a plain conversion.  The plane parameter is then ONE fma:
 //   t = (32768 + q) * adj + (org - 32768 * adj),   adj = gridStep / d,  org = (p - o) / d.
 // The cancellation costs at most 2^-9 grid steps, an eighth of the 1/64 step slack the builder guarantees.
-__device__ __forceinline__ float quant_f(uint32_t w, uint32_t i) { return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7404u | (i << 4))); }
+// `bias` must hold 0x47000000 in a REGISTER (see node_test): with the constant as an immediate ptxas moves the byte selector
+// into a fresh register before every PRMT, which doubles the cost of the decode.
+template <uint32_t I>
+__device__ __forceinline__ float quant_f(uint32_t w, uint32_t bias)
+{
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(bias), "n"(0x7404u | (I << 4)));
+  return __uint_as_float(r);
+}
 
 // Tests the 8 quantised child boxes of one node.  Returns bit s set when the box in slot s is hit.
+// opaqueZero: a value that is always 0 but that the compiler cannot prove to be (bit 31 of a child index).
 __device__ __forceinline__ uint32_t node_test(const BoxRay& b, const uint4 n0, const uint4 n2, const uint4 n3, const uint4 n4,
-                                              float tmin, float tlimit)
+                                              float tmin, float tlimit, uint32_t opaqueZero)
 {
   const uint32_t e = n0.w;
   const float adjx = __uint_as_float((e & 0xffu) << 23) * b.idx;
@@ -129,19 +138,20 @@ __device__ __forceinline__ uint32_t node_test(const BoxRay& b, const uint4 n0, c
   const uint32_t neary[2] = { ny ? n4.x : n2.z, ny ? n4.y : n2.w }, fary[2] = { ny ? n2.z : n4.x, ny ? n2.w : n4.y };
   const uint32_t nearz[2] = { nz ? n4.z : n3.x, nz ? n4.w : n3.y }, farz[2] = { nz ? n3.x : n4.z, nz ? n3.y : n4.w };
   const float tlimitPad = tlimit * (1.0f + 0x1p-17f);
+  const uint32_t bias = 0x47000000u + opaqueZero;     // kept in a register on purpose, see quant_f
   uint32_t hits = 0;
-#pragma unroll
-  for (int s = 0; s < 8; ++s)
-  {
-    const int h = s >> 2;
-    const uint32_t i = (uint32_t)(s & 3);
-    const float t0x = fmaf(quant_f(nearx[h], i), adjx, orgx), t1x = fmaf(quant_f(farx[h], i), adjx, orgx);
-    const float t0y = fmaf(quant_f(neary[h], i), adjy, orgy), t1y = fmaf(quant_f(fary[h], i), adjy, orgy);
-    const float t0z = fmaf(quant_f(nearz[h], i), adjz, orgz), t1z = fmaf(quant_f(farz[h], i), adjz, orgz);
-    const float tn = fmaxf(fmaxf(fmaxf(t0x, t0y), t0z), tmin);
-    const float tf = fminf(fminf(fminf(t1x, t1y), t1z) * (1.0f + 0x1p-17f), tlimitPad);
-    if (tn <= tf) hits |= 1u << s;
+#define RTC_BOX(S, H, I) \
+  { \
+    const float t0x = fmaf(quant_f<I>(nearx[H], bias), adjx, orgx), t1x = fmaf(quant_f<I>(farx[H], bias), adjx, orgx); \
+    const float t0y = fmaf(quant_f<I>(neary[H], bias), adjy, orgy), t1y = fmaf(quant_f<I>(fary[H], bias), adjy, orgy); \
+    const float t0z = fmaf(quant_f<I>(nearz[H], bias), adjz, orgz), t1z = fmaf(quant_f<I>(farz[H], bias), adjz, orgz); \
+    const float tn = fmaxf(fmaxf(fmaxf(t0x, t0y), t0z), tmin); \
+    const float tf = fminf(fminf(fminf(t1x, t1y), t1z) * (1.0f + 0x1p-17f), tlimitPad); \
+    if (tn <= tf) hits |= 1u << S; \
   }
+  RTC_BOX(0, 0, 0) RTC_BOX(1, 0, 1) RTC_BOX(2, 0, 2) RTC_BOX(3, 0, 3)
+  RTC_BOX(4, 1, 0) RTC_BOX(5, 1, 1) RTC_BOX(6, 1, 2) RTC_BOX(7, 1, 3)
+#undef RTC_BOX
   return hits;
 }
 
@@ -239,7 +249,7 @@ struct Traversal
       const uint4* np = nodes + (size_t)(nodeGroup.x + rel) * 5u;
       const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
       if (COUNT) counts.nodes++;
-      const uint32_t hits = node_test(br, n0, n2, n3, n4, tmin, tlimit);
+      const uint32_t hits = node_test(br, n0, n2, n3, n4, tmin, tlimit, n1.x >> 31);
       const uint32_t imask = n0.w >> 24;
       nodeGroup = make_uint2(n1.x, (xor_permute8(hits & imask, br.octinv) << 24) | imask);
       // leaf children: meta = (count << 5) | first primitive (relative to triBase)
