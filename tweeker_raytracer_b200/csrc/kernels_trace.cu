@@ -7,7 +7,7 @@
 #include "trace.cuh"
 
 #ifndef RTC_TRACE_MIN_BLOCKS
-#define RTC_TRACE_MIN_BLOCKS 6      // resident CTAs per SM the traversal kernels are compiled for (register budget) and launched with
+#define RTC_TRACE_MIN_BLOCKS 7      // resident CTAs per SM the traversal kernels are compiled for (register budget) and launched with
 #endif
 
 namespace {
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kTraceBlock, RTC_TRACE_MIN_BLOCKS)
 k_trace(const SceneDesc sc, Policy policy, uint32_t n, const uint32_t* __restrict__ nPtr, uint32_t* __restrict__ cursor,
         unsigned long long* __restrict__ counts)
 {
-  __shared__ uint2 smem[RTC_SM_STACK * kTraceBlock];
+  __shared__ uint2 smem[RTC_SM_STACK * kTraceBlock + (9 * kTraceBlock + 1) / 2];     // stack columns, then nine float columns (trace.cuh smRay)
   const uint32_t count = nPtr ? *nPtr : n;      // the wavefront keeps its queue lengths on the device
   trace_stream<ANY, COUNT, kTraceBlock>(sc, count, cursor, policy, smem, counts);
 }

@@ -180,12 +180,14 @@ __device__ unsigned int g_rtcStackOverflows = 0;
 template <bool ANY, bool COUNT, int BLOCK>
 struct Traversal
 {
-  // world ray
-  float4 org, dir;
-  float tlimit;
+  // World ray origin/direction (needed only when an instance is entered or left) and the barycentric numerators of the
+  // best hit (written once per accepted hit) live in shared memory, column-major like the stack: nine registers less,
+  // which is what lets a seventh CTA fit on the SM.  Slots: 0-2 origin, 3-5 direction, 6 V, 7 W, 8 det.
+  float* smRay;               // this thread's column: slot k at smRay[k * BLOCK]
+  float tmin, tlimit;
   bool found;
-  TraceHit hit;               // u, v hold the un-normalised V, W until result() divides them by det (same operands, same bits)
-  float hitDet;
+  float hitT;                 // best t so far (the barycentric divisions are postponed to result(): same operands, same bits)
+  uint32_t hitInst, hitPrim;
   // traversal state
   uint2 nodeGroup, triGroup;
   int sp, blasBase;
@@ -213,20 +215,26 @@ struct Traversal
 
   __device__ __forceinline__ TraceHit result() const
   {
-    TraceHit h = hit;
-    if (!ANY && found) { h.u = __fdiv_rn(hit.u, hitDet); h.v = __fdiv_rn(hit.v, hitDet); }
+    TraceHit h;
+    h.t = -1.0f; h.u = 0.0f; h.v = 0.0f; h.inst = 0xffffffffu; h.prim = 0xffffffffu;
+    if (found)
+    {
+      h.t = hitT; h.inst = hitInst; h.prim = hitPrim;
+      if (!ANY) { const float det = smRay[8 * BLOCK]; h.u = __fdiv_rn(smRay[6 * BLOCK], det); h.v = __fdiv_rn(smRay[7 * BLOCK], det); }
+    }
     return h;
   }
 
   // returns false when the ray interval is empty (nothing to traverse)
   __device__ __forceinline__ bool begin(const SceneDesc& sc, const float4 o, const float4 d)
   {
-    org = o; dir = d;
-    tlimit = d.w;
+    smRay[0] = o.x; smRay[BLOCK] = o.y; smRay[2 * BLOCK] = o.z;
+    smRay[3 * BLOCK] = d.x; smRay[4 * BLOCK] = d.y; smRay[5 * BLOCK] = d.z;
+    tmin = o.w; tlimit = d.w;
     found = false;
-    hit.t = -1.0f; hit.u = 0.0f; hit.v = 0.0f; hit.inst = 0xffffffffu; hit.prim = 0xffffffffu;
+    hitT = -1.0f; hitInst = 0xffffffffu; hitPrim = 0xffffffffu;
     if (COUNT) { counts.nodes = 0; counts.tris = 0; counts.insts = 0; }
-    if (!(tlimit > o.w)) return false;
+    if (!(tlimit > tmin)) return false;
     sp = 0; blasBase = -1; curInst = 0;
     box_setup(br, o.x, o.y, o.z, d.x, d.y, d.z);
     nodes = sc.tlasNodes; tris = nullptr;
@@ -238,7 +246,6 @@ struct Traversal
   // returns true while the ray needs more steps
   __device__ __forceinline__ bool step(const SceneDesc& sc)
   {
-    const float tmin = org.w;
     if (nodeGroup.y & 0xff000000u)
     {
       const uint32_t bit = 31u - (uint32_t)__clz((int)nodeGroup.y);
@@ -282,12 +289,14 @@ struct Traversal
         const float4* ip = sc.instances + (size_t)inst * 4u;
         const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
         if (COUNT) counts.insts++;
-        orr.ox = __fmaf_rn(r0.x, org.x, __fmaf_rn(r0.y, org.y, __fmaf_rn(r0.z, org.z, r0.w)));
-        orr.oy = __fmaf_rn(r1.x, org.x, __fmaf_rn(r1.y, org.y, __fmaf_rn(r1.z, org.z, r1.w)));
-        orr.oz = __fmaf_rn(r2.x, org.x, __fmaf_rn(r2.y, org.y, __fmaf_rn(r2.z, org.z, r2.w)));
-        orr.dx = __fmaf_rn(r0.x, dir.x, __fmaf_rn(r0.y, dir.y, __fmul_rn(r0.z, dir.z)));
-        orr.dy = __fmaf_rn(r1.x, dir.x, __fmaf_rn(r1.y, dir.y, __fmul_rn(r1.z, dir.z)));
-        orr.dz = __fmaf_rn(r2.x, dir.x, __fmaf_rn(r2.y, dir.y, __fmul_rn(r2.z, dir.z)));
+        const float wox = smRay[0], woy = smRay[BLOCK], woz = smRay[2 * BLOCK];
+        const float wdx = smRay[3 * BLOCK], wdy = smRay[4 * BLOCK], wdz = smRay[5 * BLOCK];
+        orr.ox = __fmaf_rn(r0.x, wox, __fmaf_rn(r0.y, woy, __fmaf_rn(r0.z, woz, r0.w)));
+        orr.oy = __fmaf_rn(r1.x, wox, __fmaf_rn(r1.y, woy, __fmaf_rn(r1.z, woz, r1.w)));
+        orr.oz = __fmaf_rn(r2.x, wox, __fmaf_rn(r2.y, woy, __fmaf_rn(r2.z, woz, r2.w)));
+        orr.dx = __fmaf_rn(r0.x, wdx, __fmaf_rn(r0.y, wdy, __fmul_rn(r0.z, wdz)));
+        orr.dy = __fmaf_rn(r1.x, wdx, __fmaf_rn(r1.y, wdy, __fmul_rn(r1.z, wdz)));
+        orr.dz = __fmaf_rn(r2.x, wdx, __fmaf_rn(r2.y, wdy, __fmul_rn(r2.z, wdz)));
         shear_setup(orr);
         box_setup(br, orr.ox, orr.oy, orr.oz, orr.dx, orr.dy, orr.dz);
         curInst = inst;
@@ -309,16 +318,17 @@ struct Traversal
           const uint32_t prim = __float_as_uint(v0.w);
           if (ANY)
           {
-            if (t < tlimit) { hit.t = t; hit.inst = curInst; hit.prim = prim; found = true; return false; }
+            if (t < tlimit) { hitT = t; hitInst = curInst; hitPrim = prim; found = true; return false; }
           }
           else
           {
-            const bool better = found ? (t < hit.t || (t == hit.t && (curInst < hit.inst || (curInst == hit.inst && prim < hit.prim))))
+            const bool better = found ? (t < hitT || (t == hitT && (curInst < hitInst || (curInst == hitInst && prim < hitPrim))))
                                       : (t < tlimit);
             if (better)
             {
               found = true; tlimit = t;
-              hit.t = t; hit.u = V; hit.v = W; hitDet = det; hit.inst = curInst; hit.prim = prim;
+              hitT = t; hitInst = curInst; hitPrim = prim;
+              smRay[6 * BLOCK] = V; smRay[7 * BLOCK] = W; smRay[8 * BLOCK] = det;
             }
           }
         }
@@ -331,7 +341,7 @@ struct Traversal
       {
         blasBase = -1;   // leave the instance: back to the world-space ray
         nodes = sc.tlasNodes;
-        box_setup(br, org.x, org.y, org.z, dir.x, dir.y, dir.z);
+        box_setup(br, smRay[0], smRay[BLOCK], smRay[2 * BLOCK], smRay[3 * BLOCK], smRay[4 * BLOCK], smRay[5 * BLOCK]);
       }
       if (sp == 0) return false;
       nodeGroup = pop();
@@ -350,6 +360,7 @@ __device__ __forceinline__ void trace_stream(const SceneDesc& sc, uint32_t n, ui
   Traversal<ANY, COUNT, BLOCK> tr;
   uint2 overflow[RTC_LM_STACK];
   tr.smStack = smem + threadIdx.x;
+  tr.smRay = reinterpret_cast<float*>(smem + RTC_SM_STACK * BLOCK) + threadIdx.x;
   tr.lmStack = overflow;
   const uint32_t lane = threadIdx.x & 31u;
   bool active = false, exhausted = false;
