@@ -7,7 +7,7 @@
 #include "trace.cuh"
 
 #ifndef RTC_TRACE_MIN_BLOCKS
-#define RTC_TRACE_MIN_BLOCKS 7      // resident CTAs per SM the traversal kernels are compiled for (register budget) and launched with
+#define RTC_TRACE_MIN_BLOCKS 8      // resident CTAs per SM the traversal kernels are compiled for (register budget) and launched with
 #endif
 
 namespace {
@@ -34,7 +34,7 @@ struct QueryAny
 {
   const float4* __restrict__ rays; uint32_t* __restrict__ occluded;
   __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d) const { o = __ldg(rays + 2 * (size_t)i); d = __ldg(rays + 2 * (size_t)i + 1); return true; }
-  template <class T> __device__ __forceinline__ void store(uint32_t i, const T& tr) const { occluded[i] = tr.found ? 1u : 0u; }
+  template <class T> __device__ __forceinline__ void store(uint32_t i, const T& tr) const { occluded[i] = tr.found() ? 1u : 0u; }
 };
 
 // rtc_trace_count: rays in, nothing out (the counters are the result)
@@ -70,7 +70,7 @@ struct ConnectPaths
   __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d) { path = queue[i]; o = shadowOrg[path]; d = shadowDir[path]; return true; }
   template <class T> __device__ __forceinline__ void store(uint32_t, const T& tr) const
   {
-    if (!tr.found)
+    if (!tr.found())
     {
       const float4 c = __ldcs(contrib + path);
       float4 L = __ldcs(radiance + path);
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kTraceBlock, RTC_TRACE_MIN_BLOCKS)
 k_trace(const SceneDesc sc, Policy policy, uint32_t n, const uint32_t* __restrict__ nPtr, uint32_t* __restrict__ cursor,
         unsigned long long* __restrict__ counts)
 {
-  __shared__ uint2 smem[RTC_SM_STACK * kTraceBlock + (9 * kTraceBlock + 1) / 2];     // stack columns, then nine float columns (trace.cuh smRay)
+  __shared__ uint2 smem[RTC_SM_STACK * kTraceBlock + (11 * kTraceBlock + 1) / 2];     // stack columns, then eleven float columns (trace.cuh smRay)
   const uint32_t count = nPtr ? *nPtr : n;      // the wavefront keeps its queue lengths on the device
   trace_stream<ANY, COUNT, kTraceBlock>(sc, count, cursor, policy, smem, counts);
 }

@@ -22,9 +22,11 @@ struct TraceHit
   uint32_t inst, prim;
 };
 
+// Shear constants of the current object-space ray (its origin is BoxRay::ox/oy/oz: inside an instance the box test and the
+// triangle test share it).
 struct ObjRay
 {
-  float ox, oy, oz, dx, dy, dz;
+  float dx, dy, dz;          // only live during the set-up at instance entry
   float Sx, Sy, Sz;
   int   kx, ky, kz;
 };
@@ -53,12 +55,12 @@ __device__ __forceinline__ void shear_setup(ObjRay& r)
 }
 
 // Woop/Benthin/Wald watertight test; see the oracle for the definition this mirrors operation by operation.
-__device__ __forceinline__ bool tri_test(const ObjRay& r, const float4 v0, const float4 v1, const float4 v2,
+__device__ __forceinline__ bool tri_test(const ObjRay& r, float ox, float oy, float oz, const float4 v0, const float4 v1, const float4 v2,
                                          float& t, float& det, float& V, float& W)
 {
-  const float A0 = __fsub_rn(v0.x, r.ox), A1 = __fsub_rn(v0.y, r.oy), A2 = __fsub_rn(v0.z, r.oz);
-  const float B0 = __fsub_rn(v1.x, r.ox), B1 = __fsub_rn(v1.y, r.oy), B2 = __fsub_rn(v1.z, r.oz);
-  const float C0 = __fsub_rn(v2.x, r.ox), C1 = __fsub_rn(v2.y, r.oy), C2 = __fsub_rn(v2.z, r.oz);
+  const float A0 = __fsub_rn(v0.x, ox), A1 = __fsub_rn(v0.y, oy), A2 = __fsub_rn(v0.z, oz);
+  const float B0 = __fsub_rn(v1.x, ox), B1 = __fsub_rn(v1.y, oy), B2 = __fsub_rn(v1.z, oz);
+  const float C0 = __fsub_rn(v2.x, ox), C1 = __fsub_rn(v2.y, oy), C2 = __fsub_rn(v2.z, oz);
   const float Akz = sel3(A0, A1, A2, r.kz), Bkz = sel3(B0, B1, B2, r.kz), Ckz = sel3(C0, C1, C2, r.kz);
   const float Ax = __fmaf_rn(-r.Sx, Akz, sel3(A0, A1, A2, r.kx)), Ay = __fmaf_rn(-r.Sy, Akz, sel3(A0, A1, A2, r.ky));
   const float Bx = __fmaf_rn(-r.Sx, Bkz, sel3(B0, B1, B2, r.kx)), By = __fmaf_rn(-r.Sy, Bkz, sel3(B0, B1, B2, r.ky));
@@ -182,10 +184,10 @@ struct Traversal
 {
   // World ray origin/direction (needed only when an instance is entered or left) and the barycentric numerators of the
   // best hit (written once per accepted hit) live in shared memory, column-major like the stack: nine registers less,
-  // which is what lets a seventh CTA fit on the SM.  Slots: 0-2 origin, 3-5 direction, 6 V, 7 W, 8 det.
+  // which is what lets more CTAs fit on the SM.  Slots: 0-2 origin, 3-5 direction, 6 V, 7 W, 8 det, 9-10 triangle array of the
+  // current GAS (pointer bits).
   float* smRay;               // this thread's column: slot k at smRay[k * BLOCK]
   float tmin, tlimit;
-  bool found;
   float hitT;                 // best t so far (the barycentric divisions are postponed to result(): same operands, same bits)
   uint32_t hitInst, hitPrim;
   // traversal state
@@ -195,7 +197,6 @@ struct Traversal
   BoxRay br;
   ObjRay orr;
   const uint4*  nodes;
-  const float4* tris;
   uint2* smStack;             // this thread's column of the shared stack: entry k at smStack[k * BLOCK]
   uint2* lmStack;             // overflow entries (a local array owned by the caller)
   TraceCounts counts;
@@ -213,11 +214,13 @@ struct Traversal
     return (sp < RTC_SM_STACK) ? smStack[sp * BLOCK] : lmStack[(sp - RTC_SM_STACK) & (RTC_LM_STACK - 1)];
   }
 
+  __device__ __forceinline__ bool found() const { return hitInst != 0xffffffffu; }
+
   __device__ __forceinline__ TraceHit result() const
   {
     TraceHit h;
     h.t = -1.0f; h.u = 0.0f; h.v = 0.0f; h.inst = 0xffffffffu; h.prim = 0xffffffffu;
-    if (found)
+    if (found())
     {
       h.t = hitT; h.inst = hitInst; h.prim = hitPrim;
       if (!ANY) { const float det = smRay[8 * BLOCK]; h.u = __fdiv_rn(smRay[6 * BLOCK], det); h.v = __fdiv_rn(smRay[7 * BLOCK], det); }
@@ -231,13 +234,12 @@ struct Traversal
     smRay[0] = o.x; smRay[BLOCK] = o.y; smRay[2 * BLOCK] = o.z;
     smRay[3 * BLOCK] = d.x; smRay[4 * BLOCK] = d.y; smRay[5 * BLOCK] = d.z;
     tmin = o.w; tlimit = d.w;
-    found = false;
     hitT = -1.0f; hitInst = 0xffffffffu; hitPrim = 0xffffffffu;
     if (COUNT) { counts.nodes = 0; counts.tris = 0; counts.insts = 0; }
     if (!(tlimit > tmin)) return false;
     sp = 0; blasBase = -1; curInst = 0;
     box_setup(br, o.x, o.y, o.z, d.x, d.y, d.z);
-    nodes = sc.tlasNodes; tris = nullptr;
+    nodes = sc.tlasNodes;
     nodeGroup = make_uint2(0u, 0x80000000u);
     triGroup = make_uint2(0u, 0u);
     return true;
@@ -291,42 +293,43 @@ struct Traversal
         if (COUNT) counts.insts++;
         const float wox = smRay[0], woy = smRay[BLOCK], woz = smRay[2 * BLOCK];
         const float wdx = smRay[3 * BLOCK], wdy = smRay[4 * BLOCK], wdz = smRay[5 * BLOCK];
-        orr.ox = __fmaf_rn(r0.x, wox, __fmaf_rn(r0.y, woy, __fmaf_rn(r0.z, woz, r0.w)));
-        orr.oy = __fmaf_rn(r1.x, wox, __fmaf_rn(r1.y, woy, __fmaf_rn(r1.z, woz, r1.w)));
-        orr.oz = __fmaf_rn(r2.x, wox, __fmaf_rn(r2.y, woy, __fmaf_rn(r2.z, woz, r2.w)));
+        const float oox = __fmaf_rn(r0.x, wox, __fmaf_rn(r0.y, woy, __fmaf_rn(r0.z, woz, r0.w)));
+        const float ooy = __fmaf_rn(r1.x, wox, __fmaf_rn(r1.y, woy, __fmaf_rn(r1.z, woz, r1.w)));
+        const float ooz = __fmaf_rn(r2.x, wox, __fmaf_rn(r2.y, woy, __fmaf_rn(r2.z, woz, r2.w)));
         orr.dx = __fmaf_rn(r0.x, wdx, __fmaf_rn(r0.y, wdy, __fmul_rn(r0.z, wdz)));
         orr.dy = __fmaf_rn(r1.x, wdx, __fmaf_rn(r1.y, wdy, __fmul_rn(r1.z, wdz)));
         orr.dz = __fmaf_rn(r2.x, wdx, __fmaf_rn(r2.y, wdy, __fmul_rn(r2.z, wdz)));
         shear_setup(orr);
-        box_setup(br, orr.ox, orr.oy, orr.oz, orr.dx, orr.dy, orr.dz);
+        box_setup(br, oox, ooy, ooz, orr.dx, orr.dy, orr.dz);
         curInst = inst;
         blasBase = sp;
         nodes = reinterpret_cast<const uint4*>(((unsigned long long)__float_as_uint(r3.y) << 32) | __float_as_uint(r3.x));
-        tris  = reinterpret_cast<const float4*>(((unsigned long long)__float_as_uint(r3.w) << 32) | __float_as_uint(r3.z));
+        smRay[9 * BLOCK] = r3.z; smRay[10 * BLOCK] = r3.w;
         nodeGroup = make_uint2(0u, 0x80000000u);
         triGroup = make_uint2(0u, 0u);
         break;
       }
       else
       {
+        const float4* tris = reinterpret_cast<const float4*>(((unsigned long long)__float_as_uint(smRay[10 * BLOCK]) << 32) | __float_as_uint(smRay[9 * BLOCK]));
         const float4* tp = tris + (size_t)(triGroup.x + idx) * 3u;
         const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
         if (COUNT) counts.tris++;
         float t, det, V, W;
-        if (tri_test(orr, v0, v1, v2, t, det, V, W) && t > tmin)
+        if (tri_test(orr, br.ox, br.oy, br.oz, v0, v1, v2, t, det, V, W) && t > tmin)
         {
           const uint32_t prim = __float_as_uint(v0.w);
           if (ANY)
           {
-            if (t < tlimit) { hitT = t; hitInst = curInst; hitPrim = prim; found = true; return false; }
+            if (t < tlimit) { hitT = t; hitInst = curInst; hitPrim = prim; return false; }
           }
           else
           {
-            const bool better = found ? (t < hitT || (t == hitT && (curInst < hitInst || (curInst == hitInst && prim < hitPrim))))
+            const bool better = found() ? (t < hitT || (t == hitT && (curInst < hitInst || (curInst == hitInst && prim < hitPrim))))
                                       : (t < tlimit);
             if (better)
             {
-              found = true; tlimit = t;
+              tlimit = t;
               hitT = t; hitInst = curInst; hitPrim = prim;
               smRay[6 * BLOCK] = V; smRay[7 * BLOCK] = W; smRay[8 * BLOCK] = det;
             }
