@@ -76,7 +76,12 @@ def main():
         t0 = time.perf_counter()
         gas = ctx.gas_build(verts.data_ptr(), 12, 3 * nt, idx.data_ptr(), nt, core.BUILD_GPU_LBVH)
         ctx.synchronize()
-        build_s = time.perf_counter() - t0
+        first_build_s = time.perf_counter() - t0          # includes first-use cudaMalloc / module load effects
+        ctx.gas_destroy(gas)
+        t0 = time.perf_counter()
+        gas = ctx.gas_build(verts.data_ptr(), 12, 3 * nt, idx.data_ptr(), nt, core.BUILD_GPU_LBVH)
+        ctx.synchronize()
+        build_s = time.perf_counter() - t0                # steady state: scratch allocation + kernels + the per-level host syncs
         inst = __import__("numpy").zeros(1, dtype=core.INSTANCE_DTYPE)
         inst[0]["transform"] = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0]
         inst[0]["gas"] = gas
@@ -98,6 +103,7 @@ def main():
                     ms = ctx.timer_stop()
                     best = ms if best is None or _ == 1 else min(best, ms)
                 subset = rays[::16].contiguous()          # every 16th ray: same distribution as the full set
+                torch.cuda.synchronize()                  # torch's stream and the context's stream are not ordered
                 counts = ctx.trace_count(top, subset.data_ptr(), subset.shape[0], any_hit=(mode == "any"))
                 per_ray = (48 * counts.rays + 80 * counts.nodes + 48 * counts.tris + 64 * counts.instances) / max(counts.rays, 1)
                 if mode == "closest":
@@ -108,7 +114,7 @@ def main():
                         "hit_rate": hit_rate, "nodes_per_ray": counts.nodes / max(counts.rays, 1), "tris_per_ray": counts.tris / max(counts.rays, 1),
                         "algorithmic_bytes_per_ray": per_ray, "achieved_gbs": per_ray * n / (best * 1e-3) / 1e9,
                         "frac_of_measured_hbm": per_ray * n / (best * 1e-3) / 1e9 / peak,
-                        "build_s": build_s, "build_mtris_per_s": nt / build_s / 1e6, "bvh_nodes": int(info.numNodes),
+                        "build_s": build_s, "first_build_s": first_build_s, "build_mtris_per_s": nt / build_s / 1e6, "bvh_nodes": int(info.numNodes),
                         "bvh_mb": (info.numNodes * 80 + info.numTris * 48) / 1e6}
                 lines.append(line)
                 print(json.dumps(line), flush=True)

@@ -16,7 +16,10 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <cfloat>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 namespace {
 
@@ -362,11 +365,19 @@ k_collapse_level(const CollapseParams P, const int2* __restrict__ work, uint32_t
   P.nodes[dst] = node;
 }
 
+// Build scratch comes from the stream-ordered pool (cudaMallocAsync): a synchronous cudaMalloc/cudaFree of a dozen
+// multi-gigabyte arrays costs far more wall time than the build kernels themselves (100 M triangles: 57 ms of kernels).
 struct DeviceFree
 {
+  cudaStream_t stream = nullptr;
   std::vector<void*> ptrs;
-  ~DeviceFree() { for (void* p : ptrs) cudaFree(p); }
-  template <class T> cudaError_t alloc(T** p, size_t count) { cudaError_t e = cudaMalloc((void**)p, count * sizeof(T) + 16); if (e == cudaSuccess) ptrs.push_back(*p); return e; }
+  ~DeviceFree() { for (void* p : ptrs) cudaFreeAsync(p, stream); }
+  template <class T> cudaError_t alloc(T** p, size_t count)
+  {
+    cudaError_t e = cudaMallocAsync((void**)p, count * sizeof(T) + 16, stream);
+    if (e == cudaSuccess) ptrs.push_back(*p);
+    return e;
+  }
 };
 
 } // namespace
@@ -381,7 +392,17 @@ int build_gas_gpu(rtc_context* ctx, GasRecord& rec)
   if (n == 0) RTC_FAIL("build_gas_gpu needs at least one triangle");
   if (n > 0x3fffffffu) RTC_FAIL("too many triangles for one GAS");
   cudaStream_t st = ctx->stream;
+  const bool verbose = std::getenv("RTC_BUILD_VERBOSE") != nullptr;     // phase timings on stderr
+  auto tick = std::chrono::steady_clock::now();
+  auto phase = [&](const char* name) {
+    if (!verbose) return;
+    cudaStreamSynchronize(st);
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "build_gas_gpu[%u tris] %-10s %8.3f ms\n", n, name, std::chrono::duration<double, std::milli>(now - tick).count());
+    tick = now;
+  };
   DeviceFree scratch;
+  scratch.stream = st;
   BuildArrays A{};
   uint32_t* d_counters = nullptr;       // [0] bad index, [1] cut count, [2] wide nodes, [3] tris, [4..5] level queue counts
   int* d_cut = nullptr; PrimBox* d_cutBoxes = nullptr;
@@ -397,6 +418,7 @@ int build_gas_gpu(rtc_context* ctx, GasRecord& rec)
   RTC_CUDA(scratch.alloc(&A.flags, n)); RTC_CUDA(scratch.alloc(&A.sceneBox, 8));
   RTC_CUDA(scratch.alloc(&d_counters, 8)); RTC_CUDA(scratch.alloc(&d_cut, cutCapacity)); RTC_CUDA(scratch.alloc(&d_cutBoxes, cutCapacity));
 
+  phase("alloc");
   const float initBox[6] = { FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX };
   RTC_CUDA(cudaMemcpyAsync(A.sceneBox, initBox, sizeof(initBox), cudaMemcpyHostToDevice, st));
   RTC_CUDA(cudaMemsetAsync(d_counters, 0, 8 * sizeof(uint32_t), st));
@@ -416,6 +438,7 @@ int build_gas_gpu(rtc_context* ctx, GasRecord& rec)
     RTC_CUDA(cub::DeviceRadixSort::SortPairs(temp, tempBytes, k, v, (int)n, 0, 63, st));
     A.keys = k.Current(); A.order = v.Current();
   }
+  phase("sort");
   if (n > 1)
   {
     k_radix_tree<<<(n - 1 + kB - 1) / kB, kB, 0, st>>>(A.keys, (int)n, A.child, A.parent, A.range);
@@ -432,6 +455,7 @@ int build_gas_gpu(rtc_context* ctx, GasRecord& rec)
   if (hostCounters[0]) RTC_FAIL("triangle index out of range");
   for (int k = 0; k < 3; ++k) { rec.lo[k] = hostBox[k]; rec.hi[k] = hostBox[3 + k]; }
 
+  phase("tree+fit");
   // ---- SAH-binned top levels over a cut of the radix tree
   int rootNode = (n == 1) ? 0 : 0;            // binary root (for n == 1 the single leaf has id n-1 = 0)
   if (n > 8 * kLeafMax * 64)
@@ -470,6 +494,7 @@ int build_gas_gpu(rtc_context* ctx, GasRecord& rec)
     }
   }
 
+  phase("sah-top");
   // ---- collapse, level by level
   const size_t maxWide = (size_t)n + 16;          // every wide node but the root has a sibling group parent: < n nodes
   RTC_CUDA(cudaMalloc(&rec.d_nodes, maxWide * sizeof(Node8)));
@@ -486,9 +511,10 @@ int build_gas_gpu(rtc_context* ctx, GasRecord& rec)
   RTC_CUDA(cudaMemcpyAsync(d_counters + 3, &zero, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   RTC_CUDA(cudaMemcpyAsync(d_work[0], &rootWork, sizeof(int2), cudaMemcpyHostToDevice, st));
   uint32_t workCount = 1;
-  int cur = 0;
+  int cur = 0, levels = 0;
   while (workCount)
   {
+    ++levels;
     RTC_CUDA(cudaMemcpyAsync(d_counters + 4, &zero, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     k_collapse_level<<<(workCount + 127) / 128, 128, 0, st>>>(P, d_work[cur], workCount, d_work[cur ^ 1], d_counters + 4);
     ctx->kernelLaunches++;
@@ -499,6 +525,8 @@ int build_gas_gpu(rtc_context* ctx, GasRecord& rec)
   RTC_CUDA(cudaMemcpyAsync(hostCounters, d_counters, sizeof(hostCounters), cudaMemcpyDeviceToHost, st));
   RTC_CUDA(cudaStreamSynchronize(st));
   RTC_CUDA(cudaGetLastError());
+  phase("collapse");
+  if (verbose) std::fprintf(stderr, "build_gas_gpu[%u tris] %d collapse levels, %u wide nodes\n", n, levels, hostCounters[2]);
   if (hostCounters[3] != n) RTC_FAIL("GPU build lost triangles (internal error)");
   rec.numNodes = hostCounters[2];
   // the node array was sized for the worst case (one wide node per triangle): shrink it to what the collapse produced

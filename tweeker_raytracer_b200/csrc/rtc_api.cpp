@@ -123,6 +123,16 @@ int rtc_context_create(int deviceOrdinal, rtc_context** out)
   RTC_CUDA(cudaGetDeviceProperties(&prop, deviceOrdinal));
   ctx->numSMs = prop.multiProcessorCount;
   RTC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  {
+    // keep freed build scratch in the device's default memory pool instead of returning it to the OS at every synchronise
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, deviceOrdinal) == cudaSuccess)
+    {
+      uint64_t threshold = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    cudaGetLastError();
+  }
   RTC_CUDA(cudaEventCreate(&ctx->evA));
   RTC_CUDA(cudaEventCreate(&ctx->evB));
   RTC_CUDA(cudaEventCreate(&ctx->evTimerA));
