@@ -2,7 +2,8 @@
 """bench.py -- the headline measurement: 1080p samples/s (and Mrays/s) of the rtigo3 geometry scene.
 
   python bench.py --gpus N --steps K --warmup W            the B200 core (this repository)
-  python bench.py --impl reference --gpus N ...            the scalar CPU restatement of the reference (oracle/), host cores
+  python bench.py --impl reference --gpus N ...            the reference's own device programs compiled for the host
+                                                           (oracle/_ref, one process per core; oracle port if absent)
 
 A "step" renders `--spp-per-step` iterations (samples per pixel) of the 1920x1080 frame: generate -> [extend -> shade ->
 connect] x depth -> accumulate, i.e. one pass of the hot path over one batch of 1920*1080*spp path samples.
@@ -15,7 +16,9 @@ connect] x depth -> accumulate, i.e. one pass of the hot path over one batch of 
             librtcore) with the camera uploaded from host memory and the float4 frame read back to host memory every step.
   roofline  the extend (closest-hit traversal) kernel: algorithmic bytes (rays 48 B + nodes 80 B + triangles 48 B +
             instance records 64 B, counted by a second, untimed pass with the same seeds) / its device time.
-  cpu_baseline  oracle/ (scalar C restatement, kind "port") on a bounded sample of the same workload, host threads.
+  cpu_baseline  oracle/_ref (the reference's shader sources host-compiled, kind "reference"; traversal served by the
+            oracle's intersector) on a bounded sample of the same workload, one process per host core; kind "port"
+            (oracle/rt_oracle.c, threads) where libref.so is not available.
 """
 import argparse
 import json
@@ -131,7 +134,7 @@ def scene_file(tmp, args):
 
 
 def cpu_sample(args, threads, iterations=2, row_step=16, host_only_app=None):
-    """Oracle on rows y % row_step == 0 for `iterations` samples per pixel; returns (Msamples/s, seconds, description)."""
+    """Oracle (kind "port") on rows y % row_step == 0 for `iterations` samples per pixel; returns (Msamples/s, seconds, description, Mrays/s)."""
     import helpers as H
     from oracle import orc
     from tweeker_raytracer_b200 import host
@@ -149,26 +152,91 @@ def cpu_sample(args, threads, iterations=2, row_step=16, host_only_app=None):
     return st.pathSamples / dt / 1e6, dt, desc, (st.radianceRays + st.shadowRays) / dt / 1e6
 
 
+# ---- the reference's own device programs, compiled for the host (oracle/_ref/libref.so), one process per core -------------
+_REF = {}
+
+
+def _ref_init(system_path, scene_path):
+    import helpers as H
+    from oracle import orc
+    from tweeker_raytracer_b200 import host
+    app = host.App(system_path, scene_path, host_only=True)
+    scene = H.oracle_scene(app, "libm")
+    _REF.update(app=app, scene=scene, ref=orc.Reference(scene, app.info.miss), sysd=H.oracle_sys(app))
+
+
+def _ref_rows(task):
+    k, procs, iterations = task
+    app = _REF["app"]
+    w, h = app.resolution
+    t0 = time.perf_counter()
+    _REF["ref"].render(_REF["sysd"], w, h, iter_count=iterations, row_step=procs, row_offset=k)
+    return time.perf_counter() - t0
+
+
+class ReferencePool:
+    """The reference keeps its launch parameters in a global, so it is parallelised over processes: worker k renders the
+    launch rows y % P == k.  Set-up (scene load, oracle BVH for optixTrace) happens once per worker, outside the timing."""
+
+    def __init__(self, args, procs):
+        import multiprocessing as mp
+        tmp = tempfile.mkdtemp()
+        self.system_path, self.scene_path = system_file(tmp, args, 0), scene_file(tmp, args)
+        self.procs = procs
+        self.pool = mp.get_context("fork").Pool(procs, initializer=_ref_init, initargs=(self.system_path, self.scene_path))
+        self.pool.map(_ref_rows, [(k, 64 * procs, 1) for k in range(procs)])       # touch every worker (set-up done)
+        self.resolution = tuple(int(v) for v in args.resolution.split())
+
+    def sample(self, iterations):
+        t0 = time.perf_counter()
+        self.pool.map(_ref_rows, [(k, self.procs, iterations) for k in range(self.procs)], chunksize=1)
+        dt = time.perf_counter() - t0
+        w, h = self.resolution
+        n = w * h * iterations
+        return n / dt / 1e6, dt, "full %dx%d frame, %d spp = %d path samples in %.2f s, %d processes" % (w, h, iterations, n, dt, self.procs)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_reference(args, iterations, pool=None):
+    """(value, seconds, description, cores, kind): oracle/_ref when it is built ("reference"), else the oracle port."""
+    from oracle import orc
+    cores = orc.online_cores()
+    if orc.reference_available():
+        own = pool is None
+        pool = pool or ReferencePool(args, cores)
+        v, dt, desc = pool.sample(iterations)
+        if own:
+            pool.close()
+        return v, dt, desc, cores, "reference"
+    v, dt, desc, _ = cpu_sample(args, cores, iterations=iterations, row_step=1)
+    return v, dt, desc, cores, "port"
+
+
 def run_reference(args, rank):
-    """The reference arm: the scalar CPU restatement (oracle/, kind "port") with every host thread, rank 0 only."""
+    """The reference arm: the reference's own device programs compiled for the host (oracle/_ref, kind "reference", one
+    process per host core; falls back to the oracle port where libref.so does not exist), rank 0 only."""
     if rank != 0:
         return
     from oracle import orc
     cores = orc.online_cores()
+    pool = ReferencePool(args, cores) if orc.reference_available() else None
     for _ in range(min(args.warmup, 1)):
-        cpu_sample(args, cores, iterations=1, row_step=64)
-    vals, secs, desc, mrays = [], 0.0, "", 0.0
+        cpu_reference(args, 1, pool)
+    vals, secs, desc, kind = [], 0.0, "", "port"
     for _ in range(args.steps):
-        v, dt, desc, mr = cpu_sample(args, cores, iterations=16, row_step=1)
+        v, dt, desc, cores, kind = cpu_reference(args, 16, pool)
         vals.append(v)
         secs += dt
-        mrays = mr
+    if pool:
+        pool.close()
     value = sum(vals) / len(vals)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": workload(args), "sample_per_step": desc},
-            "mrays_per_s": mrays,
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": "each step: " + desc},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": "each step: " + desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -333,10 +401,8 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 48 + 192, "d2h_bytes_per_step": pixels * 16},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline}
         if n == 1 and not args.no_cpu_baseline:
-            from oracle import orc
-            cores = orc.online_cores()
-            v, dt, desc, mr = cpu_sample(args, cores, iterations=96, row_step=1)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "mrays_per_s": mr}
+            v, dt, desc, cores, kind = cpu_reference(args, 96)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
         print(json.dumps(line), flush=True)
     app.close()
     if dist is not None:

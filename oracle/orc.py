@@ -41,6 +41,10 @@ def build_reference():
     return REF_LIB if os.path.exists(REF_LIB) else None
 
 
+def reference_available():
+    return os.path.exists(REF_LIB) or os.path.isdir(REFERENCE_SHADERS)
+
+
 class Float3(C.Structure):
     _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
 
@@ -244,6 +248,7 @@ class Reference:
         R.ref_setup.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_float]
         R.ref_render.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        R.ref_render_rows.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         R.ref_tea4.argtypes = [C.c_uint, C.c_uint]
         R.ref_tea4.restype = C.c_uint
         R.ref_rng.argtypes = [C.POINTER(C.c_uint)]
@@ -263,10 +268,12 @@ class Reference:
                     _ptr(env[0]) if env else None, env[0].shape[1] if env else 0, env[0].shape[0] if env else 0,
                     _ptr(env[1]) if env else None, _ptr(env[2]) if env else None, C.c_float(env[3] if env else 1.0))
 
-    def render(self, sys, launch_width, launch_height, local_copy=False, iter_first=0, iter_count=1):
-        n = launch_width * launch_height if local_copy else sys.resolution.x * sys.resolution.y
-        buffer = np.zeros((n, 4), dtype=np.float32)
-        self.R.ref_render(C.byref(sys), launch_width, launch_height, 1 if local_copy else 0, iter_first, iter_count, _ptr(buffer))
+    def render(self, sys, launch_width, launch_height, local_copy=False, iter_first=0, iter_count=1, row_step=1, row_offset=0, buffer=None):
+        if buffer is None:
+            n = launch_width * launch_height if local_copy else sys.resolution.x * sys.resolution.y
+            buffer = np.zeros((n, 4), dtype=np.float32)
+        self.R.ref_render_rows(C.byref(sys), launch_width, launch_height, 1 if local_copy else 0, iter_first, iter_count, row_step, row_offset,
+                               _ptr(buffer))
         return buffer
 
     def tea4(self, a, b):

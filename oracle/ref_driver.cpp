@@ -199,9 +199,21 @@ void ref_setup(const orc_scene* scene, int miss, int numInstances, const void* c
 }
 
 // values: the non-pointer fields of SystemData as this repository's rt_SystemData carries them (same layout).
+// rowStep / rowOffset restrict the work to launch rows y with y % rowStep == rowOffset, so that several PROCESSES (the
+// reference keeps its launch parameters in one global, so threads cannot share it) can split a frame between them.
+void ref_render_rows(const rt_SystemData* values, unsigned int launchWidth, unsigned int launchHeight, int localCopy,
+                     int iterFirst, int iterCount, int rowStep, int rowOffset, float* buffer);
+
 void ref_render(const rt_SystemData* values, unsigned int launchWidth, unsigned int launchHeight, int localCopy,
                 int iterFirst, int iterCount, float* buffer)
 {
+  ref_render_rows(values, launchWidth, launchHeight, localCopy, iterFirst, iterCount, 1, 0, buffer);
+}
+
+void ref_render_rows(const rt_SystemData* values, unsigned int launchWidth, unsigned int launchHeight, int localCopy,
+                     int iterFirst, int iterCount, int rowStep, int rowOffset, float* buffer)
+{
+  if (rowStep < 1) rowStep = 1;
   sysData.resolution = make_int2(values->resolution.x, values->resolution.y);
   sysData.tileSize = make_int2(values->tileSize.x, values->tileSize.y);
   sysData.tileShift = make_int2(values->tileShift.x, values->tileShift.y);
@@ -217,11 +229,14 @@ void ref_render(const rt_SystemData* values, unsigned int launchWidth, unsigned 
   {
     sysData.iterationIndex = it;
     for (unsigned int y = 0; y < launchHeight; ++y)
+    {
+      if ((int)(y % (unsigned int)rowStep) != rowOffset) continue;
       for (unsigned int x = 0; x < launchWidth; ++x)
       {
         g.launchIndex = make_uint3(x, y, 0u);
         if (localCopy) __raygen__path_tracer_local_copy(); else __raygen__path_tracer();
       }
+    }
   }
 }
 
