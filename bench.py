@@ -10,8 +10,8 @@ connect] x depth -> accumulate, i.e. one pass of the hot path over one batch of 
 
   value     whole-job Msamples/s (pixel-samples per second / 1e6) with the scene resident in HBM, device-timed with CUDA
             events on the launching stream, max over ranks.  N > 1: sample-range partition (each GPU renders its own
-            iteration indices over the full frame, scaling "weak") followed by ONE NCCL reduce of the accumulation
-            buffers, whose time is inside the timed region.
+            iteration indices over the full frame, scaling "weak") followed by ONE ncclReduce(mean) of the accumulation
+            buffers over NVLink on the render stream (the host library's own communicator), inside the timed region.
   e2e       the same metric through the reference-facing classes (Application::render -> Raytracer -> Device ->
             librtcore) with the camera uploaded from host memory and the float4 frame read back to host memory every step.
   roofline  the extend (closest-hit traversal) kernel: algorithmic bytes (rays 48 B + nodes 80 B + triangles 48 B +
@@ -63,38 +63,81 @@ def parse_args():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks, power and clock-event (throttle) reasons of ONE GPU while the timed region runs.
 
-    def __init__(self, index):
+    In-process NVML (pynvml) on a handle looked up once by UUID: ~1 kHz capable, sampled every 5 ms, and it does not
+    spawn a process per sample (nvidia-smi attaches to every GPU of the box on each call, which N ranks polling at once
+    would feel).  Falls back to polling nvidia-smi where pynvml is missing."""
+
+    def __init__(self, index, uuid=None):
         super().__init__(daemon=True)
         self.index = index
+        self.uuid = uuid
         self.stop_flag = threading.Event()
-        self.rows = []
+        self.rows = []          # (sm_mhz, sm_max_mhz, power_w, reason_bits)
+        self.source = "nvml"
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = (pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode()) if uuid
+                           else pynvml.nvmlDeviceGetHandleByIndex(index))
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.source = "nvidia-smi"
 
-    def run(self):
+    def _sample_nvml(self):
+        nv = self.nvml
+        sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+        try:
+            bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        try:
+            power = nv.nvmlDeviceGetPowerUsage(self.handle) / 1e3
+        except Exception:
+            power = None
+        reasons = set()
+        for name, bit in (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                          ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap),
+                          ("hw_power_brake_slowdown", nv.nvmlClocksEventReasonHwPowerBrakeSlowdown)):
+            if bits & bit:
+                reasons.add(name)
+        self.rows.append((sm, self.sm_max, power, reasons))
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if not out:
+            return
+        r = [c.strip() for c in out.splitlines()[0].split(",")]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = {name for k, name in enumerate(names) if len(r) > 3 + k and r[3 + k].lower().startswith("active")}
+        self.rows.append((float(r[0]), float(r[1]), float(r[2]) if r[2].replace(".", "").isdigit() else None, reasons))
+
+    def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.05)
+            self.stop_flag.wait(0.005 if self.nvml is not None else 0.05)
 
     def summary(self):
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        sm = sorted(r[0] for r in self.rows)
+        power = [r[2] for r in self.rows if r[2] is not None]
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
-            for k, name in enumerate(names):
-                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(self.rows)}
+            reasons |= r[3]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": max(r[1] for r in self.rows) if self.rows else None, "reasons": sorted(reasons),
+                "power_w_max": max(power) if power else None, "samples": len(self.rows), "source": self.source}
 
 
 def measured_traffic():
@@ -280,9 +323,20 @@ def main():
     sysd = app.system_data(0)
     info = ctx.scene_info(sysd.topObject)
 
-    # the accumulation buffer of the device-timed arm is a torch tensor so that torch.distributed (NCCL) can reduce it
+    # N > 1: the Application joins the process group of the host library (Raytracer::joinProcessGroup: sample-range partition,
+    # its own NCCL communicator on the render stream); torch.distributed carries the 128-byte id and the barriers
+    if dist is not None:
+        ids = [host.process_group_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        app.join_group(rank, world, ids[0])
+    # accumulation buffer of the device-timed arm, and the buffer the mean frame lands in on rank 0
     frame = torch.zeros(pixels * 4, dtype=torch.float32, device="cuda")
+    combined = torch.zeros(pixels * 4, dtype=torch.float32, device="cuda") if rank == 0 else None
     sysd.outputBuffer = frame.data_ptr()
+
+    def combine():
+        # the one exchange step of the path: ncclReduce(mean) of the per-rank running averages over NVLink, on the render stream
+        app.group_reduce_mean(frame.data_ptr(), combined.data_ptr() if rank == 0 else 0, pixels * 4)
 
     def step(s, count_work=False):
         # sample-range partition: rank r of n renders iteration indices (s*n + r)*S .. +S as samples s*S.. of its own average
@@ -298,28 +352,28 @@ def main():
     for s in range(W):
         step(s)
     if dist is not None:       # warm the NCCL communicator up (connection set-up is not part of a render)
-        warm = torch.zeros(pixels * 4, dtype=torch.float32, device="cuda")
-        dist.reduce(warm, dst=0, op=dist.ReduceOp.SUM)
-        del warm
-    barrier()
+        combine()
+    # NVML is initialised BEFORE the barrier: its start-up time differs from process to process, and anything between the
+    # barrier and timer_start shows up as skew in the max-over-ranks time
+    sampler = ClockSampler(local_rank, getattr(torch.cuda.get_device_properties(local_rank), "uuid", None))
     ctx.stats_reset()
     ctx.profile_enable(True)
-    sampler = ClockSampler(local_rank)
+    barrier()
+    stamps = [time.time()]
     sampler.start()
     ctx.timer_start()
+    stamps.append(time.time())
     for s in range(W, W + K):
         step(s)
-    steps_ms = ctx.timer_stop()
+    stamps.append(time.time())
+    steps_ms = ctx.timer_stop()                 # synchronises the render stream
+    stamps.append(time.time())
     reduce_ms = 0.0
     if dist is not None:
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        dist.reduce(frame, dst=0, op=dist.ReduceOp.SUM)      # NCCL over NVLink: the one exchange step of the path
-        if rank == 0:
-            frame.mul_(1.0 / n)
-        ev1.record()
-        torch.cuda.synchronize()
-        reduce_ms = ev0.elapsed_time(ev1)
+        ctx.timer_start()
+        combine()
+        reduce_ms = ctx.timer_stop()            # on each rank: waiting for the slowest rank + the transfer
+    stamps.append(time.time())
     barrier()
     sampler.stop_flag.set()
     sampler.join()
@@ -333,6 +387,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(rays, op=dist.ReduceOp.SUM)
     total_ms = float(t.item())
+    per_rank = [[steps_ms, reduce_ms]]
+    if dist is not None:        # diagnostics: each rank's own render time and its wait+reduce time
+        g = [torch.zeros(2 + len(stamps), dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(g, torch.tensor([steps_ms, reduce_ms] + stamps, dtype=torch.float64, device="cuda"))
+        t00 = min(float(x[2]) for x in g)
+        # [render ms, reduce ms, then host wall-clock ms since the first rank left the barrier: barrier exit, timer started,
+        #  steps enqueued, render finished, reduce finished]
+        per_rank = [[round(float(x[0]), 3), round(float(x[1]), 3)] + [round((float(v) - t00) * 1e3, 3) for v in x[2:]] for x in g]
     value = n * K * S * pixels / (total_ms * 1e-3) / 1e6
     mrays = float(rays.item()) / (total_ms * 1e-3) / 1e6
     launches = int(stats.kernelLaunches)
@@ -363,7 +425,9 @@ def main():
                 "note": "BVH (%.1f MB) + triangles fit the 126 MB L2, so DRAM traffic is far below the algorithmic bytes; HBM peak is the contract's denominator"
                         % ((info.numNodes * 80 + info.numTris * 48) / 1e6)}
 
-    # ---- end to end through Application::render with host buffers
+    # ---- end to end through Application::render with host buffers.  N > 1: the Application joins the process group
+    # (sample-range partition inside the host library, its own NCCL communicator), every rank renders its range and
+    # fetching the frame is a collective: ncclReduce(mean) over NVLink to rank 0, which reads the combined frame back.
     app.restart()
     cam = app.camera()
     pinned = ctx.host_alloc(48)
@@ -397,8 +461,9 @@ def main():
                            "parallelism": "sample-range x%d + NCCL reduce" % n if n > 1 else "single GPU",
                            "l2": "wavefront state per step (%.0f MB) exceeds L2 (126 MB); no explicit flush" % (S * pixels * 292 / 1e6),
                            "triangles": int(info.numTris), "bvh_nodes": int(info.numNodes), "instances": int(info.numInstances)},
-                "mrays_per_s": mrays, "reduce_ms": reduce_ms,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 48 + 192, "d2h_bytes_per_step": pixels * 16},
+                "mrays_per_s": mrays, "reduce_ms": reduce_ms, "per_rank_render_ms_and_reduce_ms": per_rank,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 48 + 192, "d2h_bytes_per_step": pixels * 16,
+                        "path": "Application::render + getOutputBufferHost per step" + (" (collective: ncclReduce mean to rank 0, then read back)" if n > 1 else "")},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline}
         if n == 1 and not args.no_cpu_baseline:
             v, dt, desc, cores, kind = cpu_reference(args, 96)

@@ -30,7 +30,7 @@ def rank_average(tmp, rank, world, steps, spp):
     frame = np.zeros((256, 4), dtype=np.float32)
     xy = np.array([(x, y) for y in range(16) for x in range(16)], dtype=np.uint32)
     for step in range(steps):
-        first, count, accum = partition.sample_range(step, rank, world, spp)
+        first, count, accum = partition.sample_range(step, rank, world, spp, steps * spp * world)
         # the oracle blends sample `it` with weight 1/(it+1); emulate accumulation index != seed index one iteration at a time
         for k in range(count):
             one = scene.path_radiance(sysd, 0, 16, xy, first + k)      # raw radiance of seed iteration first + k
@@ -69,3 +69,28 @@ def test_sample_range_partition_world2(built, tmp_path):
     single = H.oracle_scene(app).render(H.oracle_sys(app), 0, 16, 16, iter_count=8)
     app.close()
     assert np.allclose(got[:, :3], single[:, :3], rtol=1e-4, atol=1e-5)
+
+
+def test_sample_range_matches_host_library(built):
+    """partition.sample_range (Python) == Raytracer::samplesPerRank / seed offsets (C++ host), and the ranges tile the budget."""
+    from tweeker_raytracer_b200 import host, partition
+    for spp, world in [(256, 1), (256, 2), (256, 8), (1024, 4), (16, 8), (4, 8), (100, 3)]:
+        covered = []
+        for rank in range(world):
+            first, count = host.sample_range(spp, rank, world)
+            assert count == partition.samples_per_rank(spp, world)
+            assert (first, count, 0) == partition.sample_range(0, rank, world, count, spp)
+            # stepping through the range in chunks of 3 visits it exactly once
+            seen, step = [], 0
+            while True:
+                f, c, a = partition.sample_range(step, rank, world, 3, spp)
+                if c == 0:
+                    break
+                assert f == first + a
+                seen.extend(range(f, f + c))
+                step += 1
+            assert seen == list(range(first, first + count))
+            covered.extend(seen)
+        assert len(set(covered)) == len(covered)
+        if spp % world == 0:
+            assert sorted(covered) == list(range(spp))

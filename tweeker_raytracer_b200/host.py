@@ -57,7 +57,8 @@ assert C.sizeof(SystemData) == 192 and C.sizeof(CompositorData) == 56
 SYMBOLS = ["rth_last_error", "rth_app_create", "rth_app_destroy", "rth_app_info", "rth_app_geometry", "rth_app_instance",
            "rth_app_materials", "rth_app_lights", "rth_app_camera", "rth_app_system_data", "rth_app_tonemapper",
            "rth_app_environment", "rth_app_render", "rth_app_synchronize", "rth_app_frame", "rth_app_restart",
-           "rth_app_set_composite", "rth_app_save_system", "rth_app_set_camera", "rth_app_update_material", "rth_app_update_light_emission", "rth_app_benchmark", "rth_app_screenshot", "rth_app_tonemap", "rth_app_context", "rth_app_stats"]
+           "rth_app_set_composite", "rth_app_save_system", "rth_app_set_camera", "rth_app_update_material", "rth_app_update_light_emission", "rth_app_benchmark", "rth_app_screenshot", "rth_app_tonemap", "rth_app_context", "rth_app_stats",
+           "rth_process_group_id", "rth_app_join_group", "rth_app_group_reduce_mean", "rth_sample_range"]
 
 _lib = None
 
@@ -101,8 +102,28 @@ def lib():
         L.rth_app_context.argtypes = [C.c_void_p, C.c_int]
         L.rth_app_context.restype = C.c_void_p
         L.rth_app_stats.argtypes = [C.c_void_p, C.POINTER(core.Stats)]
+        L.rth_process_group_id.argtypes = [C.c_char_p]
+        L.rth_app_join_group.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+        L.rth_app_group_reduce_mean.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]
+        L.rth_sample_range.argtypes = [C.c_uint, C.c_int, C.c_int, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+        L.rth_sample_range.restype = None
         _lib = L
     return _lib
+
+
+def process_group_id():
+    """128 bytes identifying a new process group (made on rank 0; broadcast them to the other ranks out of band)."""
+    buf = C.create_string_buffer(128)
+    if lib().rth_process_group_id(buf) != 0:
+        raise core.RtcError(lib().rth_last_error().decode())
+    return buf.raw
+
+
+def sample_range(samples_per_pixel, rank, world):
+    """(first iteration, count) rank `rank` of `world` renders: Raytracer::samplesPerRank, no device needed."""
+    first, count = C.c_uint(), C.c_uint()
+    lib().rth_sample_range(samples_per_pixel, rank, world, C.byref(first), C.byref(count))
+    return first.value, count.value
 
 
 def _copy(ptr, dtype, count):
@@ -134,6 +155,12 @@ class App:
 
     def __exit__(self, *a):
         self.close()
+
+    def group_reduce_mean(self, src, dst, count):
+        """Collective: mean over the ranks of `count` floats at device address src -> dst on rank 0 (pass 0 elsewhere),
+        enqueued on the render stream (ncclReduce over NVLink)."""
+        if self.L.rth_app_group_reduce_mean(self.h, src, dst, count) != 0:
+            raise core.RtcError(self.L.rth_last_error().decode())
 
     # ---- host-side scene (valid in host_only mode too)
     @property
@@ -240,6 +267,14 @@ class App:
 
     def restart(self):
         self.L.rth_app_restart(self.h)
+
+    def join_group(self, rank, world, group_id):
+        """Raytracer::joinProcessGroup: this process becomes rank `rank` of a sample-range partition over `world`
+        processes (one GPU each).  Afterwards frame()/frame_view() are collectives; rank 0 receives the mean frame."""
+        if len(group_id) != 128:
+            raise ValueError("group_id must be the 128 bytes of process_group_id()")
+        if self.L.rth_app_join_group(self.h, rank, world, group_id) != 0:
+            raise core.RtcError(self.L.rth_last_error().decode())
 
     def set_composite(self, mode):
         self.L.rth_app_set_composite(self.h, mode)

@@ -14,8 +14,15 @@
 #include <stack>
 
 #include "ImageIO.h"
+#include "NcclComposite.h"
 #include "Parser.h"
 #include "Transform.h"
+
+static int envInt(const char* name, int fallback)
+{
+  const char* v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : fallback;
+}
 
 static const float kIdentity12[12] = { 1, 0, 0, 0,  0, 1, 0, 0,  0, 0, 1, 0 };
 
@@ -39,6 +46,14 @@ Application::Application(Options const& options, bool hostOnly)
       return;
     }
     m_camera.setResolution(m_resolution.x, m_resolution.y);
+
+    // one process per GPU: this process drives the GPU of its LOCAL_RANK as a single-GPU renderer (joined below)
+    const bool processGroup = !hostOnly && envInt("RTIGO3_PROCESS_GROUP", 0) == 1 && 1 < envInt("WORLD_SIZE", 1);
+    if (processGroup)
+    {
+      m_strategy = RS_INTERACTIVE_SINGLE_GPU;
+      m_devicesMask = 1 << envInt("LOCAL_RANK", envInt("RANK", 0));
+    }
 
     // strategy switch (Application.cpp:224-245); distribution = 1 for the multi-GPU strategies
     switch (hostOnly ? NUM_RENDERER_STRATEGIES : m_strategy)
@@ -115,6 +130,7 @@ Application::Application(Options const& options, bool hostOnly)
     m_raytracer->initMaterials(m_materialsGUI);
     m_raytracer->initScene(m_scene, m_idGeometry);
     m_isValid = true;
+    if (processGroup && !joinProcessGroupFromEnvironment()) m_isValid = false;
   }
   catch (std::exception const& e)
   {
@@ -124,6 +140,50 @@ Application::Application(Options const& options, bool hostOnly)
 }
 
 Application::~Application() {}
+
+void Application::makeProcessGroupId(char id[128]) { ncclProcessUniqueId(id); }
+
+bool Application::joinProcessGroup(int rank, int world, const char id[128])
+{
+  try { m_raytracer->joinProcessGroup(rank, world, id); return true; }
+  catch (std::exception const& e) { m_lastError = e.what(); std::cerr << e.what() << std::endl; return false; }
+}
+
+bool Application::joinProcessGroupFromEnvironment()
+{
+  const int world = envInt("WORLD_SIZE", 1), rank = envInt("RANK", 0);
+  if (envInt("RTIGO3_PROCESS_GROUP", 0) != 1 || world < 2) return false;
+  std::string file = "/tmp/rtigo3_nccl_id_" + std::to_string(envInt("MASTER_PORT", 0));
+  if (const char* f = std::getenv("RTIGO3_NCCL_ID_FILE")) file = f;
+  char id[128];
+  if (rank == 0)
+  {
+    makeProcessGroupId(id);
+    const std::string tmp = file + ".tmp";
+    FILE* fp = std::fopen(tmp.c_str(), "wb");
+    if (!fp || std::fwrite(id, 1, sizeof(id), fp) != sizeof(id)) { m_lastError = "cannot write " + tmp; if (fp) std::fclose(fp); return false; }
+    std::fclose(fp);
+    if (std::rename(tmp.c_str(), file.c_str()) != 0) { m_lastError = "cannot rename " + tmp; return false; }
+  }
+  else
+  {
+    // the rename makes the file appear complete; wait for it for up to two minutes
+    bool got = false;
+    for (int attempt = 0; attempt < 2400 && !got; ++attempt)
+    {
+      if (FILE* fp = std::fopen(file.c_str(), "rb"))
+      {
+        got = std::fread(id, 1, sizeof(id), fp) == sizeof(id);
+        std::fclose(fp);
+      }
+      if (!got) { struct timespec ts = { 0, 50 * 1000 * 1000 }; nanosleep(&ts, nullptr); }
+    }
+    if (!got) { m_lastError = "timed out waiting for " + file; std::cerr << "ERROR: " << m_lastError << std::endl; return false; }
+  }
+  const bool ok = joinProcessGroup(rank, world, id);
+  if (rank == 0 && ok) std::remove(file.c_str());   // every rank has read it once ncclCommInitRank returned
+  return ok;
+}
 
 void Application::setCompositeMode(int mode)
 {
@@ -244,7 +304,7 @@ void Application::benchmark()
 {
   try
   {
-    const unsigned int spp = (unsigned int)(m_samplesSqrt * m_samplesSqrt);
+    const unsigned int spp = m_raytracer->getSamplesPerPixelLocal();   // samplesSqrt^2, or this rank's share of it
     const auto t0 = std::chrono::steady_clock::now();
     unsigned int iterationIndex = 0;
     while (iterationIndex < spp) iterationIndex = m_raytracer->render((unsigned int)std::max(1, m_batch));
@@ -297,19 +357,21 @@ bool Application::screenshot(const bool tonemap, std::string* writtenPath)
     path << m_prefixScreenshot << "_" << m_raytracer->m_iterationIndex << "spp_" << std::put_time(&tmv, "%Y%m%d_%H%M%S");
     bool ok = false;
     std::string file;
+    const bool writer = m_raytracer->getRank() == 0;    // in a process group fetching the frame is a collective; rank 0 owns the result
     if (tonemap)
     {
       std::vector<unsigned char> rgb;
       tonemapDevice(rgb);
       file = path.str() + ".png";
-      ok = writePNG(file, m_resolution.x, m_resolution.y, rgb.data(), true);   // frame rows are bottom-up
+      ok = !writer || writePNG(file, m_resolution.x, m_resolution.y, rgb.data(), true);   // frame rows are bottom-up
     }
     else
     {
       const float* host = getOutputBufferHost();
       file = path.str() + ".hdr";
-      ok = host && writeHDR(file, m_resolution.x, m_resolution.y, host, true);
+      ok = host && (!writer || writeHDR(file, m_resolution.x, m_resolution.y, host, true));
     }
+    if (!writer) { if (writtenPath) writtenPath->clear(); return ok; }
     if (ok) std::cout << file << std::endl;
     if (writtenPath) *writtenPath = ok ? file : std::string();
     return ok;

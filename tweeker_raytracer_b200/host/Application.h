@@ -62,6 +62,15 @@ public:
   double getLastBenchmarkSeconds() const { return m_benchmarkSeconds; }
   std::string getLastError() const { return m_lastError; }
   void setCompositeMode(int mode);
+  // One process per GPU (B200 addition, see Raytracer::joinProcessGroup): this Application becomes rank `rank` of `world`
+  // processes rendering disjoint iteration ranges; getOutputBufferHost()/screenshot() are then collectives and rank 0
+  // owns the combined frame.  makeProcessGroupId() is called on rank 0; the 128 bytes travel out of band.
+  static void makeProcessGroupId(char id[128]);
+  bool joinProcessGroup(int rank, int world, const char id[128]);
+  // The same, driven by a torchrun-style environment (RANK, WORLD_SIZE, LOCAL_RANK) when RTIGO3_PROCESS_GROUP=1: the id
+  // is exchanged through the file RTIGO3_NCCL_ID_FILE (default /tmp/rtigo3_nccl_id_<MASTER_PORT>).  Returns false when
+  // the environment does not ask for a process group.
+  bool joinProcessGroupFromEnvironment();
 
 private:
   bool loadSystemDescription(std::string const& filename);

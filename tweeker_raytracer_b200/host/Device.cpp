@@ -306,8 +306,9 @@ void Device::renderIterations(const unsigned int iterationFirst, const unsigned 
 // so the per-iteration "synchronize, then upload iterationIndex" of DeviceSingleGPU.cpp:145-158 has no equivalent.
 void Device::launch(const unsigned int launchWidth, const int raygen, const unsigned int iterationFirst, const unsigned int count)
 {
-  m_systemData.iterationIndex = (int)iterationFirst;
-  RTC_CHECK(rtc_launch(m_context, &m_systemData, launchWidth, (uint32_t)m_systemData.resolution.y, raygen, m_miss, (int)iterationFirst, (int)count));
+  m_systemData.iterationIndex = (int)(m_seedOffset + iterationFirst);
+  RTC_CHECK(rtc_launch_ex(m_context, &m_systemData, launchWidth, (uint32_t)m_systemData.resolution.y, raygen, m_miss,
+                          (int)(m_seedOffset + iterationFirst), (int)count, (int)iterationFirst, 0));
   m_isDirtySystemData = false;
 }
 

@@ -62,6 +62,10 @@ public:
   std::vector<MaterialDefinition> const& getMaterials() const { return m_materials; }
   uint64_t getTopObject() const { return m_systemData.topObject; }
   void getStats(rtc_stats& stats) const;
+  // B200 extension (sample-range partition, one process per GPU): iteration i of this device draws its seeds from
+  // iteration index offset + i, while it is still blended into this device's running average as sample i.
+  void setSeedOffset(const unsigned int offset) { m_seedOffset = offset; }
+  uint64_t getOutputBufferDevice() const { return m_systemData.outputBuffer; }
 
 protected:
   void traverseNode(std::shared_ptr<sg::Node> node, float matrix[12], InstanceData data);
@@ -86,6 +90,7 @@ protected:
   bool m_isDirtyOutputBuffer = true;
   bool m_ownsSharedBuffer = false;
   int  m_launchWidth = 0;
+  unsigned int m_seedOffset = 0;
 
   std::vector<GeometryData>      m_geometryData;   // indexed by sg::Triangles id
   std::vector<rtc_instance_desc> m_instances;

@@ -1,5 +1,6 @@
 #include "NcclComposite.h"
 
+#include <cstring>
 #include <stdexcept>
 #include <vector>
 
@@ -44,4 +45,32 @@ void ncclGroupReduceSum(NcclGroup* group, const uint64_t* src, uint64_t dstRoot,
                      (cudaStream_t)(uintptr_t)streams[i]), "ncclReduce");
   }
   check(ncclGroupEnd(), "ncclGroupEnd");
+}
+
+void ncclProcessUniqueId(char out[128])
+{
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  check(ncclGetUniqueId(&id), "ncclGetUniqueId");
+  std::memcpy(out, &id, sizeof(id));
+}
+
+NcclGroup* ncclProcessGroupJoin(int rank, int world, const char idBytes[128], int ordinal)
+{
+  NcclGroup* g = new NcclGroup();
+  g->ordinals.assign(1, ordinal);
+  g->comms.resize(1);
+  ncclUniqueId id;
+  std::memcpy(&id, idBytes, sizeof(id));
+  cudaSetDevice(ordinal);
+  try { check(ncclCommInitRank(&g->comms[0], world, id, rank), "ncclCommInitRank"); }
+  catch (...) { delete g; throw; }
+  return g;
+}
+
+void ncclProcessGroupReduceMean(NcclGroup* group, uint64_t src, uint64_t dst, size_t count, uint64_t stream)
+{
+  cudaSetDevice(group->ordinals[0]);
+  check(ncclReduce((const void*)(uintptr_t)src, (void*)(uintptr_t)dst, count, ncclFloat, ncclAvg, 0, group->comms[0],
+                   (cudaStream_t)(uintptr_t)stream), "ncclReduce(avg)");
 }

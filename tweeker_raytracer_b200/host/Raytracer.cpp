@@ -15,7 +15,65 @@ Raytracer::Raytracer(RendererStrategy strategy, const int interop, const unsigne
 
 Raytracer::~Raytracer()
 {
+  if (m_processGroup && !m_activeDevices.empty())
+  {
+    rtc_context* ctx = m_activeDevices[0]->getContext();
+    RTC_CHECK_NO_THROW(rtc_synchronize(ctx));
+    if (m_combined) RTC_CHECK_NO_THROW(rtc_free(ctx, m_combined));
+    if (m_combinedHost) RTC_CHECK_NO_THROW(rtc_host_free(ctx, m_combinedHost));
+  }
+  ncclGroupDestroy(m_processGroup);
   for (Device* device : m_activeDevices) delete device;
+}
+
+void Raytracer::joinProcessGroup(const int rank, const int world, const char id[128])
+{
+  if (world < 1 || rank < 0 || world <= rank) throw std::runtime_error("ERROR: joinProcessGroup() rank/world out of range");
+  if (m_activeDevices.size() != 1) throw std::runtime_error("ERROR: joinProcessGroup() needs exactly one active device per process (strategy 0)");
+  if (m_processGroup) throw std::runtime_error("ERROR: joinProcessGroup() called twice");
+  m_processGroup = ncclProcessGroupJoin(rank, world, id, m_activeDevices[0]->m_ordinal);
+  m_rank = rank;
+  m_world = world;
+  m_iterationIndex = 0;
+  applySeedOffsets();
+}
+
+void Raytracer::reduceMeanToRoot(const uint64_t src, const uint64_t dst, const size_t count)
+{
+  if (!m_processGroup) throw std::runtime_error("ERROR: reduceMeanToRoot() without joinProcessGroup()");
+  ncclProcessGroupReduceMean(m_processGroup, src, dst, count, rtc_context_stream(m_activeDevices[0]->getContext()));
+}
+
+void Raytracer::applySeedOffsets()
+{
+  const unsigned int offset = (unsigned int)m_rank * getSamplesPerPixelLocal();
+  for (Device* d : m_activeDevices) d->setSeedOffset(1 < m_world ? offset : 0u);
+}
+
+// Collective: mean of the ranks' running averages -> rank 0 (ncclReduce with ncclAvg on the render stream, so it is
+// ordered behind the launches without a host synchronisation), then rank 0 reads the mean frame back.  The other ranks
+// return their own local frame.
+const void* Raytracer::combineProcessGroup()
+{
+  Device* device = m_activeDevices[0];
+  rtc_context* ctx = device->getContext();
+  SystemData const& sys = device->getSystemData();
+  const size_t pixels = (size_t)sys.resolution.x * (size_t)sys.resolution.y;
+  if (device->getOutputBufferDevice() == 0) throw std::runtime_error("ERROR: getOutputBufferHost() before the first render()");
+  if (m_rank == 0 && m_combinedPixels != pixels)
+  {
+    RTC_CHECK(rtc_synchronize(ctx));
+    if (m_combined) RTC_CHECK(rtc_free(ctx, m_combined));
+    if (m_combinedHost) RTC_CHECK(rtc_host_free(ctx, m_combinedHost));
+    RTC_CHECK(rtc_malloc(ctx, sizeof(float4) * pixels, &m_combined));
+    RTC_CHECK(rtc_host_alloc(ctx, sizeof(float4) * pixels, &m_combinedHost));
+    m_combinedPixels = pixels;
+  }
+  reduceMeanToRoot(device->getOutputBufferDevice(), m_combined, pixels * 4);
+  if (m_rank != 0) return device->getOutputBufferHost();
+  RTC_CHECK(rtc_download(ctx, m_combinedHost, m_combined, sizeof(float4) * pixels));
+  RTC_CHECK(rtc_synchronize(ctx));
+  return m_combinedHost;
 }
 
 template <class DeviceType>
@@ -106,6 +164,7 @@ void Raytracer::initState(DeviceState const& state)
 {
   m_samplesPerPixel = (unsigned int)(state.samplesSqrt * state.samplesSqrt);
   for (Device* d : m_activeDevices) d->setState(state);
+  applySeedOffsets();
 }
 
 // Every update restarts the accumulation (Raytracer.cpp:331-367).
@@ -116,6 +175,7 @@ void Raytracer::updateState(DeviceState const& state)
 {
   m_samplesPerPixel = (unsigned int)(state.samplesSqrt * state.samplesSqrt);
   for (Device* d : m_activeDevices) d->setState(state);
+  applySeedOffsets();
   m_iterationIndex = 0;
 }
 
@@ -124,9 +184,10 @@ unsigned int Raytracer::render(const unsigned int count) { return renderAll(coun
 // All devices work on the same iteration indices; the first device called allocates shared buffers.
 unsigned int Raytracer::renderAll(const unsigned int count)
 {
-  if (m_iterationIndex < m_samplesPerPixel)
+  const unsigned int budget = getSamplesPerPixelLocal();    // == m_samplesPerPixel unless this process is one rank of several
+  if (m_iterationIndex < budget)
   {
-    unsigned int n = m_samplesPerPixel - m_iterationIndex;
+    unsigned int n = budget - m_iterationIndex;
     if (count < n) n = count;
     void* buffer = nullptr;
     for (Device* device : m_activeDevices) device->renderIterations(m_iterationIndex, n, &buffer);

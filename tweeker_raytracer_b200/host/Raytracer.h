@@ -7,6 +7,10 @@
 //   RaytracerMultiGPULocalCopy    RaytracerMultiGPULocalCopy.cpp:38-173
 // B200 additions: render(count) enqueues several iterations at once, and the local-copy strategy can combine
 // the per-GPU results with one NCCL reduce over NVLink instead of N serial peer copies (setCompositeMode).
+// One process per GPU (torchrun-style): joinProcessGroup(rank, world, id) turns a single-GPU Raytracer into rank `rank`
+// of a sample-range partition -- it renders the iterations [rank * spp/world, (rank+1) * spp/world) as its own
+// running average, and getOutputBufferHost() becomes a collective that lands the mean of the ranks' frames on rank 0
+// with one ncclReduce over NVLink.
 #pragma once
 #include <map>
 #include <memory>
@@ -44,6 +48,22 @@ public:
 
   void getStats(rtc_stats& total);                   // summed over the active devices
 
+  // Sample-range partition across processes.  `id` = the 128 bytes of ncclProcessUniqueId() made on rank 0.
+  // Collective; needs exactly one active device.  world == 1 is allowed (the reduce is then the identity).
+  void joinProcessGroup(const int rank, const int world, const char id[128]);
+  // mean over the ranks of `count` floats at device address src -> dst on rank 0 (0 elsewhere), enqueued on the render
+  // stream behind the launches (no host synchronisation).  Collective.  The building block of getOutputBufferHost().
+  void reduceMeanToRoot(const uint64_t src, const uint64_t dst, const size_t count);
+  int getRank() const { return m_rank; }
+  int getWorld() const { return m_world; }
+  // iterations this process renders: samplesPerPixel / world (at least 1)
+  unsigned int getSamplesPerPixelLocal() const { return samplesPerRank(m_samplesPerPixel, m_world); }
+  static unsigned int samplesPerRank(const unsigned int samplesPerPixel, const int world)
+  {
+    const unsigned int n = samplesPerPixel / (unsigned int)(world > 0 ? world : 1);
+    return n ? n : 1u;
+  }
+
 public:
   RendererStrategy m_strategy;
   int              m_interop;
@@ -62,6 +82,15 @@ public:
 protected:
   template <class DeviceType> void createDevices(const int devicesMask, const int miss, const bool onlyFirst);
   unsigned int renderAll(const unsigned int count);
+  const void* combineProcessGroup();     // the collective behind getOutputBufferHost() when m_world > 1
+  void applySeedOffsets();
+
+  int m_rank = 0;
+  int m_world = 1;
+  struct NcclGroup* m_processGroup = nullptr;
+  uint64_t m_combined = 0;               // rank 0: device buffer receiving the mean frame
+  size_t   m_combinedPixels = 0;
+  void*    m_combinedHost = nullptr;     // rank 0: pinned staging of the mean frame
 };
 
 class RaytracerSingleGPU : public Raytracer
@@ -70,7 +99,7 @@ public:
   RaytracerSingleGPU(const int devicesMask, const int miss, const int interop, const unsigned int tex, const unsigned int pbo);
   unsigned int render() override { return renderAll(1); }
   void updateDisplayTexture() override { m_activeDevices[0]->updateDisplayTexture(); }
-  const void* getOutputBufferHost() override { return m_activeDevices[0]->getOutputBufferHost(); }
+  const void* getOutputBufferHost() override { return (m_processGroup != nullptr) ? combineProcessGroup() : m_activeDevices[0]->getOutputBufferHost(); }
 };
 
 class RaytracerMultiGPUZeroCopy : public Raytracer

@@ -152,6 +152,29 @@ rtc_context* rth_app_context(void* h, int deviceIndex)
   if (!rt || deviceIndex < 0 || (size_t)deviceIndex >= rt->m_activeDevices.size()) return nullptr;
   return rt->m_activeDevices[deviceIndex]->getContext();
 }
+// --- one process per GPU: sample-range partition + NCCL mean of the frames (Raytracer::joinProcessGroup) ---
+int rth_process_group_id(char id[128])
+{
+  try { Application::makeProcessGroupId(id); return 0; } catch (std::exception const& e) { g_error = e.what(); return -1; }
+}
+int rth_app_join_group(void* h, int rank, int world, const char id[128])
+{
+  Application* app = static_cast<Application*>(h);
+  if (!app->getRaytracer()) { g_error = "host-only Application has no Raytracer"; return -2; }
+  if (!app->joinProcessGroup(rank, world, id)) { g_error = app->getLastError(); return -1; }
+  return 0;
+}
+int rth_app_group_reduce_mean(void* h, uint64_t src, uint64_t dst, uint64_t count)
+{
+  try { static_cast<Application*>(h)->getRaytracer()->reduceMeanToRoot(src, dst, (size_t)count); return 0; }
+  catch (std::exception const& e) { g_error = e.what(); return -1; }
+}
+// pure index arithmetic (no device): the iteration range rank `rank` of `world` renders out of samplesPerPixel
+void rth_sample_range(unsigned int samplesPerPixel, int rank, int world, unsigned int* first, unsigned int* count)
+{
+  *count = Raytracer::samplesPerRank(samplesPerPixel, world);
+  *first = (1 < world) ? (unsigned int)rank * *count : 0u;
+}
 int rth_app_stats(void* h, rtc_stats* out)
 {
   try { static_cast<Application*>(h)->getRaytracer()->getStats(*out); return 0; } catch (std::exception const& e) { g_error = e.what(); return -1; }

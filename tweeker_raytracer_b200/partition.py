@@ -5,9 +5,11 @@ Two partitions of the same job:
   * tile partition  -- the reference's strategies 1-3: a checkerboard of tileSize tiles, row yBlock rotated by the device
     index (apps/rtigo3/shaders/raygeneration.cu:152-164); each device launches `launch_width` columns
     (apps/rtigo3/src/DeviceMultiGPULocalCopy.cpp:91-93).  Seeds depend on the device layout.
-  * sample-range partition -- device r of n renders iteration indices (step*n + r)*spp .. +spp over the whole frame and
-    keeps its OWN running average (accumulation index counts from 0); the frame is the mean of the n averages, obtained
-    with one NCCL reduce(sum) and a scale by 1/n.  Seeds are the single-GPU ones.
+  * sample-range partition -- the samplesPerPixel iterations of the render are cut into n contiguous ranges; device r
+    renders iteration indices [r*spp/n, (r+1)*spp/n) over the whole frame and keeps its OWN running average (accumulation
+    index counts from 0); the frame is the mean of the n averages, obtained with one NCCL reduce over NVLink.  Seeds are
+    the single-GPU ones: the n ranks together draw exactly the samples of the 1-GPU render.  Mirrors
+    Raytracer::samplesPerRank / joinProcessGroup (host/Raytracer.h); host.sample_range is the C++ side of it.
 """
 
 
@@ -32,9 +34,18 @@ def distribute(x, y, device_index, device_count, tile_size_x, tile_shift_x, tile
     return x_tile * tile_size_x + (x & (tile_size_x - 1))
 
 
-def sample_range(step, rank, world, spp_per_step):
-    """(first seed iteration, count, first accumulation index) of `rank` in `step`."""
-    return (step * world + rank) * spp_per_step, spp_per_step, step * spp_per_step
+def samples_per_rank(samples_per_pixel, world):
+    """Iterations each rank renders out of a budget of samples_per_pixel (at least 1)."""
+    return max(samples_per_pixel // max(world, 1), 1)
+
+
+def sample_range(step, rank, world, spp_per_step, samples_per_pixel):
+    """(first seed iteration, count, first accumulation index) of `rank` in `step` (a step = spp_per_step iterations)."""
+    local = samples_per_rank(samples_per_pixel, world)
+    offset = rank * local if world > 1 else 0
+    first = step * spp_per_step
+    count = max(0, min(spp_per_step, local - first))
+    return offset + first, count, first
 
 
 def combine_scale(world):
