@@ -23,6 +23,9 @@
  *   DeviceMultiGPULocalCopy.cpp:279-337 compositor kernel launch      rtc_composite
  *   Application.cpp:2262-2295 CPU tonemapper ("PERF Add a native CUDA rtc_tonemap
  *                       kernel doing this", :2275)
+ *   Device.cpp:1503-1513, :1141-1160 hit-record (SBT header) choice   rtc_scene_set_instance_flags
+ *                       per instance: plain or cutout programs
+ *   Texture.cpp:640-760 Texture::create (2D image -> CUtexObject)     rtc_texture_create / rtc_texture_destroy
  *   Device.cpp synchronizeStream (cuStreamSynchronize)                rtc_synchronize
  *   cuMemAlloc / cuMemFree / cuMemcpyHtoDAsync / cuMemcpyDtoHAsync    rtc_malloc / rtc_free / rtc_upload / rtc_download
  *
@@ -126,6 +129,28 @@ int rtc_scene_info_get(rtc_context* ctx, uint64_t topObject, rtc_scene_info* inf
 /* Frees one scene (the instance level and its tables; GAS stay alive until rtc_gas_destroy / context destroy). */
 int rtc_scene_destroy(rtc_context* ctx, uint64_t topObject);
 int rtc_gas_destroy(rtc_context* ctx, uint32_t gas);
+/*
+ * Which hit records an instance uses.  The reference writes the cutout program group (__anyhit__radiance_cutout,
+ * __anyhit__shadow_cutout; shaders/anyhit.cu:46-80, :94-132) into the two SBT records of every instance whose material
+ * has a cutout texture (src/Device.cpp:1503-1513) and rewrites those headers when the GUI toggles it (:1141-1160).
+ * flags[i] applies to instance first + i.  Stream-ordered on the context stream; every instance starts at 0.
+ * While at least one instance carries RTC_INSTANCE_CUTOUT, launches process the candidate intersections of a ray in the
+ * canonical order (t, instance, primitive) -- closest candidate first, an ignored candidate is followed by the next one --
+ * which is the order this library DEFINES for the reference's order-dependent stochastic alpha test.
+ */
+#define RTC_INSTANCE_CUTOUT 1u
+int rtc_scene_set_instance_flags(rtc_context* ctx, uint64_t topObject, uint32_t first, uint32_t count, const uint32_t* flags);
+/* Tells the core that MaterialDefinition.textureAlbedo may be non-zero for this scene (closesthit.cu:233-240); selects
+ * the shading kernels that interpolate texture coordinates.  Off by default, like the reference's GUI toggle. */
+int rtc_scene_set_albedo_textures(rtc_context* ctx, uint64_t topObject, int enable);
+/*
+ * Material textures.  Replaces Texture::create for 2D images (src/Texture.cpp:640-760, cuTexObjectCreate with wrap/wrap
+ * addressing, linear filter, normalised coordinates): rgba = width*height RGBA32F texels, row 0 first.  The returned
+ * handle goes into MaterialDefinition.textureAlbedo / textureCutout (0 = no texture).  The fetch is a software bilinear
+ * filter (wrap in u and v, texel centres at (i+0.5)/size) so that it is reproducible on a CPU.
+ */
+int rtc_texture_create(rtc_context* ctx, uint32_t width, uint32_t height, const float* rgba, uint64_t* handle);
+int rtc_texture_destroy(rtc_context* ctx, uint64_t handle);
 /* Copies out the 3x4 world->object matrix of one instance. */
 int rtc_instance_inverse(rtc_context* ctx, uint64_t topObject, uint32_t instance, float out[12]);
 

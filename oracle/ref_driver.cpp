@@ -25,6 +25,8 @@ extern "C" void __raygen__path_tracer();
 extern "C" void __raygen__path_tracer_local_copy();
 extern "C" void __closesthit__radiance();
 extern "C" void __anyhit__shadow();
+extern "C" void __anyhit__radiance_cutout();
+extern "C" void __anyhit__shadow_cutout();
 extern "C" void __miss__env_null();
 extern "C" void __miss__env_constant();
 extern "C" void __miss__env_sphere();
@@ -63,6 +65,8 @@ struct Runtime
   unsigned int hitInstance = 0, hitPrimitive = 0;
   float2 barycentrics;
   float rayTmax = 0.0f;
+  bool ignored = false;       // set by optixIgnoreIntersection inside an any-hit program
+  bool hasCutout = false;     // some material carries a cutout texture (decided per ref_render_rows call)
 };
 
 Runtime g;
@@ -81,14 +85,22 @@ OptixTraversableHandle optixGetTransformListHandle(unsigned int) { return (Optix
 const float4* optixGetInstanceTransformFromHandle(OptixTraversableHandle h) { return &g.objectToWorld[3 * (size_t)h]; }
 const float4* optixGetInstanceInverseTransformFromHandle(OptixTraversableHandle h) { return &g.worldToObject[3 * (size_t)h]; }
 void optixTerminateRay() {}
-void optixIgnoreIntersection() {}
+void optixIgnoreIntersection() { g.ignored = true; }
 unsigned int optixGetExceptionCode() { return 0; }
 void* ref_callable(unsigned int sbtIndex) { return sbtIndex < 15 ? g.callables[sbtIndex] : nullptr; }
 
 // The software texture fetch this repository DEFINES for the environment map (bilinear, wrap u, clamp v), identical to
 // env_lookup in oracle/rt_oracle.c and csrc/shade.cuh; the reference used the texture unit (miss.cu:90, light_sample.cu:147).
+// Material textures (closesthit.cu:235, anyhit.cu:70, :119): the handle is the address of {uint32 w, h, 0, 0} + RGBA32F
+// texels and the fetch is the one oracle/rt_oracle.c DEFINES (bilinear, wrap/wrap).
 template <> float4 tex2D<float4>(cudaTextureObject_t texture, float u, float v)
 {
+  if ((uintptr_t)texture != (uintptr_t)&g.env)
+  {
+    float rgb[3];
+    orc_tex2d((uint64_t)texture, u, v, rgb);
+    return make_float4(rgb[0], rgb[1], rgb[2], 1.0f);
+  }
   const EnvTexture* t = reinterpret_cast<const EnvTexture*>((uintptr_t)texture);
   const int W = (int)t->width, H = (int)t->height;
   const float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
@@ -113,15 +125,54 @@ template <> float4 tex2D<float4>(cudaTextureObject_t texture, float u, float v)
   return make_float4(c[0], c[1], c[2], c[3]);
 }
 
+// Next candidate intersection after `skip` in the canonical order (t, instance, primitive); false when there is none.
+static bool next_candidate(const orc_ray& ray, const orc_hit* skip, orc_hit& hit)
+{
+  if (skip) orc_trace_closest_after(g.scene, &ray, skip->t, skip->inst, skip->prim, &hit);
+  else      orc_trace_closest(g.scene, &ray, 1, 0, &hit, nullptr);
+  if (hit.inst == 0xffffffffu) return false;
+  g.hitInstance = hit.inst; g.hitPrimitive = hit.prim; g.barycentrics = make_float2(hit.u, hit.v); g.rayTmax = hit.t;
+  return true;
+}
+
+// The instance's hit records are the cutout ones when its material has a cutout texture (src/Device.cpp:1503-1513).
+static bool cutout_records(unsigned int instance)
+{
+  return sysData.materialDefinitions[g.sbt[instance].materialIndex].textureCutout != 0;
+}
+
 // optixTrace: closest hit -> __closesthit__radiance or the miss program; DISABLE_CLOSESTHIT (shadow rays) -> any hit
 // runs __anyhit__shadow once, a miss does nothing (the shadow miss program is null, src/Device.cpp:674-678).
+// With cutout materials in the scene the reference's any-hit programs run per candidate, in the canonical order this
+// repository defines (closest candidate first; see "Cutout opacity" in rt_oracle.c).
 void ref_trace(OptixTraversableHandle, float3 origin, float3 direction, float tmin, float tmax, float,
                unsigned int, unsigned int rayFlags, unsigned int, unsigned int, unsigned int, unsigned int& p0, unsigned int& p1)
 {
   orc_ray ray = { origin.x, origin.y, origin.z, tmin, direction.x, direction.y, direction.z, tmax };
   const unsigned int save0 = g.payload0, save1 = g.payload1;
   g.payload0 = p0; g.payload1 = p1;
-  if (rayFlags & OPTIX_RAY_FLAG_DISABLE_CLOSESTHIT)
+  if (g.hasCutout)
+  {
+    orc_hit hit, skip; const orc_hit* after = nullptr;
+    const bool shadowRay = (rayFlags & OPTIX_RAY_FLAG_DISABLE_CLOSESTHIT) != 0;
+    bool accepted = false;
+    while (next_candidate(ray, after, hit))
+    {
+      g.ignored = false;
+      if (shadowRay) { if (cutout_records(hit.inst)) __anyhit__shadow_cutout(); else __anyhit__shadow(); }
+      else if (cutout_records(hit.inst)) __anyhit__radiance_cutout();
+      if (!g.ignored) { accepted = true; break; }
+      skip = hit; after = &skip;
+    }
+    if (!shadowRay)
+    {
+      if (accepted) __closesthit__radiance();          // g.hit* still describe the accepted candidate
+      else if (g.miss == 2) __miss__env_sphere();
+      else if (g.miss == 1) __miss__env_constant();
+      else                  __miss__env_null();
+    }
+  }
+  else if (rayFlags & OPTIX_RAY_FLAG_DISABLE_CLOSESTHIT)
   {
     uint8_t occluded = 0;
     orc_trace_any(g.scene, &ray, 1, 0, &occluded, nullptr);
@@ -225,6 +276,8 @@ void ref_render_rows(const rt_SystemData* values, unsigned int launchWidth, unsi
   sysData.outputBuffer = (CUdeviceptr)(uintptr_t)buffer;
   sysData.texelBuffer = (CUdeviceptr)(uintptr_t)buffer;
   g.launchDim = make_uint3(launchWidth, launchHeight, 1u);
+  g.hasCutout = false;
+  for (int m = 0; m < sysData.numMaterials; ++m) if (sysData.materialDefinitions[m].textureCutout != 0) g.hasCutout = true;
   for (int it = iterFirst; it < iterFirst + iterCount; ++it)
   {
     sysData.iterationIndex = it;

@@ -136,6 +136,7 @@ struct orc_scene {
   float*   envCdfU;   float* envCdfV; float envIntegral;
   bvh      top;
   int      committed;
+  int      hasCutout;   /* some material carries a cutout texture: traces take the ordered any-hit path */
 };
 
 orc_scene* orc_scene_create(void) { return (orc_scene*)calloc(1, sizeof(orc_scene)); }
@@ -196,6 +197,8 @@ void orc_scene_set_materials(orc_scene* s, const rt_MaterialDefinition* m, int n
   s->materials = (rt_MaterialDefinition*)malloc(sizeof(*m) * (size_t)(n > 0 ? n : 1));
   memcpy(s->materials, m, sizeof(*m) * (size_t)n);
   s->numMaterials = n;
+  s->hasCutout = 0;
+  for (int i = 0; i < n; ++i) if (m[i].textureCutout != 0) s->hasCutout = 1;
 }
 
 void orc_scene_set_lights(orc_scene* s, const rt_LightDefinition* l, int n)
@@ -494,11 +497,18 @@ static inline int box_test(const oray* r, const aabb* b, float tmin, float tmax)
   return tn <= tf;
 }
 
-typedef struct { float t, u, v; uint32_t inst, prim; } besthit;
+/* skip != NULL: only candidates that come AFTER the skip key in the canonical order (t, instance, primitive) count */
+typedef struct { float t; uint32_t inst, prim; } hitkey;
+typedef struct { float t, u, v; uint32_t inst, prim; const hitkey* skip; } besthit;
 
 static inline void consider(besthit* best, float t, float u, float v, uint32_t inst, uint32_t prim, float tmin, float tmax)
 {
   if (!(t > tmin && t < tmax)) return;
+  if (best->skip)
+  {
+    const hitkey* k = best->skip;
+    if (!(t > k->t || (t == k->t && (inst > k->inst || (inst == k->inst && prim > k->prim))))) return;
+  }
   if (best->inst != 0xffffffffu)
   {
     if (t > best->t) return;
@@ -584,10 +594,10 @@ static int trace_instance(const orc_scene* s, uint32_t ii, const float o[3], con
   return 0;
 }
 
-static int trace_scene(const orc_scene* s, const float o[3], const float d[3], float tmin, float tmax,
-                       int mode, int anyHit, besthit* best, orc_stats* st)
+static int trace_scene_after(const orc_scene* s, const float o[3], const float d[3], float tmin, float tmax,
+                             int mode, int anyHit, besthit* best, orc_stats* st, const hitkey* skip)
 {
-  best->inst = 0xffffffffu; best->prim = 0xffffffffu; best->t = -1.0f; best->u = 0.0f; best->v = 0.0f;
+  best->inst = 0xffffffffu; best->prim = 0xffffffffu; best->t = -1.0f; best->u = 0.0f; best->v = 0.0f; best->skip = skip;
   if (!(tmax > tmin)) return 0;
   if (mode == 1 || s->top.numNodes == 0)
   {
@@ -614,6 +624,23 @@ static int trace_scene(const orc_scene* s, const float o[3], const float d[3], f
     }
   }
   return (!anyHit && best->inst != 0xffffffffu);
+}
+
+static int trace_scene(const orc_scene* s, const float o[3], const float d[3], float tmin, float tmax,
+                       int mode, int anyHit, besthit* best, orc_stats* st)
+{
+  return trace_scene_after(s, o, d, tmin, tmax, mode, anyHit, best, st, NULL);
+}
+
+/* Closest hit that comes after (skipT, skipInst, skipPrim) in the canonical candidate order; the building block of the
+ * ordered any-hit processing below (exported for the reference driver, which runs the reference's own any-hit programs). */
+void orc_trace_closest_after(const orc_scene* s, const orc_ray* ray, float skipT, uint32_t skipInst, uint32_t skipPrim, orc_hit* hit)
+{
+  const float o[3] = { ray->ox, ray->oy, ray->oz }, d[3] = { ray->dx, ray->dy, ray->dz };
+  const hitkey k = { skipT, skipInst, skipPrim };
+  besthit b;
+  trace_scene_after(s, o, d, ray->tmin, ray->tmax, 0, 0, &b, NULL, &k);
+  hit->t = b.t; hit->u = b.u; hit->v = b.v; hit->inst = b.inst; hit->prim = b.prim;
 }
 
 void orc_trace_closest(const orc_scene* s, const orc_ray* rays, uint64_t n, int mode, orc_hit* hits, orc_stats* stats)
@@ -666,6 +693,45 @@ static v3 env_lookup(const orc_scene* s, float u, float v)
     c[k] = a + ay * (b - a);
   }
   return V3(c[0], c[1], c[2]);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Material textures (MaterialDefinition.textureAlbedo / textureCutout; tex2D at closesthit.cu:235, anyhit.cu:70, :119).
+ * The reference samples CUDA texture objects created with wrap/wrap addressing, linear filtering and normalised
+ * coordinates (src/Texture.cpp:670-675).  DEFINED here like the environment lookup: a handle is the address of a
+ * 16-byte header {uint32 width, height, 0, 0} followed by width*height RGBA32F texels; software bilinear filter,
+ * wrap in u AND v, texel centres at (i+0.5)/W.
+ * ------------------------------------------------------------------------------------------ */
+static v3 tex2d_wrap(uint64_t handle, float u, float v)
+{
+  const uint32_t* header = (const uint32_t*)(uintptr_t)handle;
+  const float* texels = (const float*)(header + 4);
+  const int W = (int)header[0], H = (int)header[1];
+  const float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
+  const float fx = floorf(x), fy = floorf(y);
+  const float ax = x - fx, ay = y - fy;
+  int x0 = (int)fx % W; if (x0 < 0) x0 += W;
+  int x1 = x0 + 1; if (x1 >= W) x1 = 0;
+  int y0 = (int)fy % H; if (y0 < 0) y0 += H;
+  int y1 = y0 + 1; if (y1 >= H) y1 = 0;
+  const float* t00 = &texels[4 * ((size_t)y0 * W + x0)];
+  const float* t10 = &texels[4 * ((size_t)y0 * W + x1)];
+  const float* t01 = &texels[4 * ((size_t)y1 * W + x0)];
+  const float* t11 = &texels[4 * ((size_t)y1 * W + x1)];
+  float c[3];
+  for (int k = 0; k < 3; ++k)
+  {
+    const float a = t00[k] + ax * (t10[k] - t00[k]);
+    const float b = t01[k] + ax * (t11[k] - t01[k]);
+    c[k] = a + ay * (b - a);
+  }
+  return V3(c[0], c[1], c[2]);
+}
+
+void orc_tex2d(uint64_t handle, float u, float v, float out[3])
+{
+  const v3 c = tex2d_wrap(handle, u, v);
+  out[0] = c.x; out[1] = c.y; out[2] = c.z;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -1089,6 +1155,63 @@ typedef struct {
   const orc_scene* s; const rt_SystemData* sys; int miss; int mode; orc_stats* st;
 } shade_ctx;
 
+/* ------------------------------------------------------------------------------------------
+ * Cutout opacity: __anyhit__radiance_cutout / __anyhit__shadow_cutout (anyhit.cu:46-80, :94-132).
+ *
+ * OptiX runs an any-hit program for candidate intersections in an unspecified order and each invocation may draw one
+ * random number from the path's seed, so the reference's result depends on the driver's traversal order.  DEFINED
+ * here: candidates are processed in the canonical order (t, instance, primitive) ascending, i.e. the closest candidate
+ * first; an ignored candidate is followed by the next one in that order.  The instance's hit records are the cutout
+ * ones exactly when its material has a cutout texture (src/Device.cpp:1503-1513, :1141-1160).
+ * ------------------------------------------------------------------------------------------ */
+static float cutout_opacity(const orc_scene* s, const rt_MaterialDefinition* material, const besthit* hit)
+{
+  const instance* in = &s->insts[hit->inst];
+  const geometry* g = &s->geoms[in->geometry];
+  const uint32_t* tri = &g->indices[3u * hit->prim];
+  const float bx = hit->u, by = hit->v;
+  const float alpha = 1.0f - bx - by;
+  const v3 texcoord = vadd(vadd(vscale(from_f3(g->attrs[tri[0]].texcoord), alpha), vscale(from_f3(g->attrs[tri[1]].texcoord), bx)),
+                           vscale(from_f3(g->attrs[tri[2]].texcoord), by));
+  return intensity3(tex2d_wrap(material->textureCutout, texcoord.x, texcoord.y));
+}
+
+/* optixTrace of a radiance ray (raygeneration.cu:84-89) with the radiance any-hit program applied in canonical order */
+static int trace_radiance(const shade_ctx* c, const float o[3], const float d[3], float tmin, float tmax, besthit* hit, uint32_t* seed)
+{
+  const orc_scene* s = c->s;
+  if (!s->hasCutout) return trace_scene(s, o, d, tmin, tmax, c->mode, 0, hit, c->st);
+  hitkey skip; const hitkey* after = NULL;
+  for (;;)
+  {
+    if (!trace_scene_after(s, o, d, tmin, tmax, c->mode, 0, hit, c->st, after)) return 0;
+    const rt_MaterialDefinition* material = &s->materials[s->insts[hit->inst].material];
+    if (material->textureCutout == 0) return 1;                      /* hit records without an any-hit program */
+    const float opacity = cutout_opacity(s, material, hit);
+    if (opacity < 1.0f && opacity <= orc_rng(seed)) { skip.t = hit->t; skip.inst = hit->inst; skip.prim = hit->prim; after = &skip; continue; }
+    return 1;
+  }
+}
+
+/* optixTrace of a shadow ray (closesthit.cu:281-286): __anyhit__shadow terminates at any candidate, __anyhit__shadow_cutout
+ * ignores it stochastically.  Returns 1 when the visibility test failed (FLAG_SHADOW). */
+static int trace_shadow(const shade_ctx* c, const float o[3], const float d[3], float tmin, float tmax, uint32_t* seed)
+{
+  const orc_scene* s = c->s;
+  besthit hit;
+  if (!s->hasCutout) return trace_scene(s, o, d, tmin, tmax, c->mode, 1, &hit, c->st);
+  hitkey skip; const hitkey* after = NULL;
+  for (;;)
+  {
+    if (!trace_scene_after(s, o, d, tmin, tmax, c->mode, 0, &hit, c->st, after)) return 0;
+    const rt_MaterialDefinition* material = &s->materials[s->insts[hit.inst].material];
+    if (material->textureCutout == 0) return 1;
+    const float opacity = cutout_opacity(s, material, &hit);
+    if (opacity < 1.0f && opacity <= orc_rng(seed)) { skip.t = hit.t; skip.inst = hit.inst; skip.prim = hit.prim; after = &skip; continue; }
+    return 1;
+  }
+}
+
 static void closest_hit(const shade_ctx* c, const besthit* hit, prd_t* prd)
 {
   const orc_scene* s = c->s;
@@ -1142,7 +1265,8 @@ static void closest_hit(const shade_ctx* c, const besthit* hit, prd_t* prd)
   prd->pdf = 0.0f;
   const rt_MaterialDefinition* material = &s->materials[in->material];
   state.albedo = from_f3(material->albedo);
-  /* textureAlbedo: "next" row; textures are 0 in every in-scope configuration */
+  if (material->textureAlbedo != 0)   /* closesthit.cu:233-240 */
+    state.albedo = vmul(state.albedo, tex2d_wrap(material->textureAlbedo, state.texcoord.x, state.texcoord.y));
   prd->flags = (prd->flags & ~RT_FLAG_DIFFUSE) | RT_FLAG_HIT | material->flags;
   bsdf_sample(material, &state, prd);
 
@@ -1169,9 +1293,8 @@ static void closest_hit(const shade_ctx* c, const besthit* hit, prd_t* prd)
       if (0.0f < bp.w && !v3_is_null(f))
       {
         const float o[3] = { prd->pos.x, prd->pos.y, prd->pos.z }, d[3] = { ls.direction.x, ls.direction.y, ls.direction.z };
-        besthit b;
         if (c->st) c->st->shadowRays++;
-        const int occluded = trace_scene(s, o, d, c->sys->sceneEpsilon, ls.distance - c->sys->sceneEpsilon, c->mode, 1, &b, c->st);
+        const int occluded = trace_shadow(c, o, d, c->sys->sceneEpsilon, ls.distance - c->sys->sceneEpsilon, &prd->seed);
         if (!occluded)
         {
           if (prd->flags & RT_FLAG_VOLUME)
@@ -1218,7 +1341,7 @@ static v3 integrator(const shade_ctx* c, prd_t* prd)
     const float o[3] = { prd->pos.x, prd->pos.y, prd->pos.z }, d[3] = { prd->wi.x, prd->wi.y, prd->wi.z };
     besthit hit;
     if (c->st) c->st->radianceRays++;
-    if (trace_scene(c->s, o, d, c->sys->sceneEpsilon, prd->distance, c->mode, 0, &hit, c->st)) closest_hit(c, &hit, prd);
+    if (trace_radiance(c, o, d, c->sys->sceneEpsilon, prd->distance, &hit, &prd->seed)) closest_hit(c, &hit, prd);
     else miss_program(c->s, c->miss, c->sys->envRotation, prd);
 
     if (prd->flags & RT_FLAG_VOLUME)

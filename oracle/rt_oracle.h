@@ -8,7 +8,7 @@
  *   raygeneration      shaders/raygeneration.cu:42-149 (integrator), :152-164 (distribute),
  *                      :167-256 (path_tracer), :259-344 (path_tracer_local_copy)
  *   closest hit        shaders/closesthit.cu:126-305
- *   any hit (shadow)   shaders/anyhit.cu:84-91
+ *   any hit            shaders/anyhit.cu:84-91 (shadow), :46-80 and :94-132 (cutout opacity, canonical candidate order)
  *   miss               shaders/miss.cu:41-109
  *   lens shaders       shaders/lens_shader.cu:40-99
  *   light sampling     shaders/light_sample.cu:42-177
@@ -77,6 +77,13 @@ void orc_scene_get_inverse(const orc_scene* s, int instance, float out[12]);
 /* mode: 0 = oracle BVH, 1 = brute force over every triangle of every instance. */
 void orc_trace_closest(const orc_scene* s, const orc_ray* rays, uint64_t n, int mode, orc_hit* hits, orc_stats* stats);
 void orc_trace_any(const orc_scene* s, const orc_ray* rays, uint64_t n, int mode, uint8_t* occluded, orc_stats* stats);
+
+/* Closest hit AFTER the key (skipT, skipInst, skipPrim) in the canonical candidate order (t, instance, primitive): the
+ * step of the ordered any-hit processing (cutout opacity, anyhit.cu:46-132; see "Cutout opacity" in rt_oracle.c). */
+void orc_trace_closest_after(const orc_scene* s, const orc_ray* ray, float skipT, uint32_t skipInst, uint32_t skipPrim, orc_hit* hit);
+/* The material-texture fetch DEFINED by this repository (bilinear, wrap/wrap; handle = address of {uint32 w, h, 0, 0}
+ * followed by w*h RGBA32F texels).  out = rgb. */
+void orc_tex2d(uint64_t handle, float u, float v, float out[3]);
 
 /* Primary rays as the raygeneration program makes them for iteration `iteration` (one per launch index,
  * row-major launchWidth x launchHeight); rays of skipped launch indices get tmax = -1. */

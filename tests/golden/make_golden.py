@@ -25,6 +25,9 @@ CASES = {
     "cornell_sphere_24x24_2spp": ("rtigo3_cornell_box", dict(resolution="24 24", samplesSqrt=2, lensShader=2), 2),
     "geometry_48x27_4spp": ("rtigo3_geometry", dict(resolution="48 27", samplesSqrt=2), 4),
     "geometry_env_48x27_4spp": ("rtigo3_geometry", dict(resolution="48 27", samplesSqrt=2, miss=2, envMap="procedural 128 64", envRotation=0.15), 4),
+    # material textures: albedo modulation + the reference's own cutout any-hit programs run per candidate in canonical order
+    "textures_64x36_4spp": ("rtigo3_textures", dict(resolution="64 36", samplesSqrt=2), 4),
+    "textures_rr_env_48x27_3spp": ("rtigo3_textures", dict(resolution="48 27", samplesSqrt=2, miss=2, envMap="procedural 128 64", pathLengths="0 8"), 3),
     "cornell_tiled_3dev_40x16_2spp": ("rtigo3_cornell_box", dict(resolution="40 16", samplesSqrt=2, tileSize="8 8"), 2),
 }
 

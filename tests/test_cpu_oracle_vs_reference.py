@@ -53,7 +53,7 @@ def test_libm_oracle_reproduces_reference_frames(built, tmp_path, golden_frames,
 
 
 @pytest.mark.skipif(not (os.path.exists(orc.REF_LIB) or os.path.isdir(orc.REFERENCE_SHADERS)), reason="host-compiled reference not available")
-@pytest.mark.parametrize("key", ["cornell_32x32_4spp", "geometry_env_48x27_4spp"])
+@pytest.mark.parametrize("key", ["cornell_32x32_4spp", "geometry_env_48x27_4spp", "textures_64x36_4spp", "textures_rr_env_48x27_3spp"])
 def test_libm_oracle_equals_live_reference(built, tmp_path, key):
     got, app, scene, sysd = render_case(tmp_path, key, "libm")
     ref = orc.Reference(scene, app.info.miss)

@@ -25,6 +25,7 @@ SYMBOLS = [
     "rtc_device_count", "rtc_device_name", "rtc_peer_can_access", "rtc_peer_enable", "rtc_peer_disable", "rtc_memcpy_peer",
     "rtc_malloc", "rtc_free", "rtc_upload", "rtc_download", "rtc_memset", "rtc_host_alloc", "rtc_host_free",
     "rtc_gas_build", "rtc_gas_destroy", "rtc_ias_build", "rtc_scene_info_get", "rtc_scene_destroy", "rtc_instance_inverse",
+    "rtc_scene_set_instance_flags", "rtc_scene_set_albedo_textures", "rtc_texture_create", "rtc_texture_destroy",
     "rtc_launch", "rtc_launch_ex", "rtc_launch_counts_get", "rtc_launch_counts_reset", "rtc_timer_start", "rtc_timer_stop",
     "rtc_profile_enable", "rtc_profile_get", "rtc_trace_closest", "rtc_trace_any", "rtc_trace_count", "rtc_generate_primary",
     "rtc_composite", "rtc_tonemap", "rtc_stats_get", "rtc_stats_reset",
@@ -85,6 +86,10 @@ def lib():
         L.rtc_ias_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]
         L.rtc_scene_info_get.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(SceneInfo)]
         L.rtc_scene_destroy.argtypes = [C.c_void_p, C.c_uint64]
+        L.rtc_scene_set_instance_flags.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.rtc_scene_set_albedo_textures.argtypes = [C.c_void_p, C.c_uint64, C.c_int]
+        L.rtc_texture_create.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.rtc_texture_destroy.argtypes = [C.c_void_p, C.c_uint64]
         L.rtc_instance_inverse.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
         L.rtc_launch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int]
         L.rtc_launch_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -210,6 +215,23 @@ class Context:
 
     def scene_destroy(self, top):
         _check(self.L.rtc_scene_destroy(self.h, int(top)))
+
+    def set_instance_flags(self, top, first, flags):
+        f = np.ascontiguousarray(flags, dtype=np.uint32)
+        _check(self.L.rtc_scene_set_instance_flags(self.h, int(top), first, len(f), f.ctypes.data_as(C.c_void_p)))
+
+    def set_albedo_textures(self, top, enable):
+        _check(self.L.rtc_scene_set_albedo_textures(self.h, int(top), 1 if enable else 0))
+
+    def texture_create(self, rgba):
+        """rgba: float32 [height, width, 4] -> handle for MaterialDefinition.textureAlbedo / textureCutout."""
+        t = np.ascontiguousarray(rgba, dtype=np.float32)
+        h = C.c_uint64(0)
+        _check(self.L.rtc_texture_create(self.h, t.shape[1], t.shape[0], t.ctypes.data_as(C.c_void_p), C.byref(h)))
+        return h.value
+
+    def texture_destroy(self, handle):
+        _check(self.L.rtc_texture_destroy(self.h, int(handle)))
 
     def instance_inverse(self, top, instance):
         out = np.zeros(12, dtype=np.float32)

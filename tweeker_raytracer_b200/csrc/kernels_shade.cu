@@ -21,6 +21,8 @@ constexpr uint32_t kNoPixel = 0xffffffffu;
 // device counters of one batch: [0..63] extend counts per depth, [64..127] shadow counts, [128..191] extend cursors,
 // [192..255] connect cursors, [256 + 8 d + c] paths of shade class c at depth d
 constexpr uint32_t kNumCounters = 256 + 64 * 8;
+constexpr uint32_t kPendingRR = 0x80000000u;          // misc.y bit: Russian roulette postponed until the shadow ray is resolved
+constexpr uint32_t kDepthMask = 0x0000ffffu;
 constexpr uint64_t kMaxPathsInFlight = 64ull << 20;   // 64 Mi paths x 320 B of wavefront state = 21 GB of the 180 GB HBM
 
 struct WfArgs
@@ -175,12 +177,17 @@ template <int CLASS> SD float4 bsdf_eval_class(const rt_MaterialDefinition& m, c
   return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
-template <int CLASS>
+// TEX = false: the kernels of scenes without material textures (every configuration of BASELINE.json).
+// TEX = true : interpolates the texture coordinates and modulates the albedo (closesthit.cu:233-240); with deferRR the
+//              Russian roulette of a path that casts a shadow ray is left to k_cutout_shadow, because the shadow ray's
+//              any-hit programs draw from the path's seed BEFORE the integrator does (closesthit.cu:281 precedes
+//              raygeneration.cu:111).
+template <int CLASS, bool TEX>
 __global__ void __launch_bounds__(kBlock)
 k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
         const uint32_t* __restrict__ queueIn, const uint32_t* __restrict__ countIn,
         uint32_t* __restrict__ queueOut, uint32_t* __restrict__ countOut,
-        uint32_t* __restrict__ shadowQueue, uint32_t* __restrict__ shadowCount)
+        uint32_t* __restrict__ shadowQueue, uint32_t* __restrict__ shadowCount, const int deferRR)
 {
   const rt_SystemData& sys = a.sys;
   const uint32_t n = *countIn;
@@ -188,7 +195,7 @@ k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
   for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride)
   {
     const uint32_t i = base + threadIdx.x;
-    bool continues = false, shadow = false;
+    bool continues = false, shadow = false, pendingRR = false;
     uint32_t p = 0;
     if (i < n)
     {
@@ -204,7 +211,7 @@ k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
       prd.pos = f3(ro.x, ro.y, ro.z);
       prd.wi = f3(rd.x, rd.y, rd.z);
       prd.seed = misc.x;
-      int depth = (int)misc.y;
+      int depth = TEX ? (int)(misc.y & kDepthMask) : (int)misc.y;
       int stackIdx = (int)misc.z;
       float3 throughput = f3(tp.x, tp.y, tp.z);
       float3 radiance = f3(Lf.x, Lf.y, Lf.z);
@@ -292,6 +299,11 @@ k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
           prd.pdf = 0.0f;
           const rt_MaterialDefinition material = reinterpret_cast<const rt_MaterialDefinition*>(sys.materialDefinitions)[gi.materialIndex];
           state.albedo = f3(material.albedo);
+          if (TEX && material.textureAlbedo != 0)
+          {
+            const float3 texcoord = ld3(A0 + 9) * alpha + ld3(A1 + 9) * bx + ld3(A2 + 9) * by;
+            state.albedo = state.albedo * tex2d_wrap(material.textureAlbedo, texcoord.x, texcoord.y);
+          }
           prd.flags = (prd.flags & ~RT_FLAG_DIFFUSE) | RT_FLAG_HIT | material.flags;
           bsdf_sample_class<CLASS>(material, state, prd);
 
@@ -349,9 +361,13 @@ k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
         throughput = throughput * prd.f_over_pdf;
         if (sys.pathLengths.x <= depth)
         {
-          const float probability = fmax3(throughput);
-          if (probability < rng(prd.seed)) ended = true;
-          else throughput = divs(throughput, probability);
+          if (TEX && deferRR && shadow) pendingRR = true;
+          else
+          {
+            const float probability = fmax3(throughput);
+            if (probability < rng(prd.seed)) ended = true;
+            else throughput = divs(throughput, probability);
+          }
         }
       }
       if (!ended)
@@ -371,6 +387,7 @@ k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
         ++depth;
         continues = depth < sys.pathLengths.y;
       }
+      if (!continues) pendingRR = false;      // the path ends here whatever the roulette says: its draw cannot matter
 
       a.wf.radiance[p] = make_float4(radiance.x, radiance.y, radiance.z, __uint_as_float(prd.flags));
       if (continues)
@@ -378,12 +395,124 @@ k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
         a.wf.rayOrg[p] = make_float4(prd.pos.x, prd.pos.y, prd.pos.z, sys.sceneEpsilon);
         a.wf.rayDir[p] = make_float4(prd.wi.x, prd.wi.y, prd.wi.z, RT_DEFAULT_MAX);
         a.wf.throughput[p] = make_float4(throughput.x, throughput.y, throughput.z, prd.pdf);
-        misc.x = prd.seed; misc.y = (uint32_t)depth; misc.z = (uint32_t)stackIdx;
+        misc.x = prd.seed; misc.y = (uint32_t)depth | (pendingRR ? kPendingRR : 0u); misc.z = (uint32_t)stackIdx;
+        a.wf.misc[p] = misc;
+      }
+      else if (TEX && deferRR && shadow)
+      {
+        // the shadow ray's any-hit programs draw from this seed (k_cutout_shadow)
+        misc.x = prd.seed; misc.y = (uint32_t)depth;
         a.wf.misc[p] = misc;
       }
     }
-    { uint32_t* const q[1] = { queueOut }; uint32_t* const c[1] = { countOut }; block_append<1>(continues ? 0 : -1, p, q, c); }
+    // a path whose roulette is pending is appended to the next queue by k_cutout_shadow once its shadow ray is resolved
+    { uint32_t* const q[1] = { queueOut }; uint32_t* const c[1] = { countOut }; block_append<1>((continues && !pendingRR) ? 0 : -1, p, q, c); }
     { uint32_t* const q[1] = { shadowQueue }; uint32_t* const c[1] = { shadowCount }; block_append<1>(shadow ? 0 : -1, p, q, c); }
+  }
+}
+
+// ---- ordered any-hit processing of cutout materials (anyhit.cu:46-80, :94-132) --------------------------------------------
+// Candidates of a ray are presented closest first (canonical order (t, instance, primitive)); the kernels below play the
+// any-hit program on the candidate in hit[p] / hitInst[p] and queue the path for a re-trace past it when it is ignored.
+
+// opacity of the candidate of path p; false when the instance's hit records have no cutout program or no texture is bound
+SD bool cutout_candidate(const WfArgs& a, const SceneDesc& sc, uint32_t inst, const float4 hit, bool& cutoutRecords, float& opacity)
+{
+  cutoutRecords = (__ldg(sc.instFlags + inst) & RTC_INSTANCE_CUTOUT) != 0u;
+  if (!cutoutRecords) return false;
+  const rt_GeometryInstanceData gi = sc.geomInst[inst];
+  const uint64_t texture = reinterpret_cast<const rt_MaterialDefinition*>(a.sys.materialDefinitions)[gi.materialIndex].textureCutout;
+  if (texture == 0) return false;
+  const uint32_t prim = __float_as_uint(hit.w);
+  const uint32_t* ix = reinterpret_cast<const uint32_t*>(gi.indices) + 3u * (size_t)prim;
+  const uint32_t i0 = __ldg(ix), i1 = __ldg(ix + 1), i2 = __ldg(ix + 2);
+  const float* A0 = reinterpret_cast<const float*>(gi.attributes) + 12u * (size_t)i0;
+  const float* A1 = reinterpret_cast<const float*>(gi.attributes) + 12u * (size_t)i1;
+  const float* A2 = reinterpret_cast<const float*>(gi.attributes) + 12u * (size_t)i2;
+  const float bx = hit.y, by = hit.z;
+  const float alpha = 1.0f - bx - by;
+  const float3 texcoord = ld3(A0 + 9) * alpha + ld3(A1 + 9) * bx + ld3(A2 + 9) * by;
+  opacity = intensity3(tex2d_wrap(texture, texcoord.x, texcoord.y));
+  return true;
+}
+
+// __anyhit__radiance_cutout on the closest candidate of every path in queueIn; ignored -> queueOut (re-trace past it)
+__global__ void __launch_bounds__(kBlock)
+k_cutout_radiance(const __grid_constant__ WfArgs a, const SceneDesc sc, const uint32_t* __restrict__ queueIn, const uint32_t* __restrict__ countIn,
+                  uint32_t* __restrict__ queueOut, uint32_t* __restrict__ countOut)
+{
+  const uint32_t n = *countIn;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride)
+  {
+    const uint32_t i = base + threadIdx.x;
+    bool again = false; uint32_t p = 0;
+    if (i < n)
+    {
+      p = queueIn[i];
+      const uint32_t inst = a.wf.hitInst[p];
+      bool records; float opacity;
+      if (inst != 0xffffffffu && cutout_candidate(a, sc, inst, a.wf.hit[p], records, opacity) && opacity < 1.0f)
+      {
+        uint32_t seed = a.wf.misc[p].x;
+        again = opacity <= rng(seed);          // optixIgnoreIntersection
+        a.wf.misc[p].x = seed;
+      }
+    }
+    { uint32_t* const q[1] = { queueOut }; uint32_t* const c[1] = { countOut }; block_append<1>(again ? 0 : -1, p, q, c); }
+  }
+}
+
+// __anyhit__shadow / __anyhit__shadow_cutout on the closest candidate of every shadow ray in queueIn.  No candidate left: the
+// light is visible, the contribution is added (closesthit.cu:289-299).  Ignored: queueOut (re-trace past it).  Once the ray
+// is resolved, a postponed Russian roulette is played and the survivor appended to the next extend queue.
+__global__ void __launch_bounds__(kBlock)
+k_cutout_shadow(const __grid_constant__ WfArgs a, const SceneDesc sc, const uint32_t* __restrict__ queueIn, const uint32_t* __restrict__ countIn,
+                uint32_t* __restrict__ queueOut, uint32_t* __restrict__ countOut, uint32_t* __restrict__ queueNext, uint32_t* __restrict__ countNext)
+{
+  const uint32_t n = *countIn;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride)
+  {
+    const uint32_t i = base + threadIdx.x;
+    bool again = false, survives = false; uint32_t p = 0;
+    if (i < n)
+    {
+      p = queueIn[i];
+      const uint32_t inst = a.wf.hitInst[p];
+      uint4 misc = a.wf.misc[p];
+      const uint32_t seedIn = misc.x, flagsIn = misc.y;
+      if (inst == 0xffffffffu)
+      {
+        const float4 c = a.wf.shadowContrib[p];
+        float4 L = a.wf.radiance[p];
+        L.x = L.x + c.x; L.y = L.y + c.y; L.z = L.z + c.z;
+        a.wf.radiance[p] = L;
+      }
+      else
+      {
+        bool records; float opacity = 1.0f;
+        cutout_candidate(a, sc, inst, a.wf.hit[p], records, opacity);
+        if (records && opacity < 1.0f) again = opacity <= rng(misc.x);
+        // else: FLAG_SHADOW, optixTerminateRay
+      }
+      if (!again && (misc.y & kPendingRR))
+      {
+        misc.y &= ~kPendingRR;
+        float4 tp = a.wf.throughput[p];
+        const float3 throughput = f3(tp.x, tp.y, tp.z);
+        const float probability = fmax3(throughput);
+        if (!(probability < rng(misc.x)))
+        {
+          const float3 t = divs(throughput, probability);
+          a.wf.throughput[p] = make_float4(t.x, t.y, t.z, tp.w);
+          survives = true;
+        }
+      }
+      if (misc.x != seedIn || misc.y != flagsIn) a.wf.misc[p] = misc;
+    }
+    { uint32_t* const q[1] = { queueOut }; uint32_t* const c[1] = { countOut }; block_append<1>(again ? 0 : -1, p, q, c); }
+    { uint32_t* const q[1] = { queueNext }; uint32_t* const c[1] = { countNext }; block_append<1>(survives ? 0 : -1, p, q, c); }
   }
 }
 
@@ -552,21 +681,88 @@ namespace {
 
 template <int CLASS>
 void launch_shade_class(rtc_context* ctx, int grid, const WfArgs& a, const SceneDesc& sc, uint32_t* bins, uint32_t binStride, uint32_t* binCounts,
-                        uint32_t* qOut, uint32_t* countOut, uint32_t* shadowQueue, uint32_t* shadowCount)
+                        uint32_t* qOut, uint32_t* countOut, uint32_t* shadowQueue, uint32_t* shadowCount, bool tex, bool deferRR)
 {
-  k_shade<CLASS><<<grid, kBlock, 0, ctx->stream>>>(a, sc, bins + (size_t)CLASS * binStride, binCounts + CLASS, qOut, countOut, shadowQueue, shadowCount);
+  if (tex) k_shade<CLASS, true><<<grid, kBlock, 0, ctx->stream>>>(a, sc, bins + (size_t)CLASS * binStride, binCounts + CLASS, qOut, countOut, shadowQueue, shadowCount, deferRR ? 1 : 0);
+  else     k_shade<CLASS, false><<<grid, kBlock, 0, ctx->stream>>>(a, sc, bins + (size_t)CLASS * binStride, binCounts + CLASS, qOut, countOut, shadowQueue, shadowCount, 0);
 }
 
 void launch_shade_classes(rtc_context* ctx, int grid, const WfArgs& a, const SceneDesc& sc, uint32_t* bins, uint32_t binStride, uint32_t* binCounts,
-                          uint32_t* qOut, uint32_t* countOut, uint32_t* shadowQueue, uint32_t* shadowCount)
+                          uint32_t* qOut, uint32_t* countOut, uint32_t* shadowQueue, uint32_t* shadowCount, bool tex, bool deferRR)
 {
-  launch_shade_class<SHADE_MISS>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount);
-  launch_shade_class<SHADE_BRDF_DIFFUSE>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount);
-  launch_shade_class<SHADE_BRDF_SPECULAR>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount);
-  launch_shade_class<SHADE_BSDF_SPECULAR>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount);
-  launch_shade_class<SHADE_BRDF_GGX>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount);
-  launch_shade_class<SHADE_BSDF_GGX>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount);
-  launch_shade_class<SHADE_OTHER>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount);
+  launch_shade_class<SHADE_MISS>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR);
+  launch_shade_class<SHADE_BRDF_DIFFUSE>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR);
+  launch_shade_class<SHADE_BRDF_SPECULAR>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR);
+  launch_shade_class<SHADE_BSDF_SPECULAR>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR);
+  launch_shade_class<SHADE_BRDF_GGX>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR);
+  launch_shade_class<SHADE_BSDF_GGX>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR);
+  launch_shade_class<SHADE_OTHER>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR);
+}
+
+// scratch of the ordered any-hit processing: two queues of `capacity` path ids + {count 0, count 1, cursor, pad}
+int ensure_cutout_buffers(rtc_context* ctx, uint64_t capacity)
+{
+  WavefrontBuffers& wf = ctx->wf;
+  if (wf.cutCapacity >= capacity) return 0;
+  if (wf.cutBase) { RTC_CUDA(cudaStreamSynchronize(ctx->stream)); RTC_CUDA(cudaFree(wf.cutBase)); wf.cutBase = nullptr; wf.cutCapacity = 0; }
+  const uint64_t q = (4 * capacity + 255u) & ~(uint64_t)255u;
+  void* base = nullptr;
+  RTC_CUDA(cudaMalloc(&base, 2 * q + 256));
+  char* b = static_cast<char*>(base);
+  wf.cutBase = base; wf.cutCapacity = capacity;
+  wf.cutQueue[0] = (uint32_t*)b; wf.cutQueue[1] = (uint32_t*)(b + q); wf.cutCounters = (uint32_t*)(b + 2 * q);
+  return 0;
+}
+
+// reads one device counter back (the ordered any-hit rounds need to know when no candidate was ignored any more)
+int read_counter(rtc_context* ctx, const uint32_t* d_counter, uint32_t* out)
+{
+  RTC_CUDA(cudaMemcpyAsync(out, d_counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  RTC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// After extend: play __anyhit__radiance_cutout on the closest candidates, re-trace the ignored ones, repeat until none is ignored.
+int resolve_radiance_candidates(rtc_context* ctx, const SceneRecord* scene, const WfArgs& a, int grid, const uint32_t* queue, const uint32_t* count)
+{
+  const WavefrontBuffers& wf = ctx->wf;
+  for (int round = 0;; ++round)
+  {
+    const int o = round & 1;
+    RTC_CUDA(cudaMemsetAsync(wf.cutCounters + o, 0, sizeof(uint32_t), ctx->stream));
+    if (int rc = profile_begin(ctx, RTC_KERNEL_SHADE)) return rc;
+    k_cutout_radiance<<<grid, kBlock, 0, ctx->stream>>>(a, scene->desc, queue, count, wf.cutQueue[o], wf.cutCounters + o);
+    ctx->kernelLaunches++;
+    if (int rc = profile_end(ctx)) return rc;
+    uint32_t ignored = 0;
+    if (int rc = read_counter(ctx, wf.cutCounters + o, &ignored)) return rc;
+    if (ignored == 0) return 0;
+    if (int rc = launch_extend_after(ctx, &scene->desc, wf, wf.cutQueue[o], wf.cutCounters + o, wf.cutCounters + 2)) return rc;
+    queue = wf.cutQueue[o]; count = wf.cutCounters + o;
+  }
+}
+
+// Instead of connect: shadow rays as ordered closest-hit queries with __anyhit__shadow / __anyhit__shadow_cutout per candidate.
+int resolve_shadow_candidates(rtc_context* ctx, const SceneRecord* scene, const WfArgs& a, int grid, const uint32_t* shadowCount,
+                              uint32_t* queueNext, uint32_t* countNext)
+{
+  const WavefrontBuffers& wf = ctx->wf;
+  const uint32_t* queue = wf.shadowQueue; const uint32_t* count = shadowCount;
+  if (int rc = launch_connect_closest(ctx, &scene->desc, wf, queue, count, wf.cutCounters + 2, false)) return rc;
+  for (int round = 0;; ++round)
+  {
+    const int o = round & 1;
+    RTC_CUDA(cudaMemsetAsync(wf.cutCounters + o, 0, sizeof(uint32_t), ctx->stream));
+    if (int rc = profile_begin(ctx, RTC_KERNEL_SHADE)) return rc;
+    k_cutout_shadow<<<grid, kBlock, 0, ctx->stream>>>(a, scene->desc, queue, count, wf.cutQueue[o], wf.cutCounters + o, queueNext, countNext);
+    ctx->kernelLaunches++;
+    if (int rc = profile_end(ctx)) return rc;
+    uint32_t ignored = 0;
+    if (int rc = read_counter(ctx, wf.cutCounters + o, &ignored)) return rc;
+    if (ignored == 0) return 0;
+    if (int rc = launch_connect_closest(ctx, &scene->desc, wf, wf.cutQueue[o], wf.cutCounters + o, wf.cutCounters + 2, true)) return rc;
+    queue = wf.cutQueue[o]; count = wf.cutCounters + o;
+  }
 }
 
 } // namespace
@@ -589,6 +785,11 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
   uint64_t perBatch = maxPaths / pixels; if (perBatch < 1) perBatch = 1; if (perBatch > (uint64_t)iterCount) perBatch = (uint64_t)iterCount;
   if (pixels * perBatch > 0x7fffffffull) RTC_FAIL("launch too large");
   if (int rc = ensure_wavefront(ctx, pixels * perBatch)) return rc;
+  // Material textures (off in every BASELINE configuration, like the reference's GUI default): `cutout` switches to the ordered
+  // any-hit processing, which synchronises with the host between rounds; `tex` selects the texture-aware shade kernels.
+  const bool cutout = scene->numCutout > 0;
+  const bool tex = cutout || scene->albedoTextures;
+  if (cutout) { if (int rc = ensure_cutout_buffers(ctx, pixels * perBatch)) return rc; }
 
   const int gridShade = ctx->numSMs * 8;
   for (int done = 0; done < iterCount; done += (int)perBatch)
@@ -607,13 +808,18 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
     for (int d = 0; d < maxDepth; ++d)
     {
       if (int rc = launch_extend(ctx, &scene->desc, ctx->wf, qIn, cnt + d, cnt + 128 + d, countWork)) return rc;
+      if (cutout) { if (int rc = resolve_radiance_candidates(ctx, scene, a, gridShade, qIn, cnt + d)) return rc; }
       if (int rc = profile_begin(ctx, RTC_KERNEL_SHADE)) return rc;
       uint32_t* binCounts = cnt + 256 + d * 8;
       k_bin<<<gridShade, kBlock, 0, ctx->stream>>>(a, scene->desc, qIn, cnt + d, ctx->wf.bins, ctx->wf.binStride, binCounts);
-      launch_shade_classes(ctx, gridShade, a, scene->desc, ctx->wf.bins, ctx->wf.binStride, binCounts, qOut, cnt + d + 1, ctx->wf.shadowQueue, cnt + 64 + d);
+      launch_shade_classes(ctx, gridShade, a, scene->desc, ctx->wf.bins, ctx->wf.binStride, binCounts, qOut, cnt + d + 1, ctx->wf.shadowQueue, cnt + 64 + d, tex, cutout);
       ctx->kernelLaunches += 1 + SHADE_NUM_CLASSES;
       if (int rc = profile_end(ctx)) return rc;
-      if (sys.numLights > 0) { if (int rc = launch_connect(ctx, &scene->desc, ctx->wf, cnt + 64 + d, cnt + 192 + d, countWork)) return rc; }
+      if (sys.numLights > 0)
+      {
+        if (cutout) { if (int rc = resolve_shadow_candidates(ctx, scene, a, gridShade, cnt + 64 + d, qOut, cnt + d + 1)) return rc; }
+        else        { if (int rc = launch_connect(ctx, &scene->desc, ctx->wf, cnt + 64 + d, cnt + 192 + d, countWork)) return rc; }
+      }
       uint32_t* t = qIn; qIn = qOut; qOut = t;
     }
     if (int rc = profile_begin(ctx, RTC_KERNEL_ACCUMULATE)) return rc;

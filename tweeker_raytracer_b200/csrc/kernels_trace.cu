@@ -80,16 +80,64 @@ struct ConnectPaths
   }
 };
 
+// ---- ordered any-hit processing (scenes with cutout materials only; anyhit.cu:46-132) ----------------------------------
+// The closest candidate of a ray is found by the normal kernels; when the any-hit program ignores it (k_cutout_radiance /
+// k_cutout_shadow in kernels_shade.cu), the ray is traced again for the next candidate AFTER the ignored one.  The ignored
+// hit sits in hit[path] / hitInst[path] and is the skip key; tmin moves up to just below its t (ties are resolved by the key).
+
+// radiance ray of a path, again, past the candidate in hit[path]
+struct ExtendPathsAfter
+{
+  const uint32_t* __restrict__ queue; const float4* __restrict__ rayOrg; const float4* __restrict__ rayDir;
+  float4* __restrict__ hit; uint32_t* __restrict__ hitInst;
+  uint32_t path; float4 prev; uint32_t prevInst;
+  __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d)
+  {
+    path = queue[i]; o = rayOrg[path]; d = rayDir[path]; prev = hit[path]; prevInst = hitInst[path];
+    o.w = fmaxf(o.w, __uint_as_float(__float_as_uint(prev.x) - 1u));      // prev.x > tmin > 0
+    return true;
+  }
+  __device__ __forceinline__ void load_skip(float& t, uint32_t& inst, uint32_t& prim) const { t = prev.x; inst = prevInst; prim = __float_as_uint(prev.w); }
+  template <class T> __device__ __forceinline__ void store(uint32_t, const T& tr) const
+  {
+    const TraceHit h = tr.result();
+    hit[path] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+    hitInst[path] = h.inst;
+  }
+};
+
+// shadow ray of a path as a CLOSEST-hit query (first candidate, or the next one after hit[path] when AFTER)
+template <bool AFTER>
+struct ConnectClosest
+{
+  const uint32_t* __restrict__ queue; const float4* __restrict__ shadowOrg; const float4* __restrict__ shadowDir;
+  float4* __restrict__ hit; uint32_t* __restrict__ hitInst;
+  uint32_t path; float4 prev; uint32_t prevInst;
+  __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d)
+  {
+    path = queue[i]; o = shadowOrg[path]; d = shadowDir[path];
+    if (AFTER) { prev = hit[path]; prevInst = hitInst[path]; o.w = fmaxf(o.w, __uint_as_float(__float_as_uint(prev.x) - 1u)); }
+    return true;
+  }
+  __device__ __forceinline__ void load_skip(float& t, uint32_t& inst, uint32_t& prim) const { t = prev.x; inst = prevInst; prim = __float_as_uint(prev.w); }
+  template <class T> __device__ __forceinline__ void store(uint32_t, const T& tr) const
+  {
+    const TraceHit h = tr.result();
+    hit[path] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+    hitInst[path] = h.inst;
+  }
+};
+
 // ---- kernels ---------------------------------------------------------------------------------------------------------
 
-template <bool ANY, bool COUNT, class Policy>
-__global__ void __launch_bounds__(kTraceBlock, RTC_TRACE_MIN_BLOCKS)
+template <bool ANY, bool COUNT, class Policy, bool SKIP = false>
+__global__ void __launch_bounds__(kTraceBlock, SKIP ? 4 : RTC_TRACE_MIN_BLOCKS)
 k_trace(const SceneDesc sc, Policy policy, uint32_t n, const uint32_t* __restrict__ nPtr, uint32_t* __restrict__ cursor,
         unsigned long long* __restrict__ counts)
 {
   __shared__ uint2 smem[RTC_SM_STACK * kTraceBlock + (11 * kTraceBlock + 1) / 2];     // stack columns, then eleven float columns (trace.cuh smRay)
   const uint32_t count = nPtr ? *nPtr : n;      // the wavefront keeps its queue lengths on the device
-  trace_stream<ANY, COUNT, kTraceBlock>(sc, count, cursor, policy, smem, counts);
+  trace_stream<ANY, COUNT, kTraceBlock, SKIP>(sc, count, cursor, policy, smem, counts);
 }
 
 inline int persistent_grid(const rtc_context* ctx) { return ctx->numSMs * RTC_TRACE_MIN_BLOCKS; }
@@ -151,6 +199,39 @@ int launch_connect(rtc_context* ctx, const SceneDesc* scene, const WavefrontBuff
   ConnectPaths p = { wf.shadowQueue, wf.shadowOrg, wf.shadowDir, wf.shadowContrib, wf.radiance, 0u };
   if (countWork) k_trace<true, true, ConnectPaths><<<persistent_grid(ctx), kTraceBlock, 0, ctx->stream>>>(*scene, p, 0u, count, cursor, ctx->d_launchCounts + 4);
   else           k_trace<true, false, ConnectPaths><<<persistent_grid(ctx), kTraceBlock, 0, ctx->stream>>>(*scene, p, 0u, count, cursor, nullptr);
+  ctx->kernelLaunches++;
+  RTC_CUDA(cudaGetLastError());
+  return profile_end(ctx);
+}
+
+// Re-trace of the radiance rays in `queue` past their ignored candidate (see ExtendPathsAfter).
+int launch_extend_after(rtc_context* ctx, const SceneDesc* scene, const WavefrontBuffers& wf, const uint32_t* queue, const uint32_t* count, uint32_t* cursor)
+{
+  if (int rc = profile_begin(ctx, RTC_KERNEL_EXTEND)) return rc;
+  ExtendPathsAfter p = { queue, wf.rayOrg, wf.rayDir, wf.hit, wf.hitInst, 0u, make_float4(0.f, 0.f, 0.f, 0.f), 0u };
+  RTC_CUDA(cudaMemsetAsync(cursor, 0, sizeof(uint32_t), ctx->stream));
+  k_trace<false, false, ExtendPathsAfter, true><<<persistent_grid(ctx), kTraceBlock, 0, ctx->stream>>>(*scene, p, 0u, count, cursor, nullptr);
+  ctx->kernelLaunches++;
+  RTC_CUDA(cudaGetLastError());
+  return profile_end(ctx);
+}
+
+// Shadow rays of `queue` as closest-hit queries into hit[] / hitInst[] (after = past the ignored candidate already there).
+int launch_connect_closest(rtc_context* ctx, const SceneDesc* scene, const WavefrontBuffers& wf, const uint32_t* queue, const uint32_t* count,
+                           uint32_t* cursor, bool after)
+{
+  if (int rc = profile_begin(ctx, RTC_KERNEL_CONNECT)) return rc;
+  RTC_CUDA(cudaMemsetAsync(cursor, 0, sizeof(uint32_t), ctx->stream));
+  if (after)
+  {
+    ConnectClosest<true> p = { queue, wf.shadowOrg, wf.shadowDir, wf.hit, wf.hitInst, 0u, make_float4(0.f, 0.f, 0.f, 0.f), 0u };
+    k_trace<false, false, ConnectClosest<true>, true><<<persistent_grid(ctx), kTraceBlock, 0, ctx->stream>>>(*scene, p, 0u, count, cursor, nullptr);
+  }
+  else
+  {
+    ConnectClosest<false> p = { queue, wf.shadowOrg, wf.shadowDir, wf.hit, wf.hitInst, 0u, make_float4(0.f, 0.f, 0.f, 0.f), 0u };
+    k_trace<false, false, ConnectClosest<false>, false><<<persistent_grid(ctx), kTraceBlock, 0, ctx->stream>>>(*scene, p, 0u, count, cursor, nullptr);
+  }
   ctx->kernelLaunches++;
   RTC_CUDA(cudaGetLastError());
   return profile_end(ctx);

@@ -51,7 +51,7 @@ SceneRecord* find_scene(rtc_context* ctx, uint64_t topObject)
 
 void free_scene(SceneRecord* s)
 {
-  cudaFree(s->d_desc); cudaFree(s->d_tlasNodes); cudaFree(s->d_instances); cudaFree(s->d_tlasLeaves); cudaFree(s->d_o2w); cudaFree(s->d_geomInst);
+  cudaFree(s->d_desc); cudaFree(s->d_tlasNodes); cudaFree(s->d_instances); cudaFree(s->d_tlasLeaves); cudaFree(s->d_o2w); cudaFree(s->d_geomInst); cudaFree(s->d_instFlags);
   delete s;
 }
 
@@ -154,6 +154,8 @@ int rtc_context_destroy(rtc_context* ctx)
   for (SceneRecord* s : ctx->scenes) free_scene(s);
   for (GasRecord& g : ctx->gas) { cudaFree(g.d_nodes); cudaFree(g.d_tris); }
   if (ctx->wf.base) cudaFree(ctx->wf.base);
+  if (ctx->wf.cutBase) cudaFree(ctx->wf.cutBase);
+  for (void* t : ctx->textures) cudaFree(t);
   cudaFree(ctx->d_stats);
   cudaFree(ctx->d_launchCounts);
   cudaFree(ctx->d_cursor);
@@ -446,6 +448,9 @@ int rtc_ias_build(rtc_context* ctx, const rtc_instance_desc* instances, uint32_t
   if (e == cudaSuccess) e = upload(&rec->d_instances, inst.data(), inst.size() * sizeof(float4));
   if (e == cudaSuccess) e = upload(&rec->d_o2w, o2w.data(), o2w.size() * sizeof(float4));
   if (e == cudaSuccess) e = upload(&rec->d_geomInst, gi.data(), gi.size() * sizeof(rt_GeometryInstanceData));
+  rec->instFlags.assign(numInstances, 0u);
+  if (e == cudaSuccess) e = upload(&rec->d_instFlags, rec->instFlags.data(), rec->instFlags.size() * 4u);
+  rec->desc.instFlags = (const uint32_t*)rec->d_instFlags;
   rec->desc.tlasNodes = (const uint4*)rec->d_tlasNodes;
   rec->desc.tlasLeaves = (const uint32_t*)rec->d_tlasLeaves;
   rec->desc.instances = (const float4*)rec->d_instances;
@@ -486,6 +491,63 @@ int rtc_scene_destroy(rtc_context* ctx, uint64_t topObject)
       return 0;
     }
   RTC_FAIL("unknown topObject");
+}
+
+// Per-instance hit-record selection (Device.cpp:1503-1513; updateMaterial :1141-1160 rewrites the SBT headers).
+int rtc_scene_set_instance_flags(rtc_context* ctx, uint64_t topObject, uint32_t first, uint32_t count, const uint32_t* flags)
+{
+  SceneRecord* s = find_scene(ctx, topObject);
+  if (!s) RTC_FAIL("unknown topObject");
+  if ((uint64_t)first + count > s->desc.numInstances) RTC_FAIL("instance range out of bounds");
+  if (count == 0) return 0;
+  if (!flags) RTC_FAIL("flags is null");
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  for (uint32_t i = 0; i < count; ++i) s->instFlags[first + i] = flags[i];
+  s->numCutout = 0;
+  for (uint32_t f : s->instFlags) if (f & RTC_INSTANCE_CUTOUT) s->numCutout++;
+  // stream-ordered behind the launches already enqueued; `flags` may be reused by the caller at once (pageable source: staged copy)
+  RTC_CUDA(cudaMemcpyAsync((uint32_t*)s->d_instFlags + first, &s->instFlags[first], (size_t)count * 4u, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+int rtc_scene_set_albedo_textures(rtc_context* ctx, uint64_t topObject, int enable)
+{
+  SceneRecord* s = find_scene(ctx, topObject);
+  if (!s) RTC_FAIL("unknown topObject");
+  s->albedoTextures = enable != 0;
+  return 0;
+}
+
+// Material textures: 16-byte header {width, height, 0, 0} + RGBA32F texels in one allocation; the handle is its address.
+int rtc_texture_create(rtc_context* ctx, uint32_t width, uint32_t height, const float* rgba, uint64_t* handle)
+{
+  if (!handle) RTC_FAIL("handle is null");
+  if (width == 0 || height == 0 || !rgba) RTC_FAIL("empty texture");
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  const size_t texelBytes = (size_t)width * height * 16u;
+  void* d = nullptr;
+  RTC_CUDA(cudaMalloc(&d, 16u + texelBytes));
+  const uint32_t header[4] = { width, height, 0u, 0u };
+  cudaError_t e = cudaMemcpy(d, header, 16u, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy((char*)d + 16, rgba, texelBytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(d); return rtc_set_error(__FILE__, __LINE__, "rtc_texture_create upload", (int)e, cudaGetErrorString(e)); }
+  ctx->textures.push_back(d);
+  *handle = (uint64_t)(uintptr_t)d;
+  return 0;
+}
+
+int rtc_texture_destroy(rtc_context* ctx, uint64_t handle)
+{
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  for (size_t i = 0; i < ctx->textures.size(); ++i)
+    if ((uint64_t)(uintptr_t)ctx->textures[i] == handle)
+    {
+      RTC_CUDA(cudaStreamSynchronize(ctx->stream));
+      RTC_CUDA(cudaFree(ctx->textures[i]));
+      ctx->textures.erase(ctx->textures.begin() + (long)i);
+      return 0;
+    }
+  RTC_FAIL("unknown texture handle");
 }
 
 int rtc_instance_inverse(rtc_context* ctx, uint64_t topObject, uint32_t instance, float out[12])

@@ -49,6 +49,7 @@ struct SceneDesc
   const float4*   instances;
   const float4*   objectToWorld;
   const rt_GeometryInstanceData* geomInst;
+  const uint32_t* instFlags;      // RTC_INSTANCE_* per instance (which hit records the instance uses)
   uint32_t        numInstances;
   uint32_t        numTlasNodes;
   uint32_t        numTlasLeaves;
@@ -84,7 +85,10 @@ struct SceneRecord
 {
   SceneDesc desc{};          // host copy
   SceneDesc* d_desc = nullptr;
-  void *d_tlasNodes = nullptr, *d_instances = nullptr, *d_tlasLeaves = nullptr, *d_o2w = nullptr, *d_geomInst = nullptr;
+  void *d_tlasNodes = nullptr, *d_instances = nullptr, *d_tlasLeaves = nullptr, *d_o2w = nullptr, *d_geomInst = nullptr, *d_instFlags = nullptr;
+  std::vector<uint32_t> instFlags;         // host copy of the per-instance flags
+  uint32_t numCutout = 0;                  // instances using the cutout hit records: > 0 selects the ordered any-hit path
+  bool     albedoTextures = false;         // MaterialDefinition.textureAlbedo may be non-zero: selects the textured shade kernels
   std::vector<float> inverses;             // 12 floats per instance (host copy of the world->object matrices)
   uint64_t totalNodes = 0, totalTris = 0;  // unique GAS nodes / triangles referenced + instance level
   uint32_t numGas = 0;
@@ -108,6 +112,12 @@ struct WavefrontBuffers
   uint32_t *counters = nullptr;                    // [0..63] extend counts per depth, [64..127] shadow counts per depth,
                                                    // [128..191] extend ray cursors, [192..255] connect ray cursors
   void* base = nullptr;
+  // ordered any-hit processing (scenes with cutout materials only): two ping-pong queues of paths whose closest candidate
+  // was ignored, and their counters {count A, count B, cursor}; allocated on first use
+  uint32_t *cutQueue[2] = { nullptr, nullptr };
+  uint32_t *cutCounters = nullptr;
+  uint64_t cutCapacity = 0;
+  void* cutBase = nullptr;
 };
 
 struct rtc_context
@@ -130,6 +140,7 @@ struct rtc_context
   std::vector<ProfileSpan> spans;
   std::vector<cudaEvent_t> eventPool;
   rtc_profile profile{};
+  std::vector<void*> textures;                    // rtc_texture_create allocations still alive
   unsigned long long* d_launchCounts = nullptr;   // 2 x {nodes, tris, insts, rays}: extend, connect
   uint32_t* d_cursor = nullptr;                   // ray cursor of the query kernels (rtc_trace_*)
 };
@@ -157,6 +168,10 @@ int launch_trace_count(rtc_context* ctx, const SceneDesc* d_scene, const rtc_ray
 int launch_extend(rtc_context* ctx, const SceneDesc* d_scene, const WavefrontBuffers& wf, const uint32_t* queue, const uint32_t* count,
                   uint32_t* cursor, bool countWork);
 int launch_connect(rtc_context* ctx, const SceneDesc* d_scene, const WavefrontBuffers& wf, const uint32_t* count, uint32_t* cursor, bool countWork);
+// ordered any-hit processing (cutout materials): re-trace past an ignored candidate / shadow rays as closest-hit queries
+int launch_extend_after(rtc_context* ctx, const SceneDesc* d_scene, const WavefrontBuffers& wf, const uint32_t* queue, const uint32_t* count, uint32_t* cursor);
+int launch_connect_closest(rtc_context* ctx, const SceneDesc* d_scene, const WavefrontBuffers& wf, const uint32_t* queue, const uint32_t* count,
+                           uint32_t* cursor, bool after);
 int launch_generate_primary(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uint32_t h, int iteration, rtc_ray* rays);
 int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uint32_t h, int raygen, int miss, int iterFirst, int iterCount,
                      int accumFirst, bool countWork);

@@ -318,6 +318,28 @@ SD float3 env_lookup(const rt_SystemData& sys, float u, float v)
   return f3(a.x + ay * (b.x - a.x), a.y + ay * (b.y - a.y), a.z + ay * (b.z - a.z));
 }
 
+// ---- material textures: software bilinear filter, wrap u AND v (replaces tex2D at closesthit.cu:235, anyhit.cu:70, :119;
+// the reference's sampler is wrap/wrap, linear, normalised coordinates, src/Texture.cpp:670-675).  handle = address of a
+// 16-byte header {width, height, 0, 0} followed by the RGBA32F texels (rtc_texture_create).
+SD float3 tex2d_wrap(uint64_t handle, float u, float v)
+{
+  const uint4 header = __ldg(reinterpret_cast<const uint4*>(handle));
+  const float4* tex = reinterpret_cast<const float4*>(handle) + 1;
+  const int W = (int)header.x, H = (int)header.y;
+  const float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
+  const float fx = floorf(x), fy = floorf(y);
+  const float ax = x - fx, ay = y - fy;
+  int x0 = (int)fx % W; if (x0 < 0) x0 += W;
+  int x1 = x0 + 1; if (x1 >= W) x1 = 0;
+  int y0 = (int)fy % H; if (y0 < 0) y0 += H;
+  int y1 = y0 + 1; if (y1 >= H) y1 = 0;
+  const float4 t00 = __ldg(tex + (size_t)y0 * W + x0), t10 = __ldg(tex + (size_t)y0 * W + x1);
+  const float4 t01 = __ldg(tex + (size_t)y1 * W + x0), t11 = __ldg(tex + (size_t)y1 * W + x1);
+  const float3 a = f3(t00.x + ax * (t10.x - t00.x), t00.y + ax * (t10.y - t00.y), t00.z + ax * (t10.z - t00.z));
+  const float3 b = f3(t01.x + ax * (t11.x - t01.x), t01.y + ax * (t11.y - t01.y), t01.z + ax * (t11.z - t01.z));
+  return f3(a.x + ay * (b.x - a.x), a.y + ay * (b.y - a.y), a.z + ay * (b.z - a.z));
+}
+
 // ---- lights ----
 struct LightSample { float3 direction; float distance; float3 emission; float pdf; int index; };
 

@@ -179,9 +179,13 @@ __device__ unsigned int g_rtcStackOverflows = 0;
 // One ray's traversal as a resumable state machine: begin() once, then step() until it returns false.
 // A step visits one wide node (or pops a postponed leaf group) and tests the triangles / enters the instance it yields.
 // Closest hit (ANY = false): smallest t in (tmin, tmax), ties -> smaller (instance, primitive).  ANY = true: first hit ends the ray.
-template <bool ANY, bool COUNT, int BLOCK>
+// SKIP = true (ordered any-hit processing of cutout materials, anyhit.cu:46-132): only candidates that come AFTER the key
+// (skipT, skipInst, skipPrim) in the canonical order (t, instance, primitive) count, so repeated closest-hit queries
+// enumerate the candidates of a ray in that order.
+template <bool ANY, bool COUNT, int BLOCK, bool SKIP = false>
 struct Traversal
 {
+  float skipT; uint32_t skipInst, skipPrim;       // SKIP only
   // World ray origin/direction (needed only when an instance is entered or left) and the barycentric numerators of the
   // best hit (written once per accepted hit) live in shared memory, column-major like the stack: nine registers less,
   // which is what lets more CTAs fit on the SM.  Slots: 0-2 origin, 3-5 direction, 6 V, 7 W, 8 det, 9-10 triangle array of the
@@ -319,6 +323,7 @@ struct Traversal
         if (tri_test(orr, br.ox, br.oy, br.oz, v0, v1, v2, t, det, V, W) && t > tmin)
         {
           const uint32_t prim = __float_as_uint(v0.w);
+          if (SKIP && !(t > skipT || (t == skipT && (curInst > skipInst || (curInst == skipInst && prim > skipPrim))))) continue;
           if (ANY)
           {
             if (t < tlimit) { hitT = t; hitInst = curInst; hitPrim = prim; return false; }
@@ -356,11 +361,11 @@ struct Traversal
 // Persistent-warp driver: every lane owns one ray at a time; lanes whose ray has finished take the next ray index from a
 // global cursor (one atomicAdd per warp and refill), so short rays do not leave their lanes idle while the longest ray of
 // the warp finishes.  Policy supplies load(i, org, dir) -> bool (false: skip this index) and store(i, traversal).
-template <bool ANY, bool COUNT, int BLOCK, class Policy>
+template <bool ANY, bool COUNT, int BLOCK, bool SKIP, class Policy>
 __device__ __forceinline__ void trace_stream(const SceneDesc& sc, uint32_t n, uint32_t* __restrict__ cursor, Policy& policy, uint2* smem,
                                              unsigned long long* __restrict__ countsOut)
 {
-  Traversal<ANY, COUNT, BLOCK> tr;
+  Traversal<ANY, COUNT, BLOCK, SKIP> tr;
   uint2 overflow[RTC_LM_STACK];
   tr.smStack = smem + threadIdx.x;
   tr.smRay = reinterpret_cast<float*>(smem + RTC_SM_STACK * BLOCK) + threadIdx.x;
@@ -388,6 +393,7 @@ __device__ __forceinline__ void trace_stream(const SceneDesc& sc, uint32_t n, ui
           float4 o, d;
           if (policy.load(index, o, d))
           {
+            if constexpr (SKIP) policy.load_skip(tr.skipT, tr.skipInst, tr.skipPrim);
             if (tr.begin(sc, o, d)) active = true;
             else { policy.store(index, tr); if (COUNT) cRays++; }
           }

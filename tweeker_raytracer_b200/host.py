@@ -58,7 +58,7 @@ SYMBOLS = ["rth_last_error", "rth_app_create", "rth_app_destroy", "rth_app_info"
            "rth_app_materials", "rth_app_lights", "rth_app_camera", "rth_app_system_data", "rth_app_tonemapper",
            "rth_app_environment", "rth_app_render", "rth_app_synchronize", "rth_app_frame", "rth_app_restart",
            "rth_app_set_composite", "rth_app_save_system", "rth_app_set_camera", "rth_app_update_material", "rth_app_update_light_emission", "rth_app_benchmark", "rth_app_screenshot", "rth_app_tonemap", "rth_app_context", "rth_app_stats",
-           "rth_process_group_id", "rth_app_join_group", "rth_app_group_reduce_mean", "rth_sample_range"]
+           "rth_app_update_material_textures", "rth_app_picture", "rth_process_group_id", "rth_app_join_group", "rth_app_group_reduce_mean", "rth_sample_range"]
 
 _lib = None
 
@@ -94,6 +94,8 @@ def lib():
         L.rth_app_save_system.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
         L.rth_app_set_camera.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
         L.rth_app_update_material.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int]
+        L.rth_app_update_material_textures.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.rth_app_picture.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_void_p)]
         L.rth_app_update_light_emission.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.rth_app_benchmark.argtypes = [C.c_void_p]
         L.rth_app_benchmark.restype = C.c_double
@@ -234,6 +236,18 @@ class App:
                                             c.ctypes.data_as(C.c_void_p), absorption_scale, ior, 1 if thinwalled else 0)
         if rc != 0:
             raise core.RtcError("updateMaterial(%d) failed" % index)
+
+    def update_material_textures(self, index, use_albedo, use_cutout):
+        """The GUI's texture check boxes of one material (switches the instances' hit records like Device::updateMaterial)."""
+        if self.L.rth_app_update_material_textures(self.h, index, 1 if use_albedo else 0, 1 if use_cutout else 0) != 0:
+            raise core.RtcError("updateMaterial(%d) failed" % index)
+
+    def picture(self, name):
+        """float32 [height, width, 4] texels of the "albedo" / "cutout" picture (row 0 = v 0), or None."""
+        w, h, t = C.c_uint(), C.c_uint(), C.c_void_p()
+        if self.L.rth_app_picture(self.h, name.encode(), C.byref(w), C.byref(h), C.byref(t)) != 0:
+            return None
+        return _copy(t.value, np.float32, 4 * w.value * h.value).reshape(h.value, w.value, 4)
 
     def update_light_emission(self, index, emission):
         e = np.asarray(emission, dtype=np.float32)

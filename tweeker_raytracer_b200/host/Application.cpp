@@ -195,7 +195,13 @@ void Application::setCompositeMode(int mode)
 void Application::getMaterialDefinitions(std::vector<MaterialDefinition>& out) const
 {
   out.resize(m_materialsGUI.size());
-  for (size_t i = 0; i < m_materialsGUI.size(); ++i) Device::convertMaterial(m_materialsGUI[i], out[i]);
+  for (size_t i = 0; i < m_materialsGUI.size(); ++i)
+  {
+    Device::convertMaterial(m_materialsGUI[i], out[i]);
+    // HOST handles (address of header + texels), valid while this Application lives: what a CPU checker dereferences
+    if (m_materialsGUI[i].useAlbedoTexture && m_pictureAlbedo) out[i].textureAlbedo = (uint64_t)(uintptr_t)m_pictureAlbedo->getHandleBlob().data();
+    if (m_materialsGUI[i].useCutoutTexture && m_pictureCutout) out[i].textureCutout = (uint64_t)(uintptr_t)m_pictureCutout->getHandleBlob().data();
+  }
 }
 
 // SystemData of one active device; in host-only mode the value fields are derived the way Device::setState does
@@ -451,8 +457,32 @@ void Application::createLights()
 // Only the environment map is created: the reference's two hard-coded material images are not sampled unless the GUI
 // enables them (Application.cpp:679-699, :1560-1561) and are treated as absent.  `envMap procedural [w h]` (or a
 // missing file) yields the analytic map of EnvMap::createProcedural.
+EnvMap* Application::getPicture(std::string const& name) const
+{
+  std::map<std::string, EnvMap*>::const_iterator it = m_mapPictures.find(name);
+  return (it == m_mapPictures.end()) ? nullptr : it->second;
+}
+
+// Application::createPictures (Application.cpp:679-699): the "albedo" and "cutout" pictures always exist (the materials
+// refer to them once the GUI toggles are set), the environment only for miss 2.
 void Application::createPictures()
 {
+  auto picture = [&](std::unique_ptr<EnvMap>& slot, std::string const& file, const char* name, bool cutout)
+  {
+    slot.reset(new EnvMap());
+    if (!slot->loadImage(file))
+    {
+      if (FILE* f = std::fopen(file.c_str(), "rb"))
+      {
+        std::fclose(f);
+        std::cerr << "WARNING: createPictures() could not decode " << file << " (PNG, PGM/PPM and .hdr are supported), using the procedural " << name << " picture." << std::endl;
+      }
+      if (cutout) slot->createCutoutProcedural(256, 256); else slot->createAlbedoProcedural(256, 256);
+    }
+    m_mapPictures[std::string(name)] = slot.get();
+  };
+  picture(m_pictureAlbedo, m_fileAlbedo, "albedo", false);
+  picture(m_pictureCutout, m_fileCutout, "cutout", true);
   if (m_miss != 2) return;
   m_environmentMap.reset(new EnvMap());
   bool ok = false;
@@ -525,6 +555,8 @@ bool Application::loadSystemDescription(std::string const& filename)
   keywords["saturation"] = [&]() { m_tonemapperGUI.saturation = nextFloat(); };
   keywords["brightness"] = [&]() { m_tonemapperGUI.brightness = nextFloat(); };
   // extensions of this build (the reference would print its unknown-option warning and carry on)
+  keywords["textureAlbedo"] = [&]() { parser.getNextLine(token); m_fileAlbedo = token; };
+  keywords["textureCutout"] = [&]() { parser.getNextLine(token); m_fileCutout = token; };
   keywords["composite"] = [&]() { m_compositeMode = nextInt(); };
   keywords["batchIterations"] = [&]() { m_batch = std::max(1, nextInt()); };
 
@@ -597,6 +629,7 @@ bool Application::loadSceneDescription(std::string const& filename)
   float  curAbsorptionScale = 0.0f;
   float  curIOR = 1.5f;
   bool   curThinwalled = false;
+  bool   curAlbedoTexture = false, curCutoutTexture = false;   // extension keywords: the reference sets these from the GUI only
 
   static const std::map<std::string, FunctionIndex> bsdfNames = {
     { "brdf_diffuse", INDEX_BRDF_DIFFUSE }, { "brdf_specular", INDEX_BRDF_SPECULAR }, { "bsdf_specular", INDEX_BSDF_SPECULAR },
@@ -617,6 +650,8 @@ bool Application::loadSceneDescription(std::string const& filename)
     else if (token == "absorptionScale") { curAbsorptionScale = nextFloat(); }
     else if (token == "ior") { curIOR = nextFloat(); }
     else if (token == "thinwalled") { curThinwalled = (nextInt() != 0); }
+    else if (token == "albedoTexture") { curAlbedoTexture = (nextInt() != 0); }
+    else if (token == "cutoutTexture") { curCutoutTexture = (nextInt() != 0); }
     else if (token == "material")
     {
       std::string nameMaterialReference, nameMaterial;
@@ -635,6 +670,8 @@ bool Application::loadSceneDescription(std::string const& filename)
       materialGUI.absorptionScale = curAbsorptionScale;
       materialGUI.ior = curIOR;
       materialGUI.thinwalled = curThinwalled;
+      materialGUI.useAlbedoTexture = curAlbedoTexture;
+      materialGUI.useCutoutTexture = curCutoutTexture;
       m_materialsGUI.push_back(materialGUI);
       m_mapMaterialReferences[nameMaterialReference] = indexMaterial;
     }

@@ -59,6 +59,7 @@ public:
   std::vector<std::shared_ptr<sg::Triangles>> const& getGeometries() const { return m_geometries; }
   std::vector<FlatInstance> const& getFlatInstances() const { return m_flatInstances; }
   EnvMap const* getEnvironment() const { return m_environmentMap.get(); }
+  EnvMap* getPicture(std::string const& name) const;           // "albedo", "cutout", "environment"; nullptr when absent
   double getLastBenchmarkSeconds() const { return m_benchmarkSeconds; }
   std::string getLastError() const { return m_lastError; }
   void setCompositeMode(int mode);
@@ -104,6 +105,10 @@ private:
   float m_epsilonFactor = 500.0f;
   LensShader m_lensShader = LENS_SHADER_PINHOLE;
   std::string m_prefixScreenshot = "./img";
+  // the reference hard-codes these two file names (Application.cpp:684, :688); extension keywords "textureAlbedo" /
+  // "textureCutout" override them.  Unreadable or missing files fall back to procedural pictures.
+  std::string m_fileAlbedo = "./NVIDIA_Logo.jpg";
+  std::string m_fileCutout = "./slots_alpha.png";
   TonemapperGUI m_tonemapperGUI;
   int   m_compositeMode = 0;     // extension keyword "composite": 0 peer copies, 1 NCCL reduce (local-copy strategy)
   int   m_batch = 1;             // extension keyword "batchIterations": iterations per enqueue in benchmark()
@@ -120,7 +125,7 @@ private:
   std::map<std::string, int> m_mapMaterialReferences;
   std::vector<CameraDefinition> m_cameras;
   std::vector<LightDefinition> m_lights;
-  std::unique_ptr<EnvMap> m_environmentMap;
+  std::unique_ptr<EnvMap> m_environmentMap, m_pictureAlbedo, m_pictureCutout;
   std::map<std::string, EnvMap*> m_mapPictures;
   std::vector<FlatInstance> m_flatInstances;
   double m_benchmarkSeconds = 0.0;

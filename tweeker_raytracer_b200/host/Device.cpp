@@ -43,6 +43,8 @@ Device::~Device()
   release(m_systemData.envTexture);
   release(m_systemData.envCDF_U);
   release(m_systemData.envCDF_V);
+  if (m_textureAlbedo) { RTC_CHECK_NO_THROW(rtc_texture_destroy(m_context, m_textureAlbedo)); m_textureAlbedo = 0; }
+  if (m_textureCutout) { RTC_CHECK_NO_THROW(rtc_texture_destroy(m_context, m_textureCutout)); m_textureCutout = 0; }
   for (GeometryData& g : m_geometryData) { release(g.d_attributes); release(g.d_indices); }
   if (m_bufferHost) { RTC_CHECK_NO_THROW(rtc_host_free(m_context, m_bufferHost)); m_bufferHost = nullptr; }
   RTC_CHECK_NO_THROW(rtc_context_destroy(m_context));
@@ -57,12 +59,22 @@ static int2 calculateTileShift(const int2 tileSize)
   return shift;
 }
 
-// The environment map replaces the reference's Picture/Texture pair (Device.cpp:910-960): texels, CDFs and
-// integral go into SystemData.  The hard-coded albedo/cutout images of the reference are treated as absent.
+// Device::initTextures (Device.cpp:910-960): the "albedo" and "cutout" pictures become material textures (the reference
+// asserts that both exist; here a missing one just leaves its handle 0), the environment map's texels, CDFs and integral
+// go into SystemData.
 void Device::initTextures(std::map<std::string, EnvMap*> const& mapOfPictures)
 {
   activateContext();
   synchronizeStream();
+  auto createTexture = [&](const char* name, uint64_t& handle)
+  {
+    std::map<std::string, EnvMap*>::const_iterator itp = mapOfPictures.find(std::string(name));
+    if (itp == mapOfPictures.end() || itp->second == nullptr || itp->second->getWidth() == 0) return;
+    if (handle) { RTC_CHECK(rtc_texture_destroy(m_context, handle)); handle = 0; }
+    RTC_CHECK(rtc_texture_create(m_context, itp->second->getWidth(), itp->second->getHeight(), itp->second->getTexels().data(), &handle));
+  };
+  createTexture("albedo", m_textureAlbedo);
+  createTexture("cutout", m_textureCutout);
   std::map<std::string, EnvMap*>::const_iterator it = mapOfPictures.find(std::string("environment"));
   if (it == mapOfPictures.end() || it->second == nullptr) return;
   const EnvMap* env = it->second;
@@ -122,7 +134,7 @@ void Device::initLights(std::vector<LightDefinition> const& lights)
 void Device::convertMaterial(MaterialGUI const& gui, MaterialDefinition& material)
 {
   std::memset(&material, 0, sizeof(material));
-  material.textureAlbedo = 0;   // textures: "next" row of the scope table
+  material.textureAlbedo = 0;   // device handles are filled in by convertMaterialOnDevice
   material.textureCutout = 0;
   material.roughness = gui.roughness;
   material.indexBSDF = gui.indexBSDF;
@@ -140,6 +152,28 @@ void Device::convertMaterial(MaterialGUI const& gui, MaterialDefinition& materia
   material.flags = gui.thinwalled ? RT_FLAG_THINWALLED : 0u;
 }
 
+void Device::convertMaterialOnDevice(MaterialGUI const& gui, MaterialDefinition& material) const
+{
+  convertMaterial(gui, material);
+  material.textureAlbedo = gui.useAlbedoTexture ? m_textureAlbedo : 0;
+  material.textureCutout = gui.useCutoutTexture ? m_textureCutout : 0;
+}
+
+void Device::updateHitRecords()
+{
+  if (m_systemData.topObject == 0 || m_instances.empty()) return;
+  std::vector<uint32_t> flags(m_instances.size(), 0u);
+  bool albedo = false;
+  for (MaterialDefinition const& m : m_materials) albedo = albedo || m.textureAlbedo != 0;
+  for (size_t i = 0; i < m_instances.size(); ++i)
+  {
+    const int id = m_instances[i].materialIndex;
+    if (0 <= id && (size_t)id < m_materials.size() && m_materials[id].textureCutout != 0) flags[i] = RTC_INSTANCE_CUTOUT;
+  }
+  RTC_CHECK(rtc_scene_set_instance_flags(m_context, m_systemData.topObject, 0u, (uint32_t)flags.size(), flags.data()));
+  RTC_CHECK(rtc_scene_set_albedo_textures(m_context, m_systemData.topObject, albedo ? 1 : 0));
+}
+
 void Device::initMaterials(std::vector<MaterialGUI> const& materialsGUI)
 {
   activateContext();
@@ -152,11 +186,12 @@ void Device::initMaterials(std::vector<MaterialGUI> const& materialsGUI)
     RTC_CHECK(rtc_malloc(m_context, sizeof(MaterialDefinition) * (numMaterials ? numMaterials : 1), &m_systemData.materialDefinitions));
     m_materials.resize(numMaterials);
   }
-  for (int i = 0; i < numMaterials; ++i) convertMaterial(materialsGUI[i], m_materials[i]);
+  for (int i = 0; i < numMaterials; ++i) convertMaterialOnDevice(materialsGUI[i], m_materials[i]);
   RTC_CHECK(rtc_upload(m_context, m_systemData.materialDefinitions, m_materials.data(), sizeof(MaterialDefinition) * numMaterials));
   synchronizeStream();
   m_systemData.numMaterials = numMaterials;
   m_isDirtySystemData = true;
+  updateHitRecords();
 }
 
 void Device::initScene(std::shared_ptr<sg::Group> root, const unsigned int numGeometries)
@@ -173,6 +208,7 @@ void Device::initScene(std::shared_ptr<sg::Group> root, const unsigned int numGe
   RTC_CHECK(rtc_ias_build(m_context, m_instances.data(), (uint32_t)m_instances.size(), &top));
   m_systemData.topObject = top;
   m_isDirtySystemData = true;
+  updateHitRecords();
 }
 
 void Device::traverseNode(std::shared_ptr<sg::Node> node, float matrix[12], InstanceData data)
@@ -263,9 +299,11 @@ void Device::updateMaterial(const int idMaterial, MaterialGUI const& materialGUI
   synchronizeStream();
   MY_ASSERT(idMaterial < m_systemData.numMaterials);
   MaterialDefinition& material = m_materials[idMaterial];
-  convertMaterial(materialGUI, material);
+  const bool hadCutout = material.textureCutout != 0, hadAlbedo = material.textureAlbedo != 0;
+  convertMaterialOnDevice(materialGUI, material);
   RTC_CHECK(rtc_upload(m_context, m_systemData.materialDefinitions + sizeof(MaterialDefinition) * idMaterial, &material, sizeof(MaterialDefinition)));
   synchronizeStream();
+  if (hadCutout != (material.textureCutout != 0) || hadAlbedo != (material.textureAlbedo != 0)) updateHitRecords();   // "changeShader", Device.cpp:1111
 }
 
 void Device::setState(DeviceState const& state)

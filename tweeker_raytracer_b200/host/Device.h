@@ -72,6 +72,11 @@ protected:
   unsigned int createGeometry(std::shared_ptr<sg::Triangles> geometry);
   void createInstance(const unsigned int gas, float matrix[12], InstanceData const& data);
   void launch(const unsigned int launchWidth, const int raygen, const unsigned int iterationFirst, const unsigned int count);
+  // MaterialGUI -> device MaterialDefinition including the texture handles of this device (Device.cpp:1024-1052, :1112-1113)
+  void convertMaterialOnDevice(MaterialGUI const& gui, MaterialDefinition& material) const;
+  // createHitGroupRecords (Device.cpp:1492-1532) / the SBT header switch of updateMaterial (:1141-1160): instances whose
+  // material has a cutout texture get the cutout hit records
+  void updateHitRecords();
 
 public:
   RendererStrategy m_strategy;
@@ -91,6 +96,8 @@ protected:
   bool m_ownsSharedBuffer = false;
   int  m_launchWidth = 0;
   unsigned int m_seedOffset = 0;
+  uint64_t m_textureAlbedo = 0;   // the reference's m_textureAlbedo / m_textureCutout (Device.h), as rtc_texture handles
+  uint64_t m_textureCutout = 0;
 
   std::vector<GeometryData>      m_geometryData;   // indexed by sg::Triangles id
   std::vector<rtc_instance_desc> m_instances;

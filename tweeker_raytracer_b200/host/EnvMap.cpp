@@ -1,9 +1,11 @@
 #include "EnvMap.h"
 
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 
+#include "ImageIO.h"
 #include "rtigo3_abi.h"
 
 void EnvMap::setTexels(unsigned int width, unsigned int height, const float* rgba)
@@ -150,4 +152,83 @@ bool EnvMap::loadHDR(std::string const& filename)
   if (!ok) return false;
   setTexels((unsigned)w, (unsigned)h, rgba.data());
   return true;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Plain 2D pictures for the material textures
+// ------------------------------------------------------------------------------------------------------------------
+void EnvMap::setTexels2D(unsigned int width, unsigned int height, const float* rgba)
+{
+  m_width = width; m_height = height;
+  m_rgba.assign(rgba, rgba + (size_t)4 * width * height);
+  m_cdfU.clear(); m_cdfV.clear(); m_blob.clear();
+  m_integral = 1.0f;
+}
+
+std::vector<float> const& EnvMap::getHandleBlob()
+{
+  if (m_blob.empty() && m_width && m_height)
+  {
+    m_blob.resize(4 + m_rgba.size());
+    const unsigned int header[4] = { m_width, m_height, 0u, 0u };
+    std::memcpy(m_blob.data(), header, sizeof(header));
+    std::memcpy(m_blob.data() + 4, m_rgba.data(), m_rgba.size() * sizeof(float));
+  }
+  return m_blob;
+}
+
+bool EnvMap::loadImage(std::string const& filename)
+{
+  const size_t dot = filename.rfind('.');
+  std::string ext = (dot == std::string::npos) ? std::string() : filename.substr(dot + 1);
+  for (char& c : ext) c = (char)std::tolower((unsigned char)c);
+  if (ext == "hdr")
+  {
+    if (!loadHDR(filename)) return false;
+    m_cdfU.clear(); m_cdfV.clear(); m_blob.clear();
+    return true;
+  }
+  int w = 0, h = 0; std::vector<unsigned char> bytes;
+  const bool ok = (ext == "png") ? readPNG(filename, w, h, bytes) : ((ext == "ppm" || ext == "pgm" || ext == "pnm") ? readPNM(filename, w, h, bytes) : false);
+  if (!ok) return false;
+  std::vector<float> rgba((size_t)4 * w * h);
+  for (int y = 0; y < h; ++y)      // flip: texel row 0 = bottom row of the file
+    for (int x = 0; x < w; ++x)
+      for (int k = 0; k < 4; ++k)
+        rgba[4 * ((size_t)(h - 1 - y) * w + x) + k] = (float)bytes[4 * ((size_t)y * w + x) + k] / 255.0f;
+  setTexels2D((unsigned int)w, (unsigned int)h, rgba.data());
+  return true;
+}
+
+void EnvMap::createAlbedoProcedural(unsigned int width, unsigned int height)
+{
+  std::vector<float> rgba((size_t)4 * width * height);
+  for (unsigned int y = 0; y < height; ++y)
+    for (unsigned int x = 0; x < width; ++x)
+    {
+      const unsigned int tx = (x * 8u) / width, ty = (y * 8u) / height;
+      const float g = 0.25f + 0.75f * (float)((x * 8u) % width) / (float)width;      // gradient inside a tile
+      float* p = &rgba[4 * ((size_t)y * width + x)];
+      if ((tx ^ ty) & 1u) { p[0] = 0.46f * g; p[1] = 0.73f * g; p[2] = 0.0f; }       // green tiles
+      else                { p[0] = g; p[1] = g; p[2] = g; }                           // grey tiles
+      p[3] = 1.0f;
+    }
+  setTexels2D(width, height, rgba.data());
+}
+
+void EnvMap::createCutoutProcedural(unsigned int width, unsigned int height)
+{
+  std::vector<float> rgba((size_t)4 * width * height);
+  for (unsigned int y = 0; y < height; ++y)
+    for (unsigned int x = 0; x < width; ++x)
+    {
+      const unsigned int band = ((y * 16u) / height) & 3u;        // 16 horizontal bands, period 4
+      const unsigned int cell = (x * 64u) / width;                 // 64 columns
+      float v = 1.0f;                                              // bands 0 and 2: opaque bars
+      if (band == 1u) v = ((cell & 7u) >= 1u && (cell & 7u) <= 6u) ? 0.0f : 1.0f;    // slots
+      else if (band == 3u) v = 0.5f;                               // half transparent: the stochastic test at work
+      float* p = &rgba[4 * ((size_t)y * width + x)];
+      p[0] = v; p[1] = v; p[2] = v; p[3] = 1.0f;
+    }
+  setTexels2D(width, height, rgba.data());
 }

@@ -15,6 +15,16 @@ public:
   void setTexels(unsigned int width, unsigned int height, const float* rgba);
   void calculateSphericalCDF();
 
+  // Plain 2D pictures (the reference's hard-coded "albedo" and "cutout" Pictures, Application.cpp:679-690): texels only, no
+  // CDFs.  Row 0 of the texel array is v = 0, i.e. the BOTTOM row of an image file (DevIL's lower-left origin, Picture.cpp).
+  void setTexels2D(unsigned int width, unsigned int height, const float* rgba);
+  bool loadImage(std::string const& filename);         // .png, .pgm/.ppm, .hdr
+  void createAlbedoProcedural(unsigned int width, unsigned int height);   // two-tone checker with a per-tile gradient
+  void createCutoutProcedural(unsigned int width, unsigned int height);   // slots: opaque bars, holes, and a half-transparent band
+  // the texels behind a 16-byte header {width, height, 0, 0}: the layout of a material-texture handle (rtc_texture_create,
+  // oracle/rt_oracle.c tex2d_wrap); the address of the blob is a valid HOST handle for the CPU checker
+  std::vector<float> const& getHandleBlob();
+
   unsigned int getWidth() const { return m_width; }
   unsigned int getHeight() const { return m_height; }
   float getIntegral() const { return m_integral; }
@@ -25,5 +35,5 @@ public:
 private:
   unsigned int m_width = 0, m_height = 0;
   float m_integral = 1.0f;
-  std::vector<float> m_rgba, m_cdfU, m_cdfV;
+  std::vector<float> m_rgba, m_cdfU, m_cdfV, m_blob;
 };

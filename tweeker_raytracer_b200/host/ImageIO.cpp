@@ -1,7 +1,9 @@
 #include "ImageIO.h"
 
+#include <cctype>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -84,5 +86,135 @@ bool writePFM(std::string const& path, int width, int height, const float* rgba)
     std::fwrite(row.data(), sizeof(float), row.size(), f);
   }
   std::fclose(f);
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Readers
+// ------------------------------------------------------------------------------------------------------------------
+static bool readFile(std::string const& path, std::vector<unsigned char>& data)
+{
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) return false;
+  std::fseek(f, 0, SEEK_END);
+  const long n = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  if (n <= 0) { std::fclose(f); return false; }
+  data.resize((size_t)n);
+  const bool ok = std::fread(data.data(), 1, (size_t)n, f) == (size_t)n;
+  std::fclose(f);
+  return ok;
+}
+
+static unsigned int get32(const unsigned char* p) { return ((unsigned int)p[0] << 24) | ((unsigned int)p[1] << 16) | ((unsigned int)p[2] << 8) | p[3]; }
+
+static int paeth(int a, int b, int c)
+{
+  const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
+  return (pa <= pb && pa <= pc) ? a : ((pb <= pc) ? b : c);
+}
+
+bool readPNG(std::string const& path, int& width, int& height, std::vector<unsigned char>& rgba)
+{
+  std::vector<unsigned char> file;
+  if (!readFile(path, file) || file.size() < 8 + 25) return false;
+  const unsigned char sig[8] = { 0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n' };
+  if (std::memcmp(file.data(), sig, 8) != 0) return false;
+  unsigned int w = 0, h = 0; int depth = 0, colour = -1, interlace = 0;
+  std::vector<unsigned char> idat, palette, trns;
+  size_t pos = 8;
+  while (pos + 12 <= file.size())
+  {
+    const unsigned int n = get32(&file[pos]);
+    const char* type = reinterpret_cast<const char*>(&file[pos + 4]);
+    if (pos + 12 + (size_t)n > file.size()) return false;
+    const unsigned char* body = &file[pos + 8];
+    if (std::memcmp(type, "IHDR", 4) == 0 && n >= 13) { w = get32(body); h = get32(body + 4); depth = body[8]; colour = body[9]; interlace = body[12]; }
+    else if (std::memcmp(type, "PLTE", 4) == 0) palette.assign(body, body + n);
+    else if (std::memcmp(type, "tRNS", 4) == 0) trns.assign(body, body + n);
+    else if (std::memcmp(type, "IDAT", 4) == 0) idat.insert(idat.end(), body, body + n);
+    else if (std::memcmp(type, "IEND", 4) == 0) break;
+    pos += 12 + (size_t)n;
+  }
+  if (w == 0 || h == 0 || w > 65536 || h > 65536 || interlace != 0 || (depth != 8 && depth != 16)) return false;
+  int channels = 0;
+  switch (colour) { case 0: channels = 1; break; case 2: channels = 3; break; case 3: channels = 1; break; case 4: channels = 2; break; case 6: channels = 4; break; default: return false; }
+  if (colour == 3 && (depth != 8 || palette.empty())) return false;
+  const size_t bpp = (size_t)channels * (size_t)(depth / 8), stride = bpp * w;
+  std::vector<unsigned char> raw((stride + 1) * h);
+  uLongf rawSize = (uLongf)raw.size();
+  if (uncompress(raw.data(), &rawSize, idat.data(), (uLong)idat.size()) != Z_OK || rawSize != raw.size()) return false;
+  // undo the scanline filters in place
+  std::vector<unsigned char> prev(stride, 0), line(stride);
+  rgba.resize((size_t)4 * w * h);
+  for (unsigned int y = 0; y < h; ++y)
+  {
+    const unsigned char* src = &raw[(stride + 1) * y];
+    const int filter = src[0];
+    for (size_t i = 0; i < stride; ++i)
+    {
+      const int a = (i >= bpp) ? line[i - bpp] : 0, b = prev[i], c = (i >= bpp) ? prev[i - bpp] : 0;
+      int v = src[1 + i];
+      switch (filter) { case 0: break; case 1: v += a; break; case 2: v += b; break; case 3: v += (a + b) / 2; break; case 4: v += paeth(a, b, c); break; default: return false; }
+      line[i] = (unsigned char)v;
+    }
+    for (unsigned int x = 0; x < w; ++x)
+    {
+      const unsigned char* px = &line[bpp * x];
+      const size_t step = (size_t)(depth / 8);          // 16-bit samples: keep the high byte
+      unsigned char* dst = &rgba[4 * ((size_t)y * w + x)];
+      switch (colour)
+      {
+        case 0: dst[0] = dst[1] = dst[2] = px[0]; dst[3] = 255; break;
+        case 2: dst[0] = px[0]; dst[1] = px[step]; dst[2] = px[2 * step]; dst[3] = 255; break;
+        case 3:
+        {
+          const size_t idx = px[0];
+          if (3 * idx + 2 >= palette.size()) return false;
+          dst[0] = palette[3 * idx]; dst[1] = palette[3 * idx + 1]; dst[2] = palette[3 * idx + 2];
+          dst[3] = (idx < trns.size()) ? trns[idx] : 255;
+          break;
+        }
+        case 4: dst[0] = dst[1] = dst[2] = px[0]; dst[3] = px[step]; break;
+        case 6: dst[0] = px[0]; dst[1] = px[step]; dst[2] = px[2 * step]; dst[3] = px[3 * step]; break;
+      }
+    }
+    prev = line;
+  }
+  width = (int)w; height = (int)h;
+  return true;
+}
+
+// binary PGM (P5) / PPM (P6), maxval <= 255
+bool readPNM(std::string const& path, int& width, int& height, std::vector<unsigned char>& rgba)
+{
+  std::vector<unsigned char> file;
+  if (!readFile(path, file) || file.size() < 7 || file[0] != 'P' || (file[1] != '5' && file[1] != '6')) return false;
+  const int channels = (file[1] == '6') ? 3 : 1;
+  size_t pos = 2; int values[3] = { 0, 0, 0 };
+  for (int k = 0; k < 3; ++k)
+  {
+    for (;;)
+    {
+      while (pos < file.size() && std::isspace(file[pos])) ++pos;
+      if (pos < file.size() && file[pos] == '#') { while (pos < file.size() && file[pos] != '\n') ++pos; continue; }
+      break;
+    }
+    int v = 0; bool any = false;
+    while (pos < file.size() && std::isdigit(file[pos])) { v = v * 10 + (file[pos] - '0'); ++pos; any = true; }
+    if (!any) return false;
+    values[k] = v;
+  }
+  ++pos;   // the single whitespace after maxval
+  const int w = values[0], h = values[1], maxval = values[2];
+  if (w <= 0 || h <= 0 || maxval <= 0 || maxval > 255 || pos + (size_t)w * h * channels > file.size()) return false;
+  rgba.resize((size_t)4 * w * h);
+  for (size_t i = 0; i < (size_t)w * h; ++i)
+  {
+    const unsigned char* px = &file[pos + i * channels];
+    unsigned char* dst = &rgba[4 * i];
+    dst[0] = px[0]; dst[1] = px[channels == 3 ? 1 : 0]; dst[2] = px[channels == 3 ? 2 : 0]; dst[3] = 255;
+  }
+  width = w; height = h;
   return true;
 }

@@ -110,13 +110,35 @@ void rth_app_set_camera(void* h, float phi, float theta, float fov, float distan
 int rth_app_update_material(void* h, int index, int indexBSDF, const float albedo[3], const float roughness[2], const float absorptionColor[3],
                             float absorptionScale, float ior, int thinwalled)
 {
+  Application* app = static_cast<Application*>(h);
   MaterialGUI m;
+  if (0 <= index && (size_t)index < app->getMaterialsGUI().size())      // the texture check boxes keep their state
+  { m.useAlbedoTexture = app->getMaterialsGUI()[index].useAlbedoTexture; m.useCutoutTexture = app->getMaterialsGUI()[index].useCutoutTexture; }
   m.indexBSDF = static_cast<FunctionIndex>(indexBSDF);
   m.albedo = make_float3(albedo[0], albedo[1], albedo[2]);
   m.roughness = make_float2(roughness[0], roughness[1]);
   m.absorptionColor = make_float3(absorptionColor[0], absorptionColor[1], absorptionColor[2]);
   m.absorptionScale = absorptionScale; m.ior = ior; m.thinwalled = thinwalled != 0;
   try { return static_cast<Application*>(h)->updateMaterial(index, m) ? 0 : -1; } catch (std::exception const& e) { g_error = e.what(); return -2; }
+}
+
+// the GUI's "use albedo texture" / "use cutout texture" check boxes of one material (MaterialGUI.h:47-48)
+int rth_app_update_material_textures(void* h, int index, int useAlbedo, int useCutout)
+{
+  Application* app = static_cast<Application*>(h);
+  if (index < 0 || (size_t)index >= app->getMaterialsGUI().size()) return -1;
+  MaterialGUI m = app->getMaterialsGUI()[index];
+  m.useAlbedoTexture = useAlbedo != 0; m.useCutoutTexture = useCutout != 0;
+  try { return app->updateMaterial(index, m) ? 0 : -1; } catch (std::exception const& e) { g_error = e.what(); return -2; }
+}
+
+// the material pictures: name = "albedo" | "cutout"; texels = RGBA32F, row 0 = v 0
+int rth_app_picture(void* h, const char* name, unsigned int* w, unsigned int* hgt, const float** texels)
+{
+  EnvMap* p = static_cast<Application*>(h)->getPicture(name ? name : "");
+  if (!p || p->getWidth() == 0) return -1;
+  *w = p->getWidth(); *hgt = p->getHeight(); *texels = p->getTexels().data();
+  return 0;
 }
 
 int rth_app_update_light_emission(void* h, int index, const float emission[3])
