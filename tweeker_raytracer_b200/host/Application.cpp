@@ -738,8 +738,24 @@ bool Application::loadSceneDescription(std::string const& filename)
       }
       else if (token == "assimp")
       {
-        parser.getNextLine(token);
-        std::cerr << "WARNING: loadSceneDescription() model assimp " << token << " ignored: mesh import is not part of this build." << std::endl;
+        std::string filenameModel;
+        parser.getNextLine(filenameModel);
+        // relative model paths are tried as given and then next to the scene file
+        if (!filenameModel.empty() && filenameModel[0] != '/')
+        {
+          FILE* probe = std::fopen(filenameModel.c_str(), "rb");
+          if (probe) std::fclose(probe);
+          else
+          {
+            const size_t slash = filename.find_last_of("/\\");
+            if (slash != std::string::npos) filenameModel = filename.substr(0, slash + 1) + filenameModel;
+          }
+        }
+        std::shared_ptr<sg::Group> model = createASSIMP(filenameModel);
+        std::shared_ptr<sg::Instance> instance(new sg::Instance(m_idInstance++));
+        instance->setTransform(trafo);
+        instance->setChild(model);
+        m_scene->addChild(instance);
       }
       else std::cerr << "WARNING: loadSceneDescription() unknown model type " << token << std::endl;
     }

@@ -82,6 +82,9 @@ private:
   void appendInstance(std::shared_ptr<sg::Group>& group, std::shared_ptr<sg::Triangles> geometry, const float trafo[12],
                       std::string const& reference, unsigned int& idInstance);
   std::shared_ptr<sg::Triangles> cachedGeometry(std::string const& key, bool& created);
+  // `model assimp <file>` (Assimp.cpp:47-319): Wavefront OBJ through the built-in reader, see MeshImport.cpp
+  std::shared_ptr<sg::Group> createASSIMP(std::string const& filename);
+  static void calculateTangents(std::vector<TriangleAttributes>& attributes, std::vector<unsigned int> const& indices);
   void flatten(std::shared_ptr<sg::Node> node, const float matrix[12], int material, int light);
 
 private:
@@ -121,6 +124,7 @@ private:
   unsigned int m_idGroup = 0, m_idInstance = 0, m_idGeometry = 0;
   std::vector<std::shared_ptr<sg::Triangles>> m_geometries;
   std::map<std::string, unsigned int> m_mapGeometries;
+  std::map<std::string, std::shared_ptr<sg::Group>> m_mapGroups;    // imported models by file name
   std::vector<MaterialGUI> m_materialsGUI;
   std::map<std::string, int> m_mapMaterialReferences;
   std::vector<CameraDefinition> m_cameras;
