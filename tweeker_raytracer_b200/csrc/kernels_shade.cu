@@ -11,6 +11,9 @@
 // Path state lives in SoA arrays indexed by path id (WavefrontBuffers); queues hold path ids and are
 // compacted with warp ballots (one atomicAdd per warp).
 #include "shade.cuh"
+// the primary-ray extend kernel generates its rays with the shading arithmetic of this translation unit (see ExtendPrimary)
+#define RTC_STACK_OVERFLOW_COUNTER g_rtcStackOverflowsPrimary
+#include "trace.cuh"
 
 #include <cstdlib>
 
@@ -18,6 +21,7 @@ namespace {
 
 constexpr int kBlock = 256;
 constexpr uint32_t kNoPixel = 0xffffffffu;
+constexpr uint32_t kDeadPath = 0xfffffffeu;           // hitInst of a launch index that falls outside the image (fused primary path)
 // device counters of one batch: [0..63] extend counts per depth, [64..127] shadow counts, [128..191] extend cursors,
 // [192..255] connect cursors, [256 + 8 d + c] paths of shade class c at depth d
 constexpr uint32_t kNumCounters = 256 + 64 * 8;
@@ -115,6 +119,53 @@ k_generate(const __grid_constant__ WfArgs a, uint32_t* __restrict__ queue, uint3
   }
 }
 
+// ---- fused primary path: extend of the first segment without a generate pass ----------------------------------------------
+// Ray source of the depth-0 extend: the ray of path i is computed from its launch index at fetch time (start_path: TEA seed,
+// jitter, lens shader) instead of being written by k_generate and read back.  It lives in this translation unit because the
+// ray must carry the shading arithmetic's bits (-fmad=false); the intersector pins its own rounding with intrinsics and the
+// box test only has to be conservative, so the traversal is indifferent to the flag.
+struct ExtendPrimary
+{
+  WfArgs a;
+  uint32_t path;
+  __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d)
+  {
+    path = i;
+    const uint32_t pixelsPerIter = a.launchWidth * a.launchHeight;
+    const uint32_t it = i / pixelsPerIter, idx = i - it * pixelsPerIter;
+    uint32_t x, y;
+    launch_xy(idx, a.launchWidth, a.launchHeight, x, y);
+    uint32_t seed = 0, col = 0; float3 pos, wi;
+    if (!start_path(a.sys, a.launchWidth, x, y, a.iterFirst + (int)it, seed, pos, wi, col))
+    {
+      a.wf.hitInst[i] = kDeadPath;
+      return false;
+    }
+    o = make_float4(pos.x, pos.y, pos.z, a.sys.sceneEpsilon);
+    d = make_float4(wi.x, wi.y, wi.z, RT_DEFAULT_MAX);
+    return true;
+  }
+  template <class T> __device__ __forceinline__ void store(uint32_t, const T& tr) const
+  {
+    const TraceHit h = tr.result();
+    __stcs(a.wf.hit + path, make_float4(h.t, h.u, h.v, __uint_as_float(h.prim)));
+    __stcs(a.wf.hitInst + path, h.inst);
+  }
+};
+
+constexpr int kPrimaryBlock = 128;
+#ifndef RTC_TRACE_MIN_BLOCKS
+#define RTC_TRACE_MIN_BLOCKS 8
+#endif
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kPrimaryBlock, RTC_TRACE_MIN_BLOCKS)
+k_extend_primary(const SceneDesc sc, ExtendPrimary policy, uint32_t n, uint32_t* __restrict__ cursor, unsigned long long* __restrict__ counts)
+{
+  __shared__ uint2 smem[RTC_SM_STACK * kPrimaryBlock + (11 * kPrimaryBlock + 1) / 2];
+  trace_stream<false, COUNT, kPrimaryBlock, false>(sc, n, cursor, policy, smem, counts);
+}
+
 __device__ __forceinline__ float3 xf_vector(const float4 r0, const float4 r1, const float4 r2, float3 v)
 {
   return f3(r0.x * v.x + r0.y * v.y + r0.z * v.z, r1.x * v.x + r1.y * v.y + r1.z * v.z, r2.x * v.x + r2.y * v.y + r2.z * v.z);
@@ -131,11 +182,13 @@ __device__ __forceinline__ float3 ld3(const float* p) { return f3(__ldg(p), __ld
 enum : int { SHADE_MISS = 0, SHADE_BRDF_DIFFUSE = 1, SHADE_BRDF_SPECULAR = 2, SHADE_BSDF_SPECULAR = 3, SHADE_BRDF_GGX = 4, SHADE_BSDF_GGX = 5,
              SHADE_OTHER = 6, SHADE_NUM_CLASSES = 7 };
 
+// queueIn == nullptr (fused primary path): the queue is the identity over all a.numPaths paths, launch indices outside
+// the image carry hitInst == kDeadPath, and the number of live paths is added to *aliveCount (the depth-0 ray count).
 __global__ void __launch_bounds__(kBlock)
 k_bin(const __grid_constant__ WfArgs a, const SceneDesc sc, const uint32_t* __restrict__ queueIn, const uint32_t* __restrict__ countIn,
-      uint32_t* __restrict__ bins, uint32_t binStride, uint32_t* __restrict__ binCounts)
+      uint32_t* __restrict__ bins, uint32_t binStride, uint32_t* __restrict__ binCounts, uint32_t* __restrict__ aliveCount)
 {
-  const uint32_t n = *countIn;
+  const uint32_t n = queueIn ? *countIn : a.numPaths;
   const uint32_t stride = gridDim.x * blockDim.x;
   const rt_MaterialDefinition* materials = reinterpret_cast<const rt_MaterialDefinition*>(a.sys.materialDefinitions);
   for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride)
@@ -144,9 +197,10 @@ k_bin(const __grid_constant__ WfArgs a, const SceneDesc sc, const uint32_t* __re
     int cls = -1; uint32_t p = 0;
     if (i < n)
     {
-      p = queueIn[i];
+      p = queueIn ? queueIn[i] : i;
       const uint32_t inst = a.wf.hitInst[p];
       if (inst == 0xffffffffu) cls = SHADE_MISS;
+      else if (inst == kDeadPath) cls = -1;
       else
       {
         const int index = materials[sc.geomInst[inst].materialIndex].indexBSDF;
@@ -157,6 +211,11 @@ k_bin(const __grid_constant__ WfArgs a, const SceneDesc sc, const uint32_t* __re
 #pragma unroll
     for (int k = 0; k < SHADE_NUM_CLASSES; ++k) { q[k] = bins + (size_t)k * binStride; c[k] = binCounts + k; }
     block_append<SHADE_NUM_CLASSES>(cls, p, q, c);
+    if (!queueIn)
+    {
+      const int alive = __syncthreads_count(cls >= 0);
+      if (threadIdx.x == 0 && alive) atomicAdd(aliveCount, (uint32_t)alive);
+    }
   }
 }
 
@@ -182,7 +241,9 @@ template <int CLASS> SD float4 bsdf_eval_class(const rt_MaterialDefinition& m, c
 //              Russian roulette of a path that casts a shadow ray is left to k_cutout_shadow, because the shadow ray's
 //              any-hit programs draw from the path's seed BEFORE the integrator does (closesthit.cu:281 precedes
 //              raygeneration.cu:111).
-template <int CLASS, bool TEX>
+// PRIMARY = true (fused primary path, first segment only): there is no generate pass; the path's seed, ray and pixel are
+//              recomputed from the launch index instead of being read back, throughput is 1 and radiance 0.
+template <int CLASS, bool TEX, bool PRIMARY>
 __global__ void __launch_bounds__(kBlock)
 k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
         const uint32_t* __restrict__ queueIn, const uint32_t* __restrict__ countIn,
@@ -200,10 +261,28 @@ k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
     if (i < n)
     {
       p = queueIn[i];
-      const float4 ro = a.wf.rayOrg[p], rd = a.wf.rayDir[p];
-      const float4 tp = a.wf.throughput[p];
-      float4 Lf = a.wf.radiance[p];
-      uint4 misc = a.wf.misc[p];
+      float4 ro, rd, tp, Lf; uint4 misc;
+      if (PRIMARY)
+      {
+        const uint32_t pixelsPerIter = a.launchWidth * a.launchHeight;
+        const uint32_t it = p / pixelsPerIter, idx = p - it * pixelsPerIter;
+        uint32_t x, y;
+        launch_xy(idx, a.launchWidth, a.launchHeight, x, y);
+        uint32_t seed = 0, col = 0; float3 pos, wi;
+        start_path(sys, a.launchWidth, x, y, a.iterFirst + (int)it, seed, pos, wi, col);     // alive: k_bin dropped the others
+        ro = make_float4(pos.x, pos.y, pos.z, sys.sceneEpsilon);
+        rd = make_float4(wi.x, wi.y, wi.z, RT_DEFAULT_MAX);
+        tp = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+        Lf = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
+        misc = make_uint4(seed, 0u, (uint32_t)RT_MATERIAL_STACK_EMPTY, col);
+      }
+      else
+      {
+        ro = a.wf.rayOrg[p]; rd = a.wf.rayDir[p];
+        tp = a.wf.throughput[p];
+        Lf = a.wf.radiance[p];
+        misc = a.wf.misc[p];
+      }
       const float4 hit = a.wf.hit[p];
       const uint32_t hitInst = a.wf.hitInst[p];
 
@@ -523,10 +602,14 @@ k_accumulate(const __grid_constant__ WfArgs a)
   const uint32_t pixelsPerIter = a.launchWidth * a.launchHeight;
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= pixelsPerIter) return;
-  const uint32_t col = a.wf.misc[idx].w;
-  if (col == kNoPixel) return;
   uint32_t x, y;
   launch_xy(idx, a.launchWidth, a.launchHeight, x, y);
+  uint32_t col = x;      // raygeneration.cu:178-186: the pixel column of this launch index, nothing to do outside the image
+  if (a.sys.distribution && 1 < a.sys.deviceCount)
+  {
+    col = distribute(a.sys, x, y);
+    if ((uint32_t)a.sys.resolution.x <= col) return;
+  }
   float4* buffer; size_t index;
   if (a.raygen == RTC_RAYGEN_LOCAL_COPY) { buffer = reinterpret_cast<float4*>(a.sys.texelBuffer); index = (size_t)y * a.launchWidth + x; }
   else { buffer = reinterpret_cast<float4*>(a.sys.outputBuffer); index = (size_t)y * (size_t)a.sys.resolution.x + col; }
@@ -681,22 +764,23 @@ namespace {
 
 template <int CLASS>
 void launch_shade_class(rtc_context* ctx, int grid, const WfArgs& a, const SceneDesc& sc, uint32_t* bins, uint32_t binStride, uint32_t* binCounts,
-                        uint32_t* qOut, uint32_t* countOut, uint32_t* shadowQueue, uint32_t* shadowCount, bool tex, bool deferRR)
+                        uint32_t* qOut, uint32_t* countOut, uint32_t* shadowQueue, uint32_t* shadowCount, bool tex, bool deferRR, bool primary)
 {
-  if (tex) k_shade<CLASS, true><<<grid, kBlock, 0, ctx->stream>>>(a, sc, bins + (size_t)CLASS * binStride, binCounts + CLASS, qOut, countOut, shadowQueue, shadowCount, deferRR ? 1 : 0);
-  else     k_shade<CLASS, false><<<grid, kBlock, 0, ctx->stream>>>(a, sc, bins + (size_t)CLASS * binStride, binCounts + CLASS, qOut, countOut, shadowQueue, shadowCount, 0);
+  if (tex)          k_shade<CLASS, true, false><<<grid, kBlock, 0, ctx->stream>>>(a, sc, bins + (size_t)CLASS * binStride, binCounts + CLASS, qOut, countOut, shadowQueue, shadowCount, deferRR ? 1 : 0);
+  else if (primary) k_shade<CLASS, false, true><<<grid, kBlock, 0, ctx->stream>>>(a, sc, bins + (size_t)CLASS * binStride, binCounts + CLASS, qOut, countOut, shadowQueue, shadowCount, 0);
+  else              k_shade<CLASS, false, false><<<grid, kBlock, 0, ctx->stream>>>(a, sc, bins + (size_t)CLASS * binStride, binCounts + CLASS, qOut, countOut, shadowQueue, shadowCount, 0);
 }
 
 void launch_shade_classes(rtc_context* ctx, int grid, const WfArgs& a, const SceneDesc& sc, uint32_t* bins, uint32_t binStride, uint32_t* binCounts,
-                          uint32_t* qOut, uint32_t* countOut, uint32_t* shadowQueue, uint32_t* shadowCount, bool tex, bool deferRR)
+                          uint32_t* qOut, uint32_t* countOut, uint32_t* shadowQueue, uint32_t* shadowCount, bool tex, bool deferRR, bool primary)
 {
-  launch_shade_class<SHADE_MISS>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR);
-  launch_shade_class<SHADE_BRDF_DIFFUSE>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR);
-  launch_shade_class<SHADE_BRDF_SPECULAR>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR);
-  launch_shade_class<SHADE_BSDF_SPECULAR>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR);
-  launch_shade_class<SHADE_BRDF_GGX>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR);
-  launch_shade_class<SHADE_BSDF_GGX>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR);
-  launch_shade_class<SHADE_OTHER>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR);
+  launch_shade_class<SHADE_MISS>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
+  launch_shade_class<SHADE_BRDF_DIFFUSE>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
+  launch_shade_class<SHADE_BRDF_SPECULAR>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
+  launch_shade_class<SHADE_BSDF_SPECULAR>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
+  launch_shade_class<SHADE_BRDF_GGX>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
+  launch_shade_class<SHADE_BSDF_GGX>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
+  launch_shade_class<SHADE_OTHER>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
 }
 
 // scratch of the ordered any-hit processing: two queues of `capacity` path ids + {count 0, count 1, cursor, pad}
@@ -800,19 +884,37 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
     a.iterFirst = iterFirst + done; a.iterCount = batch; a.accumFirst = accumFirst + done; a.numPaths = (uint32_t)(pixels * (uint64_t)batch);
     uint32_t* cnt = ctx->wf.counters;
     RTC_CUDA(cudaMemsetAsync(cnt, 0, 4 * kNumCounters, ctx->stream));
-    if (int rc = profile_begin(ctx, RTC_KERNEL_GENERATE)) return rc;
-    k_generate<<<gridShade, kBlock, 0, ctx->stream>>>(a, ctx->wf.queueA, cnt + 0);
-    ctx->kernelLaunches++;
-    if (int rc = profile_end(ctx)) return rc;
+    // Fused primary path (scenes without material textures): no generate pass.  The depth-0 extend computes its rays from the
+    // launch index, and the depth-0 shade kernels recompute the path start instead of reading five state arrays back.
+    const bool fused = !tex;
+    if (!fused)
+    {
+      if (int rc = profile_begin(ctx, RTC_KERNEL_GENERATE)) return rc;
+      k_generate<<<gridShade, kBlock, 0, ctx->stream>>>(a, ctx->wf.queueA, cnt + 0);
+      ctx->kernelLaunches++;
+      if (int rc = profile_end(ctx)) return rc;
+    }
     uint32_t* qIn = ctx->wf.queueA; uint32_t* qOut = ctx->wf.queueB;
     for (int d = 0; d < maxDepth; ++d)
     {
-      if (int rc = launch_extend(ctx, &scene->desc, ctx->wf, qIn, cnt + d, cnt + 128 + d, countWork)) return rc;
+      const bool primary = fused && d == 0;
+      if (primary)
+      {
+        if (int rc = profile_begin(ctx, RTC_KERNEL_EXTEND)) return rc;
+        ExtendPrimary policy = { a, 0u };
+        const int gridTrace = ctx->numSMs * RTC_TRACE_MIN_BLOCKS;
+        if (countWork) k_extend_primary<true><<<gridTrace, kPrimaryBlock, 0, ctx->stream>>>(scene->desc, policy, a.numPaths, cnt + 128, ctx->d_launchCounts);
+        else           k_extend_primary<false><<<gridTrace, kPrimaryBlock, 0, ctx->stream>>>(scene->desc, policy, a.numPaths, cnt + 128, nullptr);
+        ctx->kernelLaunches++;
+        RTC_CUDA(cudaGetLastError());
+        if (int rc = profile_end(ctx)) return rc;
+      }
+      else if (int rc = launch_extend(ctx, &scene->desc, ctx->wf, qIn, cnt + d, cnt + 128 + d, countWork)) return rc;
       if (cutout) { if (int rc = resolve_radiance_candidates(ctx, scene, a, gridShade, qIn, cnt + d)) return rc; }
       if (int rc = profile_begin(ctx, RTC_KERNEL_SHADE)) return rc;
       uint32_t* binCounts = cnt + 256 + d * 8;
-      k_bin<<<gridShade, kBlock, 0, ctx->stream>>>(a, scene->desc, qIn, cnt + d, ctx->wf.bins, ctx->wf.binStride, binCounts);
-      launch_shade_classes(ctx, gridShade, a, scene->desc, ctx->wf.bins, ctx->wf.binStride, binCounts, qOut, cnt + d + 1, ctx->wf.shadowQueue, cnt + 64 + d, tex, cutout);
+      k_bin<<<gridShade, kBlock, 0, ctx->stream>>>(a, scene->desc, primary ? nullptr : qIn, cnt + d, ctx->wf.bins, ctx->wf.binStride, binCounts, cnt + d);
+      launch_shade_classes(ctx, gridShade, a, scene->desc, ctx->wf.bins, ctx->wf.binStride, binCounts, qOut, cnt + d + 1, ctx->wf.shadowQueue, cnt + 64 + d, tex, cutout, primary);
       ctx->kernelLaunches += 1 + SHADE_NUM_CLASSES;
       if (int rc = profile_end(ctx)) return rc;
       if (sys.numLights > 0)
@@ -829,6 +931,15 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
     ctx->kernelLaunches += 2;
     RTC_CUDA(cudaGetLastError());
   }
+  return 0;
+}
+
+int read_stack_overflows_primary(rtc_context* ctx, uint64_t* out)
+{
+  unsigned int v = 0;
+  RTC_CUDA(cudaMemcpyFromSymbolAsync(&v, g_rtcStackOverflowsPrimary, sizeof(v), 0, cudaMemcpyDeviceToHost, ctx->stream));
+  RTC_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = v;
   return 0;
 }
 

@@ -242,6 +242,8 @@ int read_stack_overflows(rtc_context* ctx, uint64_t* out)
   unsigned int v = 0;
   RTC_CUDA(cudaMemcpyFromSymbolAsync(&v, g_rtcStackOverflows, sizeof(v), 0, cudaMemcpyDeviceToHost, ctx->stream));
   RTC_CUDA(cudaStreamSynchronize(ctx->stream));
-  *out = v;
+  uint64_t primary = 0;
+  if (int rc = read_stack_overflows_primary(ctx, &primary)) return rc;
+  *out = (uint64_t)v + primary;
   return 0;
 }

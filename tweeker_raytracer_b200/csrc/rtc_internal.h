@@ -179,3 +179,4 @@ int launch_composite(rtc_context* ctx, const rt_CompositorData& args);
 int launch_tonemap(rtc_context* ctx, const rt_TonemapperParams& p, const float4* rgba, uint8_t* rgb, uint64_t n);
 int ensure_wavefront(rtc_context* ctx, uint64_t capacity);
 int read_stack_overflows(rtc_context* ctx, uint64_t* out);
+int read_stack_overflows_primary(rtc_context* ctx, uint64_t* out);   // the counter of the primary-ray extend kernel (kernels_shade.cu)

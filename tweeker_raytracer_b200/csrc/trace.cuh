@@ -55,16 +55,25 @@ __device__ __forceinline__ void shear_setup(ObjRay& r)
 }
 
 // Woop/Benthin/Wald watertight test; see the oracle for the definition this mirrors operation by operation.
+// The six component selections share their predicates (kx/ky/kz are per-ray constants): FSEL on three predicate pairs
+// instead of a SETP pair in front of every select.
+__device__ __forceinline__ float pick3(float x, float y, float z, bool is1, bool is2)
+{
+  float r = is1 ? y : x;
+  return is2 ? z : r;
+}
+
 __device__ __forceinline__ bool tri_test(const ObjRay& r, float ox, float oy, float oz, const float4 v0, const float4 v1, const float4 v2,
                                          float& t, float& det, float& V, float& W)
 {
   const float A0 = __fsub_rn(v0.x, ox), A1 = __fsub_rn(v0.y, oy), A2 = __fsub_rn(v0.z, oz);
   const float B0 = __fsub_rn(v1.x, ox), B1 = __fsub_rn(v1.y, oy), B2 = __fsub_rn(v1.z, oz);
   const float C0 = __fsub_rn(v2.x, ox), C1 = __fsub_rn(v2.y, oy), C2 = __fsub_rn(v2.z, oz);
-  const float Akz = sel3(A0, A1, A2, r.kz), Bkz = sel3(B0, B1, B2, r.kz), Ckz = sel3(C0, C1, C2, r.kz);
-  const float Ax = __fmaf_rn(-r.Sx, Akz, sel3(A0, A1, A2, r.kx)), Ay = __fmaf_rn(-r.Sy, Akz, sel3(A0, A1, A2, r.ky));
-  const float Bx = __fmaf_rn(-r.Sx, Bkz, sel3(B0, B1, B2, r.kx)), By = __fmaf_rn(-r.Sy, Bkz, sel3(B0, B1, B2, r.ky));
-  const float Cx = __fmaf_rn(-r.Sx, Ckz, sel3(C0, C1, C2, r.kx)), Cy = __fmaf_rn(-r.Sy, Ckz, sel3(C0, C1, C2, r.ky));
+  const bool x1 = r.kx == 1, x2 = r.kx == 2, y1 = r.ky == 1, y2 = r.ky == 2, z1 = r.kz == 1, z2 = r.kz == 2;
+  const float Akz = pick3(A0, A1, A2, z1, z2), Bkz = pick3(B0, B1, B2, z1, z2), Ckz = pick3(C0, C1, C2, z1, z2);
+  const float Ax = __fmaf_rn(-r.Sx, Akz, pick3(A0, A1, A2, x1, x2)), Ay = __fmaf_rn(-r.Sy, Akz, pick3(A0, A1, A2, y1, y2));
+  const float Bx = __fmaf_rn(-r.Sx, Bkz, pick3(B0, B1, B2, x1, x2)), By = __fmaf_rn(-r.Sy, Bkz, pick3(B0, B1, B2, y1, y2));
+  const float Cx = __fmaf_rn(-r.Sx, Ckz, pick3(C0, C1, C2, x1, x2)), Cy = __fmaf_rn(-r.Sy, Ckz, pick3(C0, C1, C2, y1, y2));
   float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
   V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
   W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
@@ -174,7 +183,11 @@ struct TraceCounts { uint32_t nodes, tris, insts; };
 
 // Rays whose traversal stack ran out of its 40 entries (the dropped subtree may hide a hit).  Never non-zero for the 8-wide
 // trees this library builds; exported through rtc_stats so that a violation is loud instead of a silently wrong image.
-__device__ unsigned int g_rtcStackOverflows = 0;
+// (one counter per translation unit that instantiates the traversal: kernels_trace.cu and kernels_shade.cu)
+#ifndef RTC_STACK_OVERFLOW_COUNTER
+#define RTC_STACK_OVERFLOW_COUNTER g_rtcStackOverflows
+#endif
+__device__ unsigned int RTC_STACK_OVERFLOW_COUNTER = 0;
 
 // One ray's traversal as a resumable state machine: begin() once, then step() until it returns false.
 // A step visits one wide node (or pops a postponed leaf group) and tests the triangles / enters the instance it yields.
@@ -209,7 +222,7 @@ struct Traversal
   {
     if (sp < RTC_SM_STACK) smStack[sp * BLOCK] = v;
     else if (sp < RTC_SM_STACK + RTC_LM_STACK) lmStack[sp - RTC_SM_STACK] = v;
-    else { atomicAdd(&g_rtcStackOverflows, 1u); return; }
+    else { atomicAdd(&RTC_STACK_OVERFLOW_COUNTER, 1u); return; }
     ++sp;
   }
   __device__ __forceinline__ uint2 pop()
