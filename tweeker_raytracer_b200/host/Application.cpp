@@ -320,6 +320,8 @@ void Application::benchmark()
     std::ostringstream stream;
     stream.precision(3);
     stream << std::fixed << iterationIndex << " / " << m_benchmarkSeconds << " = " << fps << " fps";
+    if (1 < m_raytracer->getWorld())   // one process per GPU: this rank's share of the samples
+      stream << " (rank " << m_raytracer->getRank() << " of " << m_raytracer->getWorld() << ": " << iterationIndex * (unsigned int)m_raytracer->getWorld() << " spp in the combined frame)";
     std::cout << stream.str() << std::endl;
     screenshot(true);
   }
