@@ -58,31 +58,60 @@ __device__ __forceinline__ void launch_xy(uint32_t idx, uint32_t w, uint32_t h, 
 }
 
 // Queue append aggregated over the whole CTA: every thread offers (class, value), class < 0 meaning nothing.  Lanes of a
-// warp with the same class are found with one match.any, each warp reserves its run in a shared counter, ONE thread per
-// class reserves the CTA's run in the global counter, then every thread writes its slot.  A 256-thread CTA therefore
-// issues at most NCLS global atomics per 256 paths instead of one per warp and class, which matters because all of them
-// hit the same few addresses.  Must be called by all threads of the CTA (it synchronises).
+// warp with the same class are found with one ballot per class (NCLS is small; match.any is several times slower), each
+// warp reserves its run in a shared counter, ONE thread per class reserves the CTA's run in the global counter, then every
+// thread writes its slot.  A 256-thread CTA therefore issues at most NCLS global atomics per 256 paths instead of one per
+// warp and class, which matters because all of them hit the same few addresses.  Class k appends to queue0 + k * stride
+// and counter0 + k.  Must be called by all threads of the CTA (three barriers; consecutive calls need no fourth: the
+// shared words are rewritten only behind the next call's barriers).
 template <int NCLS>
-__device__ __forceinline__ void block_append(int cls, uint32_t value, uint32_t* __restrict__ const* queues, uint32_t* __restrict__ const* counters)
+__device__ __forceinline__ void block_append(int cls, uint32_t value, uint32_t* __restrict__ queue0, uint32_t stride, uint32_t* __restrict__ counter0)
 {
   __shared__ uint32_t sCount[NCLS], sBase[NCLS];
   if (threadIdx.x < NCLS) sCount[threadIdx.x] = 0u;
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t peers = __match_any_sync(0xffffffffu, cls);
-  uint32_t offset = 0;
-  if (cls >= 0)
+  uint32_t peers = 0u;
+#pragma unroll
+  for (int k = 0; k < NCLS; ++k)
   {
-    const uint32_t leader = (uint32_t)__ffs((int)peers) - 1u;
-    if (lane == leader) offset = atomicAdd(&sCount[cls], (uint32_t)__popc(peers));
+    const uint32_t m = __ballot_sync(0xffffffffu, cls == k);
+    if (cls == k) peers = m;
   }
+  uint32_t offset = 0;
+  const uint32_t leader = peers ? (uint32_t)__ffs((int)peers) - 1u : lane;
+  if (peers && lane == leader) offset = atomicAdd(&sCount[cls], (uint32_t)__popc(peers));
   // peers of the same class share their leader's reservation
-  offset = __shfl_sync(0xffffffffu, offset, (cls >= 0) ? (uint32_t)__ffs((int)peers) - 1u : lane) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+  offset = __shfl_sync(0xffffffffu, offset, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
   __syncthreads();
-  if (threadIdx.x < NCLS && sCount[threadIdx.x]) sBase[threadIdx.x] = atomicAdd(counters[threadIdx.x], sCount[threadIdx.x]);
+  if (threadIdx.x < NCLS && sCount[threadIdx.x]) sBase[threadIdx.x] = atomicAdd(counter0 + threadIdx.x, sCount[threadIdx.x]);
   __syncthreads();
-  if (cls >= 0) queues[cls][sBase[cls] + offset] = value;
+  if (peers) queue0[(size_t)cls * stride + sBase[cls] + offset] = value;
+}
+
+// Two independent appends (a path may enter both queues) behind ONE set of barriers.
+__device__ __forceinline__ void block_append2(bool inA, uint32_t* __restrict__ queueA, uint32_t* __restrict__ counterA,
+                                              bool inB, uint32_t* __restrict__ queueB, uint32_t* __restrict__ counterB, uint32_t value)
+{
+  __shared__ uint32_t sCount[2], sBase[2];
+  if (threadIdx.x < 2) sCount[threadIdx.x] = 0u;
   __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+  const uint32_t mA = __ballot_sync(0xffffffffu, inA), mB = __ballot_sync(0xffffffffu, inB);
+  uint32_t offA = 0, offB = 0;
+  if (lane == 0)
+  {
+    if (mA) offA = atomicAdd(&sCount[0], (uint32_t)__popc(mA));
+    if (mB) offB = atomicAdd(&sCount[1], (uint32_t)__popc(mB));
+  }
+  offA = __shfl_sync(0xffffffffu, offA, 0) + (uint32_t)__popc(mA & below);
+  offB = __shfl_sync(0xffffffffu, offB, 0) + (uint32_t)__popc(mB & below);
+  __syncthreads();
+  if (threadIdx.x == 0 && sCount[0]) sBase[0] = atomicAdd(counterA, sCount[0]);
+  if (threadIdx.x == 1 && sCount[1]) sBase[1] = atomicAdd(counterB, sCount[1]);
+  __syncthreads();
+  if (inA) queueA[sBase[0] + offA] = value;
+  if (inB) queueB[sBase[1] + offB] = value;
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -115,7 +144,7 @@ k_generate(const __grid_constant__ WfArgs a, uint32_t* __restrict__ queue, uint3
         a.wf.misc[p] = make_uint4(0u, 0u, 0u, kNoPixel);
       }
     }
-    { uint32_t* const q[1] = { queue }; uint32_t* const c[1] = { count }; block_append<1>(alive ? 0 : -1, p, q, c); }
+    block_append<1>(alive ? 0 : -1, p, queue, 0u, count);
   }
 }
 
@@ -207,10 +236,7 @@ k_bin(const __grid_constant__ WfArgs a, const SceneDesc sc, const uint32_t* __re
         cls = (0 <= index && index < RT_NUM_BSDF_INDICES) ? 1 + index : SHADE_OTHER;
       }
     }
-    uint32_t* q[SHADE_NUM_CLASSES]; uint32_t* c[SHADE_NUM_CLASSES];
-#pragma unroll
-    for (int k = 0; k < SHADE_NUM_CLASSES; ++k) { q[k] = bins + (size_t)k * binStride; c[k] = binCounts + k; }
-    block_append<SHADE_NUM_CLASSES>(cls, p, q, c);
+    block_append<SHADE_NUM_CLASSES>(cls, p, bins, binStride, binCounts);
     if (!queueIn)
     {
       const int alive = __syncthreads_count(cls >= 0);
@@ -485,8 +511,7 @@ k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
       }
     }
     // a path whose roulette is pending is appended to the next queue by k_cutout_shadow once its shadow ray is resolved
-    { uint32_t* const q[1] = { queueOut }; uint32_t* const c[1] = { countOut }; block_append<1>((continues && !pendingRR) ? 0 : -1, p, q, c); }
-    { uint32_t* const q[1] = { shadowQueue }; uint32_t* const c[1] = { shadowCount }; block_append<1>(shadow ? 0 : -1, p, q, c); }
+    block_append2(continues && !pendingRR, queueOut, countOut, shadow, shadowQueue, shadowCount, p);
   }
 }
 
@@ -538,7 +563,7 @@ k_cutout_radiance(const __grid_constant__ WfArgs a, const SceneDesc sc, const ui
         a.wf.misc[p].x = seed;
       }
     }
-    { uint32_t* const q[1] = { queueOut }; uint32_t* const c[1] = { countOut }; block_append<1>(again ? 0 : -1, p, q, c); }
+    block_append<1>(again ? 0 : -1, p, queueOut, 0u, countOut);
   }
 }
 
@@ -590,8 +615,7 @@ k_cutout_shadow(const __grid_constant__ WfArgs a, const SceneDesc sc, const uint
       }
       if (misc.x != seedIn || misc.y != flagsIn) a.wf.misc[p] = misc;
     }
-    { uint32_t* const q[1] = { queueOut }; uint32_t* const c[1] = { countOut }; block_append<1>(again ? 0 : -1, p, q, c); }
-    { uint32_t* const q[1] = { queueNext }; uint32_t* const c[1] = { countNext }; block_append<1>(survives ? 0 : -1, p, q, c); }
+    block_append2(again, queueOut, countOut, survives, queueNext, countNext, p);
   }
 }
 
