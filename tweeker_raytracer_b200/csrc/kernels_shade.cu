@@ -89,6 +89,50 @@ __device__ __forceinline__ void block_append(int cls, uint32_t value, uint32_t* 
   if (peers) queue0[(size_t)cls * stride + sBase[cls] + offset] = value;
 }
 
+// The two appends of the shade kernels behind ONE set of barriers: queue A (paths that continue) and queue B (shadow rays);
+// a path may enter both.  Within the CTA's run of each queue the entries are grouped by the direction octant of their ray
+// (octA / octB in 0..7): the persistent traversal warps take consecutive queue entries, so a refill mostly brings rays that
+// descend the BVH in the same child order.
+__device__ __forceinline__ void block_append2_sorted(bool inA, uint32_t octA, uint32_t* __restrict__ queueA, uint32_t* __restrict__ counterA,
+                                                     bool inB, uint32_t octB, uint32_t* __restrict__ queueB, uint32_t* __restrict__ counterB, uint32_t value)
+{
+  __shared__ uint32_t sCount[16], sBase[16];
+  if (threadIdx.x < 16) sCount[threadIdx.x] = 0u;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+  uint32_t peersA = 0u, peersB = 0u;
+#pragma unroll
+  for (uint32_t k = 0; k < 8u; ++k)
+  {
+    const uint32_t mA = __ballot_sync(0xffffffffu, inA && octA == k), mB = __ballot_sync(0xffffffffu, inB && octB == k);
+    if (inA && octA == k) peersA = mA;
+    if (inB && octB == k) peersB = mB;
+  }
+  uint32_t offA = 0, offB = 0;
+  const uint32_t leaderA = peersA ? (uint32_t)__ffs((int)peersA) - 1u : lane, leaderB = peersB ? (uint32_t)__ffs((int)peersB) - 1u : lane;
+  if (peersA && lane == leaderA) offA = atomicAdd(&sCount[octA], (uint32_t)__popc(peersA));
+  if (peersB && lane == leaderB) offB = atomicAdd(&sCount[8u + octB], (uint32_t)__popc(peersB));
+  offA = __shfl_sync(0xffffffffu, offA, leaderA) + (uint32_t)__popc(peersA & below);
+  offB = __shfl_sync(0xffffffffu, offB, leaderB) + (uint32_t)__popc(peersB & below);
+  __syncthreads();
+  if (threadIdx.x < 2)     // thread 0: queue A, thread 1: queue B -- one global reservation for the eight octant runs
+  {
+    const uint32_t first = 8u * threadIdx.x;
+    uint32_t total = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 8u; ++k) total += sCount[first + k];
+    if (total)
+    {
+      uint32_t base = atomicAdd(threadIdx.x ? counterB : counterA, total);
+#pragma unroll
+      for (uint32_t k = 0; k < 8u; ++k) { sBase[first + k] = base; base += sCount[first + k]; }
+    }
+  }
+  __syncthreads();
+  if (inA) queueA[sBase[octA] + offA] = value;
+  if (inB) queueB[sBase[8u + octB] + offB] = value;
+}
+
 // Two independent appends (a path may enter both queues) behind ONE set of barriers.
 __device__ __forceinline__ void block_append2(bool inA, uint32_t* __restrict__ queueA, uint32_t* __restrict__ counterA,
                                               bool inB, uint32_t* __restrict__ queueB, uint32_t* __restrict__ counterB, uint32_t value)
@@ -283,7 +327,7 @@ k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
   {
     const uint32_t i = base + threadIdx.x;
     bool continues = false, shadow = false, pendingRR = false;
-    uint32_t p = 0;
+    uint32_t p = 0, octContinue = 0, octShadow = 0;
     if (i < n)
     {
       p = queueIn[i];
@@ -448,6 +492,7 @@ k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
                 a.wf.shadowOrg[p] = make_float4(prd.pos.x, prd.pos.y, prd.pos.z, sys.sceneEpsilon);
                 a.wf.shadowDir[p] = make_float4(ls.direction.x, ls.direction.y, ls.direction.z, ls.distance - sys.sceneEpsilon);
                 a.wf.shadowContrib[p] = make_float4(tc.x, tc.y, tc.z, 0.0f);
+                octShadow = ((ls.direction.x < 0.0f) ? 4u : 0u) | ((ls.direction.y < 0.0f) ? 2u : 0u) | ((ls.direction.z < 0.0f) ? 1u : 0u);
                 shadow = true;
               }
             }
@@ -499,6 +544,7 @@ k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
       {
         a.wf.rayOrg[p] = make_float4(prd.pos.x, prd.pos.y, prd.pos.z, sys.sceneEpsilon);
         a.wf.rayDir[p] = make_float4(prd.wi.x, prd.wi.y, prd.wi.z, RT_DEFAULT_MAX);
+        octContinue = ((prd.wi.x < 0.0f) ? 4u : 0u) | ((prd.wi.y < 0.0f) ? 2u : 0u) | ((prd.wi.z < 0.0f) ? 1u : 0u);
         a.wf.throughput[p] = make_float4(throughput.x, throughput.y, throughput.z, prd.pdf);
         misc.x = prd.seed; misc.y = (uint32_t)depth | (pendingRR ? kPendingRR : 0u); misc.z = (uint32_t)stackIdx;
         a.wf.misc[p] = misc;
@@ -511,7 +557,7 @@ k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
       }
     }
     // a path whose roulette is pending is appended to the next queue by k_cutout_shadow once its shadow ray is resolved
-    block_append2(continues && !pendingRR, queueOut, countOut, shadow, shadowQueue, shadowCount, p);
+    block_append2_sorted(continues && !pendingRR, octContinue, queueOut, countOut, shadow, octShadow, shadowQueue, shadowCount, p);
   }
 }
 
