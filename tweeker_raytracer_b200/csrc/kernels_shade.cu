@@ -395,15 +395,19 @@ k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
         const uint32_t prim = __float_as_uint(hit.w);
         const uint32_t* ix = reinterpret_cast<const uint32_t*>(gi.indices) + 3u * (size_t)prim;
         const uint32_t i0 = __ldg(ix), i1 = __ldg(ix + 1), i2 = __ldg(ix + 2);
-        const float* A0 = reinterpret_cast<const float*>(gi.attributes) + 12u * (size_t)i0;
-        const float* A1 = reinterpret_cast<const float*>(gi.attributes) + 12u * (size_t)i1;
-        const float* A2 = reinterpret_cast<const float*>(gi.attributes) + 12u * (size_t)i2;
+        // TriangleAttributes = 48 bytes = three 16-byte loads per vertex: vertex.xyz|tangent.x, tangent.yz|normal.xy, normal.z|texcoord.xyz
+        const float4* V0 = reinterpret_cast<const float4*>(gi.attributes) + 3u * (size_t)i0;
+        const float4* V1 = reinterpret_cast<const float4*>(gi.attributes) + 3u * (size_t)i1;
+        const float4* V2 = reinterpret_cast<const float4*>(gi.attributes) + 3u * (size_t)i2;
+        const float4 a00 = __ldg(V0), a01 = __ldg(V0 + 1), a02 = __ldg(V0 + 2);
+        const float4 a10 = __ldg(V1), a11 = __ldg(V1 + 1), a12 = __ldg(V1 + 2);
+        const float4 a20 = __ldg(V2), a21 = __ldg(V2 + 1), a22 = __ldg(V2 + 2);
         const float bx = hit.y, by = hit.z;
         const float alpha = 1.0f - bx - by;
-        const float3 p0 = ld3(A0), p1 = ld3(A1), p2 = ld3(A2);
+        const float3 p0 = f3(a00.x, a00.y, a00.z), p1 = f3(a10.x, a10.y, a10.z), p2 = f3(a20.x, a20.y, a20.z);
         const float3 ng = cross(p1 - p0, p2 - p0);
-        const float3 tg = ld3(A0 + 3) * alpha + ld3(A1 + 3) * bx + ld3(A2 + 3) * by;
-        const float3 ns = ld3(A0 + 6) * alpha + ld3(A1 + 6) * bx + ld3(A2 + 6) * by;
+        const float3 tg = f3(a00.w, a01.x, a01.y) * alpha + f3(a10.w, a11.x, a11.y) * bx + f3(a20.w, a21.x, a21.y) * by;
+        const float3 ns = f3(a01.z, a01.w, a02.x) * alpha + f3(a11.z, a11.w, a12.x) * bx + f3(a21.z, a21.w, a22.x) * by;
 
         const float4* o2w = sc.objectToWorld + (size_t)hitInst * 3u;
         const float4* w2o = sc.instances + (size_t)hitInst * 4u;
@@ -450,7 +454,7 @@ k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
           state.albedo = f3(material.albedo);
           if (TEX && material.textureAlbedo != 0)
           {
-            const float3 texcoord = ld3(A0 + 9) * alpha + ld3(A1 + 9) * bx + ld3(A2 + 9) * by;
+            const float3 texcoord = f3(a02.y, a02.z, a02.w) * alpha + f3(a12.y, a12.z, a12.w) * bx + f3(a22.y, a22.z, a22.w) * by;
             state.albedo = state.albedo * tex2d_wrap(material.textureAlbedo, texcoord.x, texcoord.y);
           }
           prd.flags = (prd.flags & ~RT_FLAG_DIFFUSE) | RT_FLAG_HIT | material.flags;
