@@ -1,0 +1,52 @@
+"""GPU parity, part 8: launch shapes and path lengths at the edges -- resolutions that do not tile into 8x4 warps, a single
+pixel, paths of length 0 and 1, Russian roulette from the first vertex, an empty scene, more samples than one batch holds.
+All frames bit-exact against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+from tweeker_raytracer_b200 import host
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(tmp_path, scene="rtigo3_cornell_box", iterations=3, scene_file=None, **overrides):
+    with host.App(H.write_system(tmp_path, scene, **overrides), scene_file or H.scene_path(scene)) as app:
+        w, h = app.resolution
+        assert app.render(iterations) == iterations
+        got = app.frame()
+        want = H.oracle_scene(app).render(H.oracle_sys(app), app.info.miss, w, h, iter_count=iterations).reshape(h, w, 4)
+        assert got.tobytes() == want.tobytes()
+        assert app.stats().stackOverflows == 0
+        return got
+
+
+@pytest.mark.parametrize("resolution", ["1 1", "7 5", "33 17", "130 3", "8 4", "64 36"])
+def test_launch_shapes(cuda_device, tmp_path, resolution):
+    _check(tmp_path, resolution=resolution, samplesSqrt=2, iterations=4)
+
+
+@pytest.mark.parametrize("lengths", ["0 0", "0 1", "1 1", "0 2", "3 3", "0 16"])
+def test_path_lengths(cuda_device, tmp_path, lengths):
+    frame = _check(tmp_path, scene="rtigo3_geometry", resolution="72 40", samplesSqrt=2, pathLengths=lengths, iterations=3)
+    if lengths == "0 0":
+        assert not frame[..., :3].any() and np.all(frame[..., 3] == 1.0)     # no segment is traced: black, alpha 1
+
+
+def test_empty_scene_shows_the_environment(cuda_device, tmp_path):
+    scene = os.path.join(str(tmp_path), "scene_empty.txt")
+    with open(scene, "w") as f:
+        f.write("albedo 1 1 1\nmaterial default brdf_diffuse\n")
+    frame = _check(tmp_path, scene="rtigo3_geometry", scene_file=scene, resolution="40 24", samplesSqrt=2, light=0, miss=1, iterations=2)
+    assert np.all(frame[..., :3] == 1.0)                                     # constant white environment, nothing in front of it
+
+
+def test_more_paths_than_one_batch(cuda_device, tmp_path, monkeypatch):
+    """RTC_MAX_PATHS forces several batches per enqueue; the running average must not depend on the batching."""
+    monkeypatch.setenv("RTC_MAX_PATHS", str(64 * 36 * 3))
+    a = _check(tmp_path, scene="rtigo3_geometry", resolution="64 36", samplesSqrt=4, iterations=10)
+    monkeypatch.delenv("RTC_MAX_PATHS")
+    b = _check(tmp_path, scene="rtigo3_geometry", resolution="64 36", samplesSqrt=4, iterations=10)
+    assert a.tobytes() == b.tobytes()

@@ -960,7 +960,7 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
     RTC_CUDA(cudaMemsetAsync(cnt, 0, 4 * kNumCounters, ctx->stream));
     // Fused primary path (scenes without material textures): no generate pass.  The depth-0 extend computes its rays from the
     // launch index, and the depth-0 shade kernels recompute the path start instead of reading five state arrays back.
-    const bool fused = !tex;
+    const bool fused = !tex && 0 < maxDepth;      // pathLengths.y == 0: nothing is traced, generate still zeroes the radiance
     if (!fused)
     {
       if (int rc = profile_begin(ctx, RTC_KERNEL_GENERATE)) return rc;
