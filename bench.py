@@ -41,6 +41,7 @@ WORKLOADS = {
     "rtigo3_geometry": WORKLOAD,
     "rtigo3_cornell_box": "rtigo3 Cornell box (area light, mirror + glass spheres)",
     "rtigo3_instances": "instanced stress scene: instances of a 50 000-triangle torus (two-level BVH), constant environment",
+    "rtigo3_textures": "rtigo3 geometry scene with albedo and cutout textures (ordered any-hit processing, host-synchronised rounds)",
 }
 
 
