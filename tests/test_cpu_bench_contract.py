@@ -1,0 +1,43 @@
+"""The bench.py contract that can be checked without a GPU: the reference arm prints ONE JSON line with the agreed keys
+(it times the reference's own host-compiled device programs, or the oracle port where those are not built), and the clock
+sampler degrades gracefully where neither NVML nor nvidia-smi can see a GPU."""
+import json
+import os
+import subprocess
+import sys
+
+import helpers as H
+
+
+def test_reference_arm_prints_the_contract_line(built):
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, os.path.join(H.ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--resolution", "192 108"], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "rtigo3_geometry_1080p_samples_per_s" and d["unit"] == "Msamples/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "192x108" in d["config"]["workload"]
+
+
+def test_reference_arm_is_silent_on_other_ranks(built):
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(H.ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=120, env=env)
+    assert out.returncode == 0 and not [l for l in out.stdout.splitlines() if l.startswith("{")]
+
+
+def test_clock_sampler_without_a_gpu():
+    sys.path.insert(0, H.ROOT)
+    import bench
+    s = bench.ClockSampler(0)
+    s.start()
+    s.stop_flag.set()
+    s.join(timeout=10)
+    summary = s.summary()
+    assert set(summary) >= {"sm_mhz", "sm_max_mhz", "reasons", "samples", "source"}
+    assert summary["source"] in ("nvml", "nvidia-smi")
