@@ -5,6 +5,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 CSRC      := tweeker_raytracer_b200/csrc
 HOST      := tweeker_raytracer_b200/host
 LIB       := tweeker_raytracer_b200/lib
+$(shell mkdir -p $(LIB))
 INC       := -Iinclude -I$(CSRC)
 NVFLAGS   := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC $(INC)
 CXXFLAGS  := -O2 -std=c++17 -fPIC -ffp-contract=off $(INC) -I/usr/local/cuda/include -Wall
