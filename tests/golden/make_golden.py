@@ -28,6 +28,9 @@ CASES = {
     # material textures: albedo modulation + the reference's own cutout any-hit programs run per candidate in canonical order
     "textures_64x36_4spp": ("rtigo3_textures", dict(resolution="64 36", samplesSqrt=2), 4),
     "textures_rr_env_48x27_3spp": ("rtigo3_textures", dict(resolution="48 27", samplesSqrt=2, miss=2, envMap="procedural 128 64", pathLengths="0 8"), 3),
+    # converged frames for the PSNR >= 40 dB check of BASELINE.json (the host-compiled reference stands in for the OptiX build)
+    "geometry_converged_96x54_256spp": ("rtigo3_geometry", dict(resolution="96 54", samplesSqrt=16), 256),
+    "cornell_converged_64x64_256spp": ("rtigo3_cornell_box", dict(resolution="64 64", samplesSqrt=16), 256),
     "cornell_tiled_3dev_40x16_2spp": ("rtigo3_cornell_box", dict(resolution="40 16", samplesSqrt=2, tileSize="8 8"), 2),
 }
 

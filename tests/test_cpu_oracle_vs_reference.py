@@ -97,3 +97,16 @@ def test_geometry_scene_pinned_vs_libm_psnr(built, tmp_path):
     b = H.oracle_scene(app, "libm").render(sysd, app.info.miss, 64, 36, iter_count=36)
     assert H.psnr(np.clip(a[:, :3], 0, 1), np.clip(b[:, :3], 0, 1)) > 40.0
     app.close()
+
+
+@pytest.mark.parametrize("key", ["geometry_converged_96x54_256spp", "cornell_converged_64x64_256spp"])
+def test_converged_frames_reach_40_db_against_the_reference(built, tmp_path, golden_frames, key):
+    """BASELINE.json's image check: converged frames at PSNR >= 40 dB against the reference's output.  The reference here is its
+    own device code compiled for the host (libm transcendentals); the frame compared is the pinned-arithmetic oracle's, which
+    the GPU reproduces bit for bit (tests/test_gpu_render_parity.py), so this bounds the GPU image as well."""
+    got, app, _, _ = render_case(tmp_path, key, "pinned")
+    want = golden_frames[key]
+    a, b = np.clip(got[key][..., :3], 0.0, 1.0), np.clip(want[..., :3], 0.0, 1.0)
+    assert H.psnr(a, b) >= 40.0, H.psnr(a, b)
+    assert abs(float(a.mean()) - float(b.mean())) < 2e-3
+    app.close()

@@ -204,3 +204,20 @@ def test_mutators_restart_and_match_oracle(cuda_device, tmp_path):
         assert app.stats().stackOverflows == 0
     finally:
         app.close()
+
+
+@pytest.mark.parametrize("key", ["geometry_converged_96x54_256spp", "cornell_converged_64x64_256spp"])
+def test_converged_frames_reach_40_db_against_the_reference(cuda_device, tmp_path, key):
+    """BASELINE.json: converged images at PSNR >= 40 dB against the reference's output -- here the committed frames of the
+    reference's own device code compiled for the host (tests/golden/make_golden.py), rendered on the GPU with the same seeds."""
+    import os
+    from golden import make_golden
+    golden = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_frames.npz"))
+    name, overrides, iterations = make_golden.CASES[key]
+    with host.App(H.write_system(tmp_path, name, **overrides), H.scene_path(name)) as app:
+        while app.render(64) < iterations:
+            pass
+        got = app.frame()
+    want = golden[key]
+    a, b = np.clip(got[..., :3], 0.0, 1.0), np.clip(want[..., :3], 0.0, 1.0)
+    assert H.psnr(a, b) >= 40.0, H.psnr(a, b)
