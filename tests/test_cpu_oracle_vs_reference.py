@@ -110,3 +110,25 @@ def test_converged_frames_reach_40_db_against_the_reference(built, tmp_path, gol
     assert H.psnr(a, b) >= 40.0, H.psnr(a, b)
     assert abs(float(a.mean()) - float(b.mean())) < 2e-3
     app.close()
+
+
+@pytest.mark.skipif(not (os.path.exists(orc.REF_LIB) or os.path.isdir(orc.REFERENCE_SHADERS)), reason="host-compiled reference not available")
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_random_scenes_equal_live_reference(built, tmp_path, seed):
+    """Randomly generated scenes (the generator of tests/test_gpu_fuzz.py), half of them with albedo and cutout textures: the
+    libm oracle must reproduce the reference's own device programs bit for bit, any-hit programs included."""
+    import test_gpu_fuzz as fuzz
+    rng = np.random.default_rng(7000 + seed)
+    scene_file = os.path.join(str(tmp_path), "scene_fuzz.txt")
+    fuzz.random_scene(scene_file, rng, textures=bool(seed & 1))
+    miss = int(rng.integers(0, 3))
+    overrides = dict(resolution="40 24", samplesSqrt=2, miss=miss, light=int(rng.integers(0 if miss else 1, 3)),
+                     lensShader=int(rng.integers(0, 3)), pathLengths="%d %d" % (int(rng.integers(0, 3)), int(rng.integers(2, 9))),
+                     envMap="procedural 64 32", envRotation="%.3f" % rng.uniform(0, 1))
+    app = host.App(H.write_system(tmp_path, "rtigo3_textures", **overrides), scene_file, host_only=True)
+    scene = H.oracle_scene(app, "libm")
+    sysd = H.oracle_sys(app)
+    got = scene.render(sysd, app.info.miss, 40, 24, iter_count=3, threads=2)
+    want = orc.Reference(scene, app.info.miss).render(sysd, 40, 24, iter_count=3)
+    assert got.tobytes() == want.tobytes()
+    app.close()
