@@ -12,6 +12,9 @@
 
 #include "rtc_internal.h"
 
+#ifndef RTC_I2F_AXES
+#define RTC_I2F_AXES 1            // number of axes (0, 1 or 2; swept with tools/sweep_i2f.sh: 1 and 2 are +0.4 %) whose plane bytes are converted by I2F.U8 instead of PRMT
+#endif
 #ifndef RTC_FETCH_THRESHOLD
 #define RTC_FETCH_THRESHOLD 8     // refill a warp when at least this many lanes have finished their ray
 #endif
@@ -130,6 +133,15 @@ __device__ __forceinline__ float quant_f(uint32_t w, uint32_t bias)
   return __uint_as_float(r);
 }
 
+// q as a float through the conversion unit: one I2F.U8 with a byte selector.  It runs on the XU pipe, which the traversal
+// barely uses, while PRMT competes with the selects, min/max and integer work for the ALU pipe (72 % busy on primary rays):
+// RTC_I2F_AXES of the three axes are decoded this way to balance the two pipes.
+template <uint32_t I>
+__device__ __forceinline__ float quant_i2f(uint32_t w)
+{
+  return (float)((w >> (8u * I)) & 0xffu);
+}
+
 // Tests the 8 quantised child boxes of one node.  Returns bit s set when the box in slot s is hit.
 // opaqueZero: a value that is always 0 but that the compiler cannot prove to be (bit 31 of a child index).
 __device__ __forceinline__ uint32_t node_test(const BoxRay& b, const uint4 n0, const uint4 n2, const uint4 n3, const uint4 n4,
@@ -140,8 +152,16 @@ __device__ __forceinline__ uint32_t node_test(const BoxRay& b, const uint4 n0, c
   const float adjy = __uint_as_float(((e >> 8) & 0xffu) << 23) * b.idy;
   const float adjz = __uint_as_float(((e >> 16) & 0xffu) << 23) * b.idz;
   const float orgx = fmaf(-32768.0f, adjx, (__uint_as_float(n0.x) - b.ox) * b.idx);
+#if RTC_I2F_AXES >= 2
+  const float orgy = (__uint_as_float(n0.y) - b.oy) * b.idy;
+#else
   const float orgy = fmaf(-32768.0f, adjy, (__uint_as_float(n0.y) - b.oy) * b.idy);
+#endif
+#if RTC_I2F_AXES >= 1
+  const float orgz = (__uint_as_float(n0.z) - b.oz) * b.idz;            // z planes: plain q through I2F, no bias to cancel
+#else
   const float orgz = fmaf(-32768.0f, adjz, (__uint_as_float(n0.z) - b.oz) * b.idz);
+#endif
   // near/far plane words per axis, selected by the direction sign
   // layout: n2 = qlox[0..3], qlox[4..7], qloy[0..3], qloy[4..7]; n3 = qloz, qhix; n4 = qhiy, qhiz
   const bool nx = b.idx < 0.0f, ny = b.idy < 0.0f, nz = b.idz < 0.0f;
@@ -151,11 +171,21 @@ __device__ __forceinline__ uint32_t node_test(const BoxRay& b, const uint4 n0, c
   const float tlimitPad = tlimit * (1.0f + 0x1p-17f);
   const uint32_t bias = 0x47000000u + opaqueZero;     // kept in a register on purpose, see quant_f
   uint32_t hits = 0;
+#if RTC_I2F_AXES >= 1
+#define RTC_QZ(I, W) quant_i2f<I>(W)
+#else
+#define RTC_QZ(I, W) quant_f<I>(W, bias)
+#endif
+#if RTC_I2F_AXES >= 2
+#define RTC_QY(I, W) quant_i2f<I>(W)
+#else
+#define RTC_QY(I, W) quant_f<I>(W, bias)
+#endif
 #define RTC_BOX(S, H, I) \
   { \
     const float t0x = fmaf(quant_f<I>(nearx[H], bias), adjx, orgx), t1x = fmaf(quant_f<I>(farx[H], bias), adjx, orgx); \
-    const float t0y = fmaf(quant_f<I>(neary[H], bias), adjy, orgy), t1y = fmaf(quant_f<I>(fary[H], bias), adjy, orgy); \
-    const float t0z = fmaf(quant_f<I>(nearz[H], bias), adjz, orgz), t1z = fmaf(quant_f<I>(farz[H], bias), adjz, orgz); \
+    const float t0y = fmaf(RTC_QY(I, neary[H]), adjy, orgy), t1y = fmaf(RTC_QY(I, fary[H]), adjy, orgy); \
+    const float t0z = fmaf(RTC_QZ(I, nearz[H]), adjz, orgz), t1z = fmaf(RTC_QZ(I, farz[H]), adjz, orgz); \
     const float tn = fmaxf(fmaxf(fmaxf(t0x, t0y), t0z), tmin); \
     const float tf = fminf(fminf(fminf(t1x, t1y), t1z) * (1.0f + 0x1p-17f), tlimitPad); \
     if (tn <= tf) hits |= 1u << S; \
@@ -163,6 +193,8 @@ __device__ __forceinline__ uint32_t node_test(const BoxRay& b, const uint4 n0, c
   RTC_BOX(0, 0, 0) RTC_BOX(1, 0, 1) RTC_BOX(2, 0, 2) RTC_BOX(3, 0, 3)
   RTC_BOX(4, 1, 0) RTC_BOX(5, 1, 1) RTC_BOX(6, 1, 2) RTC_BOX(7, 1, 3)
 #undef RTC_BOX
+#undef RTC_QZ
+#undef RTC_QY
   return hits;
 }
 
