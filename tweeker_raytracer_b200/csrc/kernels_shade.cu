@@ -837,24 +837,59 @@ __global__ void k_stats(const uint32_t* __restrict__ counters, int maxDepth, uin
 namespace {
 
 template <int CLASS>
-void launch_shade_class(rtc_context* ctx, int grid, const WfArgs& a, const SceneDesc& sc, uint32_t* bins, uint32_t binStride, uint32_t* binCounts,
+void launch_shade_class(rtc_context* ctx, cudaStream_t stream, int grid, const WfArgs& a, const SceneDesc& sc, uint32_t* bins, uint32_t binStride, uint32_t* binCounts,
                         uint32_t* qOut, uint32_t* countOut, uint32_t* shadowQueue, uint32_t* shadowCount, bool tex, bool deferRR, bool primary)
 {
-  if (tex)          k_shade<CLASS, true, false><<<grid, kBlock, 0, ctx->stream>>>(a, sc, bins + (size_t)CLASS * binStride, binCounts + CLASS, qOut, countOut, shadowQueue, shadowCount, deferRR ? 1 : 0);
-  else if (primary) k_shade<CLASS, false, true><<<grid, kBlock, 0, ctx->stream>>>(a, sc, bins + (size_t)CLASS * binStride, binCounts + CLASS, qOut, countOut, shadowQueue, shadowCount, 0);
-  else              k_shade<CLASS, false, false><<<grid, kBlock, 0, ctx->stream>>>(a, sc, bins + (size_t)CLASS * binStride, binCounts + CLASS, qOut, countOut, shadowQueue, shadowCount, 0);
+  if (tex)          k_shade<CLASS, true, false><<<grid, kBlock, 0, stream>>>(a, sc, bins + (size_t)CLASS * binStride, binCounts + CLASS, qOut, countOut, shadowQueue, shadowCount, deferRR ? 1 : 0);
+  else if (primary) k_shade<CLASS, false, true><<<grid, kBlock, 0, stream>>>(a, sc, bins + (size_t)CLASS * binStride, binCounts + CLASS, qOut, countOut, shadowQueue, shadowCount, 0);
+  else              k_shade<CLASS, false, false><<<grid, kBlock, 0, stream>>>(a, sc, bins + (size_t)CLASS * binStride, binCounts + CLASS, qOut, countOut, shadowQueue, shadowCount, 0);
 }
 
-void launch_shade_classes(rtc_context* ctx, int grid, const WfArgs& a, const SceneDesc& sc, uint32_t* bins, uint32_t binStride, uint32_t* binCounts,
-                          uint32_t* qOut, uint32_t* countOut, uint32_t* shadowQueue, uint32_t* shadowCount, bool tex, bool deferRR, bool primary)
+// The seven class kernels of one depth only share the output queues (atomic appends): the diffuse class, the largest, stays on
+// the context stream, the other six fork onto side streams after k_bin and join before the next stage, so the small ones fill
+// the tails of the large ones instead of each running alone.  RTC_SHADE_STREAMS=0 keeps everything on the context stream.
+int launch_shade_classes(rtc_context* ctx, int grid, const WfArgs& a, const SceneDesc& sc, uint32_t* bins, uint32_t binStride, uint32_t* binCounts,
+                         uint32_t* qOut, uint32_t* countOut, uint32_t* shadowQueue, uint32_t* shadowCount, bool tex, bool deferRR, bool primary)
 {
-  launch_shade_class<SHADE_MISS>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
-  launch_shade_class<SHADE_BRDF_DIFFUSE>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
-  launch_shade_class<SHADE_BRDF_SPECULAR>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
-  launch_shade_class<SHADE_BSDF_SPECULAR>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
-  launch_shade_class<SHADE_BRDF_GGX>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
-  launch_shade_class<SHADE_BSDF_GGX>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
-  launch_shade_class<SHADE_OTHER>(ctx, grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
+  static const bool concurrent = []() { const char* e = getenv("RTC_SHADE_STREAMS"); return !(e && atoi(e) == 0); }();
+  cudaStream_t s[7];
+  for (int k = 0; k < 7; ++k) s[k] = ctx->stream;
+  if (concurrent)
+  {
+    if (!ctx->shadeFork)
+    {
+      RTC_CUDA(cudaEventCreateWithFlags(&ctx->shadeFork, cudaEventDisableTiming));
+      for (int k = 0; k < 6; ++k)
+      {
+        RTC_CUDA(cudaStreamCreateWithFlags(&ctx->shadeStreams[k], cudaStreamNonBlocking));
+        RTC_CUDA(cudaEventCreateWithFlags(&ctx->shadeJoin[k], cudaEventDisableTiming));
+      }
+    }
+    RTC_CUDA(cudaEventRecord(ctx->shadeFork, ctx->stream));
+    int side = 0;
+    for (int k = 0; k < 7; ++k)
+    {
+      if (k == SHADE_BRDF_DIFFUSE) continue;
+      s[k] = ctx->shadeStreams[side++];
+      RTC_CUDA(cudaStreamWaitEvent(s[k], ctx->shadeFork, 0));
+    }
+  }
+  launch_shade_class<SHADE_MISS>(ctx, s[SHADE_MISS], grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
+  launch_shade_class<SHADE_BRDF_DIFFUSE>(ctx, s[SHADE_BRDF_DIFFUSE], grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
+  launch_shade_class<SHADE_BRDF_SPECULAR>(ctx, s[SHADE_BRDF_SPECULAR], grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
+  launch_shade_class<SHADE_BSDF_SPECULAR>(ctx, s[SHADE_BSDF_SPECULAR], grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
+  launch_shade_class<SHADE_BRDF_GGX>(ctx, s[SHADE_BRDF_GGX], grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
+  launch_shade_class<SHADE_BSDF_GGX>(ctx, s[SHADE_BSDF_GGX], grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
+  launch_shade_class<SHADE_OTHER>(ctx, s[SHADE_OTHER], grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
+  if (concurrent)
+  {
+    for (int k = 0; k < 6; ++k)
+    {
+      RTC_CUDA(cudaEventRecord(ctx->shadeJoin[k], ctx->shadeStreams[k]));
+      RTC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->shadeJoin[k], 0));
+    }
+  }
+  return 0;
 }
 
 // scratch of the ordered any-hit processing: two queues of `capacity` path ids + {count 0, count 1, cursor, pad}
@@ -988,7 +1023,7 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
       if (int rc = profile_begin(ctx, RTC_KERNEL_SHADE)) return rc;
       uint32_t* binCounts = cnt + 256 + d * 8;
       k_bin<<<gridShade, kBlock, 0, ctx->stream>>>(a, scene->desc, primary ? nullptr : qIn, cnt + d, ctx->wf.bins, ctx->wf.binStride, binCounts, cnt + d);
-      launch_shade_classes(ctx, gridShade, a, scene->desc, ctx->wf.bins, ctx->wf.binStride, binCounts, qOut, cnt + d + 1, ctx->wf.shadowQueue, cnt + 64 + d, tex, cutout, primary);
+      if (int rc = launch_shade_classes(ctx, gridShade, a, scene->desc, ctx->wf.bins, ctx->wf.binStride, binCounts, qOut, cnt + d + 1, ctx->wf.shadowQueue, cnt + 64 + d, tex, cutout, primary)) return rc;
       ctx->kernelLaunches += 1 + SHADE_NUM_CLASSES;
       if (int rc = profile_end(ctx)) return rc;
       if (sys.numLights > 0)

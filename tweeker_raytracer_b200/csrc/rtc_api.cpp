@@ -163,6 +163,8 @@ int rtc_context_destroy(rtc_context* ctx)
   for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
   cudaEventDestroy(ctx->evA); cudaEventDestroy(ctx->evB);
   cudaEventDestroy(ctx->evTimerA); cudaEventDestroy(ctx->evTimerB);
+  for (int k = 0; k < 6; ++k) { if (ctx->shadeStreams[k]) cudaStreamDestroy(ctx->shadeStreams[k]); if (ctx->shadeJoin[k]) cudaEventDestroy(ctx->shadeJoin[k]); }
+  if (ctx->shadeFork) cudaEventDestroy(ctx->shadeFork);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;

@@ -141,6 +141,10 @@ struct rtc_context
   std::vector<cudaEvent_t> eventPool;
   rtc_profile profile{};
   std::vector<void*> textures;                    // rtc_texture_create allocations still alive
+  // side streams of the shade stage: the class-specialised kernels of one depth are independent of each other and mostly
+  // small, so they run concurrently (fork from `stream` after k_bin, join before connect); created on first use
+  cudaStream_t shadeStreams[6] = {};
+  cudaEvent_t  shadeFork = nullptr, shadeJoin[6] = {};
   unsigned long long* d_launchCounts = nullptr;   // 2 x {nodes, tris, insts, rays}: extend, connect
   uint32_t* d_cursor = nullptr;                   // ray cursor of the query kernels (rtc_trace_*)
 };
