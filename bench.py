@@ -161,7 +161,7 @@ def measured_peak():
 
 def system_file(tmp, args, device_ordinal):
     import helpers as H
-    return H.write_system(tmp, args.scene, resolution=args.resolution, samplesSqrt=128, devicesMask=1 << device_ordinal, strategy=0)
+    return H.write_system(tmp, args.scene, resolution=args.resolution, samplesSqrt=256, devicesMask=1 << device_ordinal, strategy=0)
 
 
 def scene_file(tmp, args):
