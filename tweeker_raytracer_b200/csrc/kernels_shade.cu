@@ -326,6 +326,58 @@ k_shade(const __grid_constant__ WfArgs a, const SceneDesc sc,
   for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride)
   {
     const uint32_t i = base + threadIdx.x;
+    if (CLASS == SHADE_MISS)
+    {
+      // A path that left the scene ends here (the miss programs set FLAG_TERMINATE): it touches its throughput, its radiance and
+      // its volume-stack index, the ray direction only for the spherical environment -- not the ray origin, the hit record or
+      // the seed -- and joins no queue, so this instantiation has no barrier.  Same operations as the general path below.
+      if (i < n)
+      {
+        const uint32_t pm = queueIn[i];
+        float4 tpm, Lfm; float3 wim = f3(0.0f, 0.0f, 1.0f); int stackIdxM;
+        if (PRIMARY)
+        {
+          tpm = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+          Lfm = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
+          stackIdxM = RT_MATERIAL_STACK_EMPTY;
+          if (a.miss == RT_MISS_SPHERE)
+          {
+            const uint32_t pixelsPerIter = a.launchWidth * a.launchHeight;
+            const uint32_t it = pm / pixelsPerIter, idx = pm - it * pixelsPerIter;
+            uint32_t x, y;
+            launch_xy(idx, a.launchWidth, a.launchHeight, x, y);
+            uint32_t seed = 0, col = 0; float3 pos;
+            start_path(sys, a.launchWidth, x, y, a.iterFirst + (int)it, seed, pos, wim, col);
+          }
+        }
+        else
+        {
+          tpm = a.wf.throughput[pm];
+          Lfm = a.wf.radiance[pm];
+          stackIdxM = (int)a.wf.misc[pm].z;
+          if (a.miss == RT_MISS_SPHERE) { const float4 rd = a.wf.rayDir[pm]; wim = f3(rd.x, rd.y, rd.z); }
+        }
+        Prd prd;
+        prd.wi = wim;
+        prd.pdf = tpm.w;
+        prd.flags = __float_as_uint(Lfm.w) & RT_FLAG_CLEAR_MASK;
+        prd.sigma_t = f3(0.0f);
+        prd.distance = RT_DEFAULT_MAX;
+        if (RT_MATERIAL_STACK_FIRST <= stackIdxM)
+        {
+          const float4 top = a.wf.absStack[(size_t)pm * 4 + stackIdxM];
+          prd.flags |= RT_FLAG_VOLUME;
+          prd.sigma_t = f3(top.x, top.y, top.z);
+        }
+        miss_program(sys, a.miss, prd);
+        float3 throughput = f3(tpm.x, tpm.y, tpm.z);
+        if (prd.flags & RT_FLAG_VOLUME)
+          throughput = throughput * f3(rt_expf(-prd.distance * prd.sigma_t.x), rt_expf(-prd.distance * prd.sigma_t.y), rt_expf(-prd.distance * prd.sigma_t.z));
+        const float3 radiance = f3(Lfm.x, Lfm.y, Lfm.z) + throughput * prd.radiance;
+        a.wf.radiance[pm] = make_float4(radiance.x, radiance.y, radiance.z, __uint_as_float(prd.flags));
+      }
+      continue;
+    }
     bool continues = false, shadow = false, pendingRR = false;
     uint32_t p = 0, octContinue = 0, octShadow = 0;
     if (i < n)
