@@ -444,8 +444,9 @@ def main():
     for _ in range(K):
         ctx.upload_async(sys_host.cameraDefinitions, pinned, 48)      # this step's camera, from pinned host memory
         app.render(S)
-        fr = app.frame_view()                                         # device -> host read of the step's result
-        checksum += float(fr[0, 0, 0])
+        fr = app.frame_view()                                         # device -> host read of the step's result (rank 0 in a group)
+        if fr is not None:
+            checksum += float(fr[0, 0, 0])
     ctx.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")

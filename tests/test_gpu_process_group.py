@@ -61,8 +61,9 @@ with host.App(system, H.scene_path("rtigo3_cornell_box")) as app:
     budget = {sqrt} * {sqrt} // world
     assert app.render(3) == 3
     assert app.render(1000) == budget          # stops at this rank's share
-    frame = app.frame()                        # collective
-    np.save(os.path.join(tmp, "frame%d.npy" % rank), frame)
+    frame = app.frame()                        # collective: the mean frame on rank 0, None elsewhere
+    assert (frame is None) == (rank != 0)
+    np.save(os.path.join(tmp, "frame%d.npy" % rank), frame if rank == 0 else app.local_frame())
 """
 
 
@@ -95,7 +96,7 @@ def test_two_processes_two_gpus(cuda_device, tmp_path):
         return frame.reshape(HGT, W, 4)
 
     a0, a1 = average(0), average(half)
-    assert local1.tobytes() == a1.tobytes()                       # a non-root rank returns its own running average
+    assert local1.tobytes() == a1.tobytes()                       # local_frame() of rank 1: its own running average
     want = (a0 * np.float32(0.5) + a1 * np.float32(0.5)).astype(np.float32)
     assert got.tobytes() == want.tobytes()                        # mean of two: exact in binary floating point
     single = ref.render(sysd, app.info.miss, W, HGT, iter_count=2 * half).reshape(HGT, W, 4)

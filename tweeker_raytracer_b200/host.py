@@ -56,7 +56,7 @@ assert C.sizeof(SystemData) == 192 and C.sizeof(CompositorData) == 56
 
 SYMBOLS = ["rth_last_error", "rth_app_create", "rth_app_destroy", "rth_app_info", "rth_app_geometry", "rth_app_instance",
            "rth_app_materials", "rth_app_lights", "rth_app_camera", "rth_app_system_data", "rth_app_tonemapper",
-           "rth_app_environment", "rth_app_render", "rth_app_synchronize", "rth_app_frame", "rth_app_restart",
+           "rth_app_environment", "rth_app_render", "rth_app_synchronize", "rth_app_frame", "rth_app_local_frame", "rth_app_restart",
            "rth_app_set_composite", "rth_app_save_system", "rth_app_set_camera", "rth_app_update_material", "rth_app_update_light_emission", "rth_app_benchmark", "rth_app_screenshot", "rth_app_tonemap", "rth_app_context", "rth_app_stats",
            "rth_app_update_material_textures", "rth_app_picture", "rth_process_group_id", "rth_app_join_group", "rth_app_group_reduce_mean", "rth_sample_range"]
 
@@ -89,6 +89,8 @@ def lib():
         L.rth_app_synchronize.argtypes = [C.c_void_p]
         L.rth_app_frame.argtypes = [C.c_void_p]
         L.rth_app_frame.restype = C.c_void_p
+        L.rth_app_local_frame.argtypes = [C.c_void_p]
+        L.rth_app_local_frame.restype = C.c_void_p
         L.rth_app_restart.argtypes = [C.c_void_p]
         L.rth_app_set_composite.argtypes = [C.c_void_p, C.c_int]
         L.rth_app_save_system.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
@@ -146,6 +148,7 @@ class App:
         self.h = C.c_void_p(self.h)
         self.info = Info()
         self.L.rth_app_info(self.h, C.byref(self.info))
+        self.group_rank = 0
 
     def close(self):
         if self.h:
@@ -262,10 +265,21 @@ class App:
         if self.L.rth_app_synchronize(self.h) != 0:
             raise core.RtcError(self.L.rth_last_error().decode())
 
+    def local_frame(self):
+        """This process's own running average (no collective), float32 [height, width, 4]."""
+        p = self.L.rth_app_local_frame(self.h)
+        if not p:
+            raise core.RtcError("getLocalOutputBufferHost failed")
+        w, h = self.resolution
+        return _copy(p, np.float32, 4 * w * h).reshape(h, w, 4)
+
     def frame(self):
-        """float32 [height, width, 4], row 0 = bottom of the image."""
+        """float32 [height, width, 4], row 0 = bottom of the image.  In a process group this is a collective and only rank 0
+        receives the (mean) frame: the other ranks get None."""
         p = self.L.rth_app_frame(self.h)
         if not p:
+            if self.group_rank > 0:
+                return None
             raise core.RtcError("getOutputBufferHost failed")
         w, h = self.resolution
         return _copy(p, np.float32, 4 * w * h).reshape(h, w, 4)
@@ -274,6 +288,8 @@ class App:
         """Like frame() but a zero-copy view of the host staging buffer (valid until the next frame call)."""
         p = self.L.rth_app_frame(self.h)
         if not p:
+            if self.group_rank > 0:
+                return None
             raise core.RtcError("getOutputBufferHost failed")
         w, h = self.resolution
         buf = (C.c_float * (4 * w * h)).from_address(p)
@@ -289,6 +305,7 @@ class App:
             raise ValueError("group_id must be the 128 bytes of process_group_id()")
         if self.L.rth_app_join_group(self.h, rank, world, group_id) != 0:
             raise core.RtcError(self.L.rth_last_error().decode())
+        self.group_rank = rank
 
     def set_composite(self, mode):
         self.L.rth_app_set_composite(self.h, mode)

@@ -340,7 +340,7 @@ void Application::tonemapDevice(std::vector<unsigned char>& rgb)
 {
   const size_t pixels = (size_t)m_resolution.x * (size_t)m_resolution.y;
   rgb.resize(3 * pixels);
-  const float* host = getOutputBufferHost();
+  const float* host = getOutputBufferHost();      // collective in a process group; only rank 0 holds the frame
   if (!host) return;
   Device* device = m_raytracer->m_activeDevices[0];
   rtc_context* ctx = device->getContext();
@@ -375,9 +375,9 @@ bool Application::screenshot(const bool tonemap, std::string* writtenPath)
     }
     else
     {
-      const float* host = getOutputBufferHost();
+      const float* host = getOutputBufferHost();      // nullptr on the other ranks of a process group
       file = path.str() + ".hdr";
-      ok = host && (!writer || writeHDR(file, m_resolution.x, m_resolution.y, host, true));
+      ok = !writer || (host && writeHDR(file, m_resolution.x, m_resolution.y, host, true));
     }
     if (!writer) { if (writtenPath) writtenPath->clear(); return ok; }
     if (ok) std::cout << file << std::endl;

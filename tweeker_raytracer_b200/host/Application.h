@@ -43,7 +43,8 @@ public:
   // accessors
   Raytracer* getRaytracer() { return m_raytracer.get(); }
   int2 getResolution() const { return m_resolution; }
-  int getSamplesPerPixel() const { return m_samplesSqrt * m_samplesSqrt; }
+  // the iterations render() can reach: samplesSqrt^2, or this rank's share of them once the process joined a group
+  int getSamplesPerPixel() const { return m_raytracer ? (int)m_raytracer->getSamplesPerPixelLocal() : m_samplesSqrt * m_samplesSqrt; }
   int getMiss() const { return m_miss; }
   int getLightMode() const { return m_light; }
   int getDevicesMask() const { return m_devicesMask; }

@@ -44,6 +44,11 @@ void Raytracer::reduceMeanToRoot(const uint64_t src, const uint64_t dst, const s
   ncclProcessGroupReduceMean(m_processGroup, src, dst, count, rtc_context_stream(m_activeDevices[0]->getContext()));
 }
 
+const void* Raytracer::getLocalOutputBufferHost()
+{
+  return m_activeDevices.empty() ? nullptr : m_activeDevices[0]->getOutputBufferHost();
+}
+
 void Raytracer::applySeedOffsets()
 {
   const unsigned int offset = (unsigned int)m_rank * getSamplesPerPixelLocal();
@@ -52,7 +57,8 @@ void Raytracer::applySeedOffsets()
 
 // Collective: mean of the ranks' running averages -> rank 0 (ncclReduce with ncclAvg on the render stream, so it is
 // ordered behind the launches without a host synchronisation), then rank 0 reads the mean frame back.  The other ranks
-// return their own local frame.
+// return nullptr: the frame lives on rank 0, and seven more 33 MB read-backs per step would only compete with rank 0's for
+// host memory bandwidth (getLocalOutputBufferHost() fetches a rank's own running average when a tool wants it).
 const void* Raytracer::combineProcessGroup()
 {
   Device* device = m_activeDevices[0];
@@ -70,7 +76,7 @@ const void* Raytracer::combineProcessGroup()
     m_combinedPixels = pixels;
   }
   reduceMeanToRoot(device->getOutputBufferDevice(), m_combined, pixels * 4);
-  if (m_rank != 0) return device->getOutputBufferHost();
+  if (m_rank != 0) return nullptr;
   RTC_CHECK(rtc_download(ctx, m_combinedHost, m_combined, sizeof(float4) * pixels));
   RTC_CHECK(rtc_synchronize(ctx));
   return m_combinedHost;

@@ -10,7 +10,7 @@
 // One process per GPU (torchrun-style): joinProcessGroup(rank, world, id) turns a single-GPU Raytracer into rank `rank`
 // of a sample-range partition -- it renders the iterations [rank * spp/world, (rank+1) * spp/world) as its own
 // running average, and getOutputBufferHost() becomes a collective that lands the mean of the ranks' frames on rank 0
-// with one ncclReduce over NVLink.
+// with one ncclReduce over NVLink (the other ranks get nullptr).
 #pragma once
 #include <map>
 #include <memory>
@@ -54,6 +54,8 @@ public:
   // mean over the ranks of `count` floats at device address src -> dst on rank 0 (0 elsewhere), enqueued on the render
   // stream behind the launches (no host synchronisation).  Collective.  The building block of getOutputBufferHost().
   void reduceMeanToRoot(const uint64_t src, const uint64_t dst, const size_t count);
+  // this process's own running average (not a collective); equals getOutputBufferHost() outside a process group
+  const void* getLocalOutputBufferHost();
   int getRank() const { return m_rank; }
   int getWorld() const { return m_world; }
   // iterations this process renders: samplesPerPixel / world (at least 1)

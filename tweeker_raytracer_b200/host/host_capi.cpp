@@ -153,6 +153,12 @@ int rth_app_synchronize(void* h)
   try { static_cast<Application*>(h)->getRaytracer()->synchronize(); return 0; } catch (std::exception const& e) { g_error = e.what(); return -1; }
 }
 const float* rth_app_frame(void* h) { return static_cast<Application*>(h)->getOutputBufferHost(); }
+// a rank's own running average (no collective); the same as rth_app_frame outside a process group
+const float* rth_app_local_frame(void* h)
+{
+  try { return reinterpret_cast<const float*>(static_cast<Application*>(h)->getRaytracer()->getLocalOutputBufferHost()); }
+  catch (std::exception const& e) { g_error = e.what(); return nullptr; }
+}
 void rth_app_restart(void* h) { static_cast<Application*>(h)->restartAccumulation(); }
 void rth_app_set_composite(void* h, int mode) { static_cast<Application*>(h)->setCompositeMode(mode); }
 double rth_app_benchmark(void* h) { Application* app = static_cast<Application*>(h); app->benchmark(); return app->getLastBenchmarkSeconds(); }

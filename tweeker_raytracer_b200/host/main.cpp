@@ -18,7 +18,8 @@ int main(int argc, char* argv[])
   }
   else
   {
-    const unsigned int spp = (unsigned int)app.getSamplesPerPixel();
+    // samplesSqrt^2 iterations, or this rank's share of them in a process group (render() stops at the local budget)
+    const unsigned int spp = app.getRaytracer()->getSamplesPerPixelLocal();
     while (app.render(1) < spp && app.isValid()) {}
     app.screenshot(true);
     app.screenshot(false);
