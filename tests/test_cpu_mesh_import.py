@@ -126,3 +126,33 @@ def test_obj_normals_from_file_and_render(built, tmp_path):
         hits = ref.trace_closest(rays)
         hit_instances = set(hits["inst"][hits["inst"] != 0xffffffff].tolist())
         assert hit_instances & {2, 3, 4, 5, 6, 7}, hit_instances            # instance 0 = light quad, 1 = floor
+
+
+def test_obj_reader_survives_bad_input(built, tmp_path):
+    """Out-of-range and malformed face corners are skipped with a warning, lines / points / unknown statements are ignored,
+    CRLF line ends and trailing blanks are tolerated, an empty file yields an empty model; nothing crashes."""
+    d = str(tmp_path)
+    with open(os.path.join(d, "bad.obj"), "w", newline="") as f:
+        f.write("# comment\r\nv 0 0 0\r\nv 1 0 0\r\nv 0 1 0\r\nv 1 1 0 \r\n"
+                "l 1 2\r\np 3\r\ns off\r\nbogus statement\r\n"
+                "f 1 2 3\r\n"            # good
+                "f 1 2 9\r\n"            # index out of range
+                "f 1 2\r\n"              # too few corners
+                "f a/b/c 2 3\r\n"        # garbage corner
+                "f 2 4 3 \r\n")          # good, trailing blank
+    with open(os.path.join(d, "empty.obj"), "w") as f:
+        f.write("# nothing here\n")
+    scene = os.path.join(d, "scene_bad.txt")
+    with open(scene, "w") as f:
+        f.write("material default brdf_diffuse\nidentity\npush\nmodel assimp bad.obj\npop\npush\nmodel assimp empty.obj\npop\n"
+                "push\nmodel assimp model.fbx\npop\n")
+    with open(os.path.join(d, "model.fbx"), "w") as f:
+        f.write("not an obj")
+    with host.App(H.write_system(tmp_path, "rtigo3_cornell_box", resolution="16 16", light=0, miss=1), scene, host_only=True) as app:
+        assert app.info.numGeometries == 1 and app.info.numInstances == 1
+        attrs, idx = app.geometry(0)
+        assert idx.shape == (2, 3) and len(attrs) == 6
+        assert np.array_equal(attrs["vertex"][3:], np.array([[1, 0, 0], [1, 1, 0], [0, 1, 0]], dtype=np.float32))
+        assert np.allclose(attrs["normal"], [0, 0, 1])                     # generated: both triangles face +z
+        img = H.oracle_scene(app).render(H.oracle_sys(app), app.info.miss, 16, 16, iter_count=1)
+        assert np.isfinite(img).all()

@@ -199,3 +199,25 @@ def test_candidate_order_with_exact_ties(built, tmp_path):
         # the frame renders (the stochastic test runs on tied candidates without looping)
         img = scene.render(H.oracle_sys(app), app.info.miss, 8, 8, iter_count=2)
         assert np.isfinite(img).all()
+
+
+def test_damaged_picture_files_fall_back_to_the_procedural_pictures(built, tmp_path):
+    """A truncated PNG, a PNG with a wrong signature and an interlaced PNG are rejected by the reader; the Application then uses
+    the procedural picture (the reference would assert)."""
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, size=(9, 7, 4), dtype=np.uint8)
+    good = os.path.join(str(tmp_path), "good.png")
+    _write_png(good, img)
+    data = open(good, "rb").read()
+    cases = {"truncated.png": data[: len(data) // 2], "signature.png": b"\x89PNX" + data[4:], "empty.png": b""}
+    interlaced = bytearray(data)
+    interlaced[28] = 1                                   # IHDR interlace method (offset 8 + 8 + 12)
+    cases["interlaced.png"] = bytes(interlaced)          # (the CRC no longer matches; the reader rejects the method first)
+    for name, blob in cases.items():
+        path = os.path.join(str(tmp_path), name)
+        with open(path, "wb") as f:
+            f.write(blob)
+        with _app(tmp_path, textureAlbedo=path) as app:
+            assert app.picture("albedo").shape == (256, 256, 4), name      # procedural fallback
+    with _app(tmp_path, textureAlbedo=good) as app:
+        assert app.picture("albedo").shape == (9, 7, 4)
