@@ -230,14 +230,15 @@ def test_radiance_hdr_file_round_trip(built, tmp_path):
 
 
 def test_save_system_description_round_trip(built, tmp_path):
-    app = load(tmp_path, name="rtigo3_geometry", resolution="320 180", envRotation=0.25, composite=1)
+    app = load(tmp_path, name="rtigo3_geometry", resolution="320 180", envRotation=0.25, composite=1, textureCutout="./my_slots.png")
     app.set_camera(0.6, 0.4, 35.0, 7.5, (0.5, 1.5, -0.25))
     path = app.save_system(os.path.join(str(tmp_path), "saved_system.txt"))
     assert path and os.path.exists(path)
     text = open(path).read()
     for line in ("strategy 0", "resolution 320 180", "samplesSqrt 16", "miss 1", "light 2", "pathLengths 2 6", "envRotation 0.25",
-                 "camera 0.6 0.4 35 7.5", "center 0.5 1.5 -0.25", "composite 1", "batchIterations 32"):
+                 "camera 0.6 0.4 35 7.5", "center 0.5 1.5 -0.25", "composite 1", "batchIterations 32", "textureCutout ./my_slots.png"):
         assert line in text, line
+    assert "textureAlbedo" not in text          # the reference's hard-coded default is not written out
     again = host.App(path, H.scene_path("rtigo3_geometry"), host_only=True)
     a, b = app.system_data(), again.system_data()
     assert bytes(a) == bytes(b)

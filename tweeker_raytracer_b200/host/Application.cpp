@@ -248,6 +248,8 @@ bool Application::saveSystemDescription(std::string const& filename, std::string
     << "brightness " << m_tonemapperGUI.brightness << '\n';
   if (m_compositeMode) d << "composite " << m_compositeMode << '\n';
   if (m_batch != 1) d << "batchIterations " << m_batch << '\n';
+  if (m_fileAlbedo != "./NVIDIA_Logo.jpg") d << "textureAlbedo " << m_fileAlbedo << '\n';
+  if (m_fileCutout != "./slots_alpha.png") d << "textureCutout " << m_fileCutout << '\n';
   std::string path = filename;
   if (path.empty())
   {
