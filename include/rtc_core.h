@@ -84,6 +84,13 @@ typedef struct {
   uint64_t nodes, tris, instances, rays;
 } rtc_trace_counts;
 
+/* How the ray pool of the traversal kernels (csrc/trace_pool.cuh) spent its passes during launches made with countWork:
+ * passes[p] warp-level passes of phase p and lanes[p] the ray slots they processed (<= 32 per pass), p = 0 node visit,
+ * 1 triangle tests, 2 instance entry, 3 store + fetch.  lanes / (32 * passes) is the SIMD occupancy of the phase. */
+typedef struct {
+  uint64_t passes[4], lanes[4];
+} rtc_pass_stats;
+
 enum { RTC_RAYGEN_FULL_FRAME = 0,      /* __raygen__path_tracer            (raygeneration.cu:167) */
        RTC_RAYGEN_LOCAL_COPY = 1 };    /* __raygen__path_tracer_local_copy (raygeneration.cu:259) */
 
@@ -174,6 +181,8 @@ int rtc_launch_ex(rtc_context* ctx, const rt_SystemData* sys, uint32_t launchWid
 /* Work counters of the launches made with countWork since the last reset: [0] extend (radiance rays), [1] connect (shadow rays). */
 int rtc_launch_counts_get(rtc_context* ctx, rtc_trace_counts out[2]);
 int rtc_launch_counts_reset(rtc_context* ctx);
+/* Pass statistics of the same launches: [0] extend, [1] connect. */
+int rtc_launch_pass_stats_get(rtc_context* ctx, rtc_pass_stats out[2]);
 
 /* Device-side timing on the context stream (CUDA events). */
 int rtc_timer_start(rtc_context* ctx);
@@ -199,6 +208,17 @@ int rtc_generate_primary(rtc_context* ctx, const rt_SystemData* sys, uint32_t la
 
 int rtc_composite(rtc_context* ctx, const rt_CompositorData* args);
 int rtc_tonemap(rtc_context* ctx, const rt_TonemapperParams* params, uint64_t rgba, uint64_t rgb8, uint64_t numPixels);
+
+/*
+ * Roofline denominators measured on this GPU (csrc/probes.cu), for the fractions bench.py reports next to the HBM one
+ * (L2 and FP32 peaks are not in MEASURED_PEAKS.json).  Synchronous.
+ *   rtc_probe_gather: random 16-byte gathers (the access pattern of node / triangle fetches) over a working set of
+ *                     `bytes` (rounded down to a power of two): L2-resident below the L2 size, HBM gathers above it.
+ *   rtc_probe_pipes : mode 0 -> FP32 TFLOP/s of independent FFMA chains; mode 1 -> 1e9 warp instructions issued per
+ *                     second with FFMA and LOP3 alternating (fma pipe + alu pipe), the issue-slot peak.
+ */
+int rtc_probe_gather(rtc_context* ctx, uint64_t bytes, uint32_t loadsPerThread, double* gigabytesPerSecond);
+int rtc_probe_pipes(rtc_context* ctx, int mode, double* rate);
 
 int rtc_stats_get(rtc_context* ctx, rtc_stats* out);   /* synchronises the context stream */
 int rtc_stats_reset(rtc_context* ctx);

@@ -29,6 +29,7 @@ SYMBOLS = [
     "rtc_launch", "rtc_launch_ex", "rtc_launch_counts_get", "rtc_launch_counts_reset", "rtc_timer_start", "rtc_timer_stop",
     "rtc_profile_enable", "rtc_profile_get", "rtc_trace_closest", "rtc_trace_any", "rtc_trace_count", "rtc_generate_primary",
     "rtc_composite", "rtc_tonemap", "rtc_stats_get", "rtc_stats_reset",
+    "rtc_launch_pass_stats_get", "rtc_probe_gather", "rtc_probe_pipes",
 ]
 
 
@@ -44,6 +45,10 @@ class SceneInfo(C.Structure):
 
 class TraceCounts(C.Structure):
     _fields_ = [("nodes", C.c_uint64), ("tris", C.c_uint64), ("instances", C.c_uint64), ("rays", C.c_uint64)]
+
+
+class PassStats(C.Structure):
+    _fields_ = [("passes", C.c_uint64 * 4), ("lanes", C.c_uint64 * 4)]
 
 
 KERNEL_CLASSES = ["generate", "extend", "shade", "connect", "accumulate", "other"]
@@ -106,6 +111,9 @@ def lib():
         L.rtc_composite.argtypes = [C.c_void_p, C.c_void_p]
         L.rtc_tonemap.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]
         L.rtc_stats_get.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.rtc_launch_pass_stats_get.argtypes = [C.c_void_p, C.POINTER(PassStats)]
+        L.rtc_probe_gather.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_double)]
+        L.rtc_probe_pipes.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -250,6 +258,25 @@ class Context:
         out = (TraceCounts * 2)()
         _check(self.L.rtc_launch_counts_get(self.h, out))
         return out[0], out[1]
+
+    def launch_pass_stats(self):
+        """(extend, connect): {phase: (passes, slots processed, mean lanes per pass)} of the ray pool during count_work launches."""
+        out = (PassStats * 2)()
+        _check(self.L.rtc_launch_pass_stats_get(self.h, out))
+        names = ["node", "triangle", "instance", "fetch"]
+        return tuple({n: (int(o.passes[k]), int(o.lanes[k]), o.lanes[k] / max(o.passes[k], 1)) for k, n in enumerate(names)} for o in out)
+
+    def probe_gather(self, nbytes, loads_per_thread=256):
+        """GB/s of random 16-byte gathers over a working set of nbytes (L2-resident when it fits)."""
+        v = C.c_double(0.0)
+        _check(self.L.rtc_probe_gather(self.h, nbytes, loads_per_thread, C.byref(v)))
+        return v.value
+
+    def probe_pipes(self, mode):
+        """mode 0: FP32 TFLOP/s (FFMA); mode 1: 1e9 warp instructions per second (FFMA + LOP3 alternating)."""
+        v = C.c_double(0.0)
+        _check(self.L.rtc_probe_pipes(self.h, mode, C.byref(v)))
+        return v.value
 
     def launch_counts_reset(self):
         _check(self.L.rtc_launch_counts_reset(self.h))

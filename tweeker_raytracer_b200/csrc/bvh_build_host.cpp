@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -40,6 +41,7 @@ struct Builder
 {
   const PrimBox* prims;
   uint32_t leafMax = kLeafMax;
+  float splitCost = 1.2f;           // cost of one more node level relative to one triangle test (SAH termination of small leaves)
   std::vector<uint32_t> order;
   std::vector<BinNode> nodes;
 
@@ -90,7 +92,7 @@ struct Builder
     if (count <= leafMax)
     {
       const float leafCost = box.halfArea() * (float)count;
-      if (bestAxis < 0 || bestCost + 1.2f * box.halfArea() >= leafCost) return idx;
+      if (bestAxis < 0 || bestCost + splitCost * box.halfArea() >= leafCost) return idx;
     }
     uint32_t mid;
     if (bestAxis < 0)
@@ -229,7 +231,7 @@ struct Emitter
 
 } // namespace
 
-void build_wide_bvh_host(const PrimBox* prims, uint32_t numPrims, WideBvh& out)
+void build_wide_bvh_host(const PrimBox* prims, uint32_t numPrims, WideBvh& out, uint32_t leafMax)
 {
   out.nodes.clear(); out.primOrder.clear();
   for (int k = 0; k < 3; ++k) { out.lo[k] = 0.0f; out.hi[k] = 0.0f; }
@@ -243,6 +245,7 @@ void build_wide_bvh_host(const PrimBox* prims, uint32_t numPrims, WideBvh& out)
     return;
   }
   Builder b; b.prims = prims;
+  b.leafMax = std::min(std::max(leafMax, 1u), kLeafMax);
   b.order.resize(numPrims);
   for (uint32_t i = 0; i < numPrims; ++i) b.order[i] = i;
   b.nodes.reserve(2 * (size_t)numPrims);

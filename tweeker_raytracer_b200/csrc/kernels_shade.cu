@@ -13,7 +13,7 @@
 #include "shade.cuh"
 // the primary-ray extend kernel generates its rays with the shading arithmetic of this translation unit (see ExtendPrimary)
 #define RTC_STACK_OVERFLOW_COUNTER g_rtcStackOverflowsPrimary
-#include "trace.cuh"
+#include "trace_pool.cuh"
 
 #include <cstdlib>
 
@@ -200,8 +200,7 @@ k_generate(const __grid_constant__ WfArgs a, uint32_t* __restrict__ queue, uint3
 struct ExtendPrimary
 {
   WfArgs a;
-  uint32_t path;
-  __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d)
+  __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d, uint32_t& path) const
   {
     path = i;
     const uint32_t pixelsPerIter = a.launchWidth * a.launchHeight;
@@ -218,9 +217,8 @@ struct ExtendPrimary
     d = make_float4(wi.x, wi.y, wi.z, RT_DEFAULT_MAX);
     return true;
   }
-  template <class T> __device__ __forceinline__ void store(uint32_t, const T& tr) const
+  __device__ __forceinline__ void store(uint32_t path, const TraceHit& h) const
   {
-    const TraceHit h = tr.result();
     __stcs(a.wf.hit + path, make_float4(h.t, h.u, h.v, __uint_as_float(h.prim)));
     __stcs(a.wf.hitInst + path, h.inst);
   }
@@ -230,14 +228,35 @@ constexpr int kPrimaryBlock = 128;
 #ifndef RTC_TRACE_MIN_BLOCKS
 #define RTC_TRACE_MIN_BLOCKS 8
 #endif
+#ifndef RTC_POOL_BLOCKS
+#define RTC_POOL_BLOCKS 4
+#endif
 
+#if RTC_TRACE_POOL
+template <bool COUNT>
+__global__ void __launch_bounds__(kPrimaryBlock, RTC_POOL_BLOCKS)
+k_extend_primary(const SceneDesc sc, const ExtendPrimary policy, uint32_t n, uint32_t* __restrict__ cursor, unsigned long long* __restrict__ counts,
+                 uint2* __restrict__ overflow)
+{
+  extern __shared__ uint32_t poolWords[];
+  const uint32_t warp = threadIdx.x >> 5;
+  const size_t warpGlobal = (size_t)blockIdx.x * (kPrimaryBlock / 32) + warp;
+  rtpool::trace_pool<false, COUNT, false>(sc, n, cursor, policy, poolWords + warp * rtpool::warp_words(false, false), overflow + warpGlobal * rtpool::kOverflowPerWarp, counts);
+}
+constexpr int kPrimaryBlocksPerSM = RTC_POOL_BLOCKS;
+constexpr size_t kPrimarySmem = (size_t)(kPrimaryBlock / 32) * rtpool::warp_bytes(false, false);
+#else
 template <bool COUNT>
 __global__ void __launch_bounds__(kPrimaryBlock, RTC_TRACE_MIN_BLOCKS)
-k_extend_primary(const SceneDesc sc, ExtendPrimary policy, uint32_t n, uint32_t* __restrict__ cursor, unsigned long long* __restrict__ counts)
+k_extend_primary(const SceneDesc sc, ExtendPrimary policy, uint32_t n, uint32_t* __restrict__ cursor, unsigned long long* __restrict__ counts,
+                 uint2* __restrict__)
 {
-  __shared__ uint2 smem[RTC_SM_STACK * kPrimaryBlock + (11 * kPrimaryBlock + 1) / 2];
+  __shared__ uint2 smem[RTC_SM_STACK * kPrimaryBlock + (RTC_SM_RAY_WORDS * kPrimaryBlock + 1) / 2];
   trace_stream<false, COUNT, kPrimaryBlock, false>(sc, n, cursor, policy, smem, counts);
 }
+constexpr int kPrimaryBlocksPerSM = RTC_TRACE_MIN_BLOCKS;
+constexpr size_t kPrimarySmem = 0;
+#endif
 
 __device__ __forceinline__ float3 xf_vector(const float4 r0, const float4 r1, const float4 r2, float3 v)
 {
@@ -1062,10 +1081,16 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
       if (primary)
       {
         if (int rc = profile_begin(ctx, RTC_KERNEL_EXTEND)) return rc;
-        ExtendPrimary policy = { a, 0u };
-        const int gridTrace = ctx->numSMs * RTC_TRACE_MIN_BLOCKS;
-        if (countWork) k_extend_primary<true><<<gridTrace, kPrimaryBlock, 0, ctx->stream>>>(scene->desc, policy, a.numPaths, cnt + 128, ctx->d_launchCounts);
-        else           k_extend_primary<false><<<gridTrace, kPrimaryBlock, 0, ctx->stream>>>(scene->desc, policy, a.numPaths, cnt + 128, nullptr);
+        ExtendPrimary policy = { a };
+        const int gridTrace = ctx->numSMs * kPrimaryBlocksPerSM;
+        uint2* overflow = nullptr;
+#if RTC_TRACE_POOL
+        if (int rc = ensure_pool_scratch(ctx, (size_t)gridTrace * (kPrimaryBlock / 32), &overflow)) return rc;
+        RTC_CUDA(cudaFuncSetAttribute(k_extend_primary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrimarySmem));
+        RTC_CUDA(cudaFuncSetAttribute(k_extend_primary<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrimarySmem));
+#endif
+        if (countWork) k_extend_primary<true><<<gridTrace, kPrimaryBlock, kPrimarySmem, ctx->stream>>>(scene->desc, policy, a.numPaths, cnt + 128, ctx->d_launchCounts, overflow);
+        else           k_extend_primary<false><<<gridTrace, kPrimaryBlock, kPrimarySmem, ctx->stream>>>(scene->desc, policy, a.numPaths, cnt + 128, nullptr, overflow);
         ctx->kernelLaunches++;
         RTC_CUDA(cudaGetLastError());
         if (int rc = profile_end(ctx)) return rc;

@@ -4,28 +4,30 @@
 // resident slot, rays handed out through a device-side cursor.
 // Built for sm_100a with FMA contraction ON: only the box tests may contract; the intersector in
 // trace.cuh pins its own rounding with intrinsics.
-#include "trace.cuh"
+#include "trace_pool.cuh"
 
 #ifndef RTC_TRACE_MIN_BLOCKS
-#define RTC_TRACE_MIN_BLOCKS 8      // resident CTAs per SM the traversal kernels are compiled for (register budget) and launched with
+#define RTC_TRACE_MIN_BLOCKS 8      // one ray per lane: resident CTAs per SM the kernels are compiled for (register budget) and launched with
+#endif
+#ifndef RTC_POOL_BLOCKS
+#define RTC_POOL_BLOCKS 4           // ray pool: resident CTAs (4 warps each) per SM; bounded by shared memory (rtpool::kWarpBytes per warp)
 #endif
 
 namespace {
 
 constexpr int kTraceBlock = 128;
 
-// ---- ray sources / hit sinks -------------------------------------------------------------------------------------
+// ---- ray sources / hit sinks (stateless: the per-ray word `tag` travels with the ray) -------------------------------
 
 // rtc_trace_closest: AoS rays in, rtc_hit out
 struct QueryClosest
 {
   const float4* __restrict__ rays; rtc_hit* __restrict__ hits;
-  __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d) const { o = __ldg(rays + 2 * (size_t)i); d = __ldg(rays + 2 * (size_t)i + 1); return true; }
-  template <class T> __device__ __forceinline__ void store(uint32_t i, const T& tr) const
+  __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d, uint32_t& tag) const { tag = i; o = __ldg(rays + 2 * (size_t)i); d = __ldg(rays + 2 * (size_t)i + 1); return true; }
+  __device__ __forceinline__ void store(uint32_t tag, const TraceHit& h) const
   {
-    const TraceHit h = tr.result();
     rtc_hit out; out.t = h.t; out.u = h.u; out.v = h.v; out.inst = h.inst; out.prim = h.prim;
-    hits[i] = out;
+    hits[tag] = out;
   }
 };
 
@@ -33,16 +35,16 @@ struct QueryClosest
 struct QueryAny
 {
   const float4* __restrict__ rays; uint32_t* __restrict__ occluded;
-  __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d) const { o = __ldg(rays + 2 * (size_t)i); d = __ldg(rays + 2 * (size_t)i + 1); return true; }
-  template <class T> __device__ __forceinline__ void store(uint32_t i, const T& tr) const { occluded[i] = tr.found() ? 1u : 0u; }
+  __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d, uint32_t& tag) const { tag = i; o = __ldg(rays + 2 * (size_t)i); d = __ldg(rays + 2 * (size_t)i + 1); return true; }
+  __device__ __forceinline__ void store(uint32_t tag, const TraceHit& h) const { occluded[tag] = h.inst != 0xffffffffu ? 1u : 0u; }
 };
 
 // rtc_trace_count: rays in, nothing out (the counters are the result)
 struct QueryCount
 {
   const float4* __restrict__ rays;
-  __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d) const { o = __ldg(rays + 2 * (size_t)i); d = __ldg(rays + 2 * (size_t)i + 1); return true; }
-  template <class T> __device__ __forceinline__ void store(uint32_t, const T&) const {}
+  __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d, uint32_t& tag) const { tag = i; o = __ldg(rays + 2 * (size_t)i); d = __ldg(rays + 2 * (size_t)i + 1); return true; }
+  __device__ __forceinline__ void store(uint32_t, const TraceHit&) const {}
 };
 
 // extend: queue of path ids -> SoA radiance rays; hit record per path (raygeneration.cu:84-89 optixTrace RADIANCE)
@@ -50,11 +52,9 @@ struct ExtendPaths
 {
   const uint32_t* __restrict__ queue; const float4* __restrict__ rayOrg; const float4* __restrict__ rayDir;
   float4* __restrict__ hit; uint32_t* __restrict__ hitInst;
-  uint32_t path;
-  __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d) { path = queue[i]; o = rayOrg[path]; d = rayDir[path]; return true; }
-  template <class T> __device__ __forceinline__ void store(uint32_t, const T& tr) const
+  __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d, uint32_t& path) const { path = queue[i]; o = rayOrg[path]; d = rayDir[path]; return true; }
+  __device__ __forceinline__ void store(uint32_t path, const TraceHit& h) const
   {
-    const TraceHit h = tr.result();
     __stcs(hit + path, make_float4(h.t, h.u, h.v, __uint_as_float(h.prim)));
     __stcs(hitInst + path, h.inst);
   }
@@ -66,11 +66,10 @@ struct ConnectPaths
 {
   const uint32_t* __restrict__ queue; const float4* __restrict__ shadowOrg; const float4* __restrict__ shadowDir;
   const float4* __restrict__ contrib; float4* __restrict__ radiance;
-  uint32_t path;
-  __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d) { path = queue[i]; o = shadowOrg[path]; d = shadowDir[path]; return true; }
-  template <class T> __device__ __forceinline__ void store(uint32_t, const T& tr) const
+  __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d, uint32_t& path) const { path = queue[i]; o = shadowOrg[path]; d = shadowDir[path]; return true; }
+  __device__ __forceinline__ void store(uint32_t path, const TraceHit& h) const
   {
-    if (!tr.found())
+    if (h.inst == 0xffffffffu)
     {
       const float4 c = __ldcs(contrib + path);
       float4 L = __ldcs(radiance + path);
@@ -90,17 +89,19 @@ struct ExtendPathsAfter
 {
   const uint32_t* __restrict__ queue; const float4* __restrict__ rayOrg; const float4* __restrict__ rayDir;
   float4* __restrict__ hit; uint32_t* __restrict__ hitInst;
-  uint32_t path; float4 prev; uint32_t prevInst;
-  __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d)
+  __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d, uint32_t& path) const
   {
-    path = queue[i]; o = rayOrg[path]; d = rayDir[path]; prev = hit[path]; prevInst = hitInst[path];
-    o.w = fmaxf(o.w, __uint_as_float(__float_as_uint(prev.x) - 1u));      // prev.x > tmin > 0
+    path = queue[i]; o = rayOrg[path]; d = rayDir[path];
+    o.w = fmaxf(o.w, __uint_as_float(__float_as_uint(hit[path].x) - 1u));      // previous t > tmin > 0
     return true;
   }
-  __device__ __forceinline__ void load_skip(float& t, uint32_t& inst, uint32_t& prim) const { t = prev.x; inst = prevInst; prim = __float_as_uint(prev.w); }
-  template <class T> __device__ __forceinline__ void store(uint32_t, const T& tr) const
+  __device__ __forceinline__ void skip_key(uint32_t path, float& t, uint32_t& inst, uint32_t& prim) const
   {
-    const TraceHit h = tr.result();
+    const float4 prev = hit[path];
+    t = prev.x; inst = hitInst[path]; prim = __float_as_uint(prev.w);
+  }
+  __device__ __forceinline__ void store(uint32_t path, const TraceHit& h) const
+  {
     hit[path] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
     hitInst[path] = h.inst;
   }
@@ -112,17 +113,19 @@ struct ConnectClosest
 {
   const uint32_t* __restrict__ queue; const float4* __restrict__ shadowOrg; const float4* __restrict__ shadowDir;
   float4* __restrict__ hit; uint32_t* __restrict__ hitInst;
-  uint32_t path; float4 prev; uint32_t prevInst;
-  __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d)
+  __device__ __forceinline__ bool load(uint32_t i, float4& o, float4& d, uint32_t& path) const
   {
     path = queue[i]; o = shadowOrg[path]; d = shadowDir[path];
-    if (AFTER) { prev = hit[path]; prevInst = hitInst[path]; o.w = fmaxf(o.w, __uint_as_float(__float_as_uint(prev.x) - 1u)); }
+    if (AFTER) o.w = fmaxf(o.w, __uint_as_float(__float_as_uint(hit[path].x) - 1u));
     return true;
   }
-  __device__ __forceinline__ void load_skip(float& t, uint32_t& inst, uint32_t& prim) const { t = prev.x; inst = prevInst; prim = __float_as_uint(prev.w); }
-  template <class T> __device__ __forceinline__ void store(uint32_t, const T& tr) const
+  __device__ __forceinline__ void skip_key(uint32_t path, float& t, uint32_t& inst, uint32_t& prim) const
   {
-    const TraceHit h = tr.result();
+    const float4 prev = hit[path];
+    t = prev.x; inst = hitInst[path]; prim = __float_as_uint(prev.w);
+  }
+  __device__ __forceinline__ void store(uint32_t path, const TraceHit& h) const
+  {
     hit[path] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
     hitInst[path] = h.inst;
   }
@@ -130,19 +133,71 @@ struct ConnectClosest
 
 // ---- kernels ---------------------------------------------------------------------------------------------------------
 
+#if RTC_TRACE_POOL
+
+template <bool ANY, bool COUNT, class Policy, bool SKIP = false>
+__global__ void __launch_bounds__(kTraceBlock, RTC_POOL_BLOCKS)
+k_trace(const SceneDesc sc, const Policy policy, uint32_t n, const uint32_t* __restrict__ nPtr, uint32_t* __restrict__ cursor,
+        unsigned long long* __restrict__ counts, uint2* __restrict__ overflow)
+{
+  extern __shared__ uint32_t poolWords[];
+  const uint32_t count = nPtr ? *nPtr : n;      // the wavefront keeps its queue lengths on the device
+  const uint32_t warp = threadIdx.x >> 5;
+  const size_t warpGlobal = (size_t)blockIdx.x * (kTraceBlock / 32) + warp;
+  rtpool::trace_pool<ANY, COUNT, SKIP>(sc, count, cursor, policy, poolWords + warp * rtpool::warp_words(ANY, SKIP), overflow + warpGlobal * rtpool::kOverflowPerWarp, counts);
+}
+
+inline int persistent_grid(const rtc_context* ctx) { return ctx->numSMs * RTC_POOL_BLOCKS; }
+constexpr size_t trace_smem(bool any, bool skip) { return (size_t)(kTraceBlock / 32) * rtpool::warp_bytes(any, skip); }
+
+#else
+
 template <bool ANY, bool COUNT, class Policy, bool SKIP = false>
 __global__ void __launch_bounds__(kTraceBlock, SKIP ? 4 : RTC_TRACE_MIN_BLOCKS)
 k_trace(const SceneDesc sc, Policy policy, uint32_t n, const uint32_t* __restrict__ nPtr, uint32_t* __restrict__ cursor,
-        unsigned long long* __restrict__ counts)
+        unsigned long long* __restrict__ counts, uint2* __restrict__)
 {
-  __shared__ uint2 smem[RTC_SM_STACK * kTraceBlock + (11 * kTraceBlock + 1) / 2];     // stack columns, then eleven float columns (trace.cuh smRay)
-  const uint32_t count = nPtr ? *nPtr : n;      // the wavefront keeps its queue lengths on the device
+  __shared__ uint2 smem[RTC_SM_STACK * kTraceBlock + (RTC_SM_RAY_WORDS * kTraceBlock + 1) / 2];     // stack columns, then the float columns (trace.cuh smRay)
+  const uint32_t count = nPtr ? *nPtr : n;
   trace_stream<ANY, COUNT, kTraceBlock, SKIP>(sc, count, cursor, policy, smem, counts);
 }
 
 inline int persistent_grid(const rtc_context* ctx) { return ctx->numSMs * RTC_TRACE_MIN_BLOCKS; }
+constexpr size_t trace_smem(bool, bool) { return 0; }
+
+#endif
+
+template <bool ANY, bool COUNT, class Policy, bool SKIP>
+int launch_k_trace(rtc_context* ctx, const SceneDesc* scene, const Policy& p, uint32_t n, const uint32_t* nPtr, uint32_t* cursor, unsigned long long* counts)
+{
+  auto kernel = k_trace<ANY, COUNT, Policy, SKIP>;
+  const int grid = persistent_grid(ctx);
+  uint2* overflow = nullptr;
+#if RTC_TRACE_POOL
+  if (int rc = ensure_pool_scratch(ctx, (size_t)grid * (kTraceBlock / 32), &overflow)) return rc;
+  RTC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem(ANY, SKIP)));
+#endif
+  kernel<<<grid, kTraceBlock, trace_smem(ANY, SKIP), ctx->stream>>>(*scene, p, n, nPtr, cursor, counts, overflow);
+  ctx->kernelLaunches++;
+  RTC_CUDA(cudaGetLastError());
+  return 0;
+}
 
 } // namespace
+
+// Global scratch of the ray pool: the part of every slot's traversal stack that does not fit in shared memory.
+int ensure_pool_scratch(rtc_context* ctx, size_t warps, uint2** out)
+{
+  const size_t need = warps * rtpool::kOverflowPerWarp * sizeof(uint2);
+  if (ctx->poolScratchBytes < need)
+  {
+    if (ctx->d_poolScratch) { RTC_CUDA(cudaStreamSynchronize(ctx->stream)); RTC_CUDA(cudaFree(ctx->d_poolScratch)); ctx->d_poolScratch = nullptr; ctx->poolScratchBytes = 0; }
+    RTC_CUDA(cudaMalloc(&ctx->d_poolScratch, need));
+    ctx->poolScratchBytes = need;
+  }
+  *out = static_cast<uint2*>(ctx->d_poolScratch);
+  return 0;
+}
 
 int launch_trace_closest(rtc_context* ctx, const SceneDesc* scene, const rtc_ray* rays, uint64_t n, rtc_hit* hits)
 {
@@ -150,10 +205,7 @@ int launch_trace_closest(rtc_context* ctx, const SceneDesc* scene, const rtc_ray
   if (n > 0xfffffff0ull) RTC_FAIL("more than 2^32 rays in one call");
   RTC_CUDA(cudaMemsetAsync(ctx->d_cursor, 0, sizeof(uint32_t), ctx->stream));
   QueryClosest p = { reinterpret_cast<const float4*>(rays), hits };
-  k_trace<false, false, QueryClosest><<<persistent_grid(ctx), kTraceBlock, 0, ctx->stream>>>(*scene, p, (uint32_t)n, nullptr, ctx->d_cursor, nullptr);
-  ctx->kernelLaunches++;
-  RTC_CUDA(cudaGetLastError());
-  return 0;
+  return launch_k_trace<false, false, QueryClosest, false>(ctx, scene, p, (uint32_t)n, nullptr, ctx->d_cursor, nullptr);
 }
 
 int launch_trace_any(rtc_context* ctx, const SceneDesc* scene, const rtc_ray* rays, uint64_t n, uint32_t* occluded)
@@ -162,10 +214,7 @@ int launch_trace_any(rtc_context* ctx, const SceneDesc* scene, const rtc_ray* ra
   if (n > 0xfffffff0ull) RTC_FAIL("more than 2^32 rays in one call");
   RTC_CUDA(cudaMemsetAsync(ctx->d_cursor, 0, sizeof(uint32_t), ctx->stream));
   QueryAny p = { reinterpret_cast<const float4*>(rays), occluded };
-  k_trace<true, false, QueryAny><<<persistent_grid(ctx), kTraceBlock, 0, ctx->stream>>>(*scene, p, (uint32_t)n, nullptr, ctx->d_cursor, nullptr);
-  ctx->kernelLaunches++;
-  RTC_CUDA(cudaGetLastError());
-  return 0;
+  return launch_k_trace<true, false, QueryAny, false>(ctx, scene, p, (uint32_t)n, nullptr, ctx->d_cursor, nullptr);
 }
 
 int launch_trace_count(rtc_context* ctx, const SceneDesc* scene, const rtc_ray* rays, uint64_t n, int anyHit, unsigned long long* d_counts)
@@ -174,33 +223,26 @@ int launch_trace_count(rtc_context* ctx, const SceneDesc* scene, const rtc_ray* 
   if (n > 0xfffffff0ull) RTC_FAIL("more than 2^32 rays in one call");
   RTC_CUDA(cudaMemsetAsync(ctx->d_cursor, 0, sizeof(uint32_t), ctx->stream));
   QueryCount p = { reinterpret_cast<const float4*>(rays) };
-  if (anyHit) k_trace<true, true, QueryCount><<<persistent_grid(ctx), kTraceBlock, 0, ctx->stream>>>(*scene, p, (uint32_t)n, nullptr, ctx->d_cursor, d_counts);
-  else        k_trace<false, true, QueryCount><<<persistent_grid(ctx), kTraceBlock, 0, ctx->stream>>>(*scene, p, (uint32_t)n, nullptr, ctx->d_cursor, d_counts);
-  ctx->kernelLaunches++;
-  RTC_CUDA(cudaGetLastError());
-  return 0;
+  if (anyHit) return launch_k_trace<true, true, QueryCount, false>(ctx, scene, p, (uint32_t)n, nullptr, ctx->d_cursor, d_counts);
+  return launch_k_trace<false, true, QueryCount, false>(ctx, scene, p, (uint32_t)n, nullptr, ctx->d_cursor, d_counts);
 }
 
 int launch_extend(rtc_context* ctx, const SceneDesc* scene, const WavefrontBuffers& wf, const uint32_t* queue, const uint32_t* count,
                   uint32_t* cursor, bool countWork)
 {
   if (int rc = profile_begin(ctx, RTC_KERNEL_EXTEND)) return rc;
-  ExtendPaths p = { queue, wf.rayOrg, wf.rayDir, wf.hit, wf.hitInst, 0u };
-  if (countWork) k_trace<false, true, ExtendPaths><<<persistent_grid(ctx), kTraceBlock, 0, ctx->stream>>>(*scene, p, 0u, count, cursor, ctx->d_launchCounts);
-  else           k_trace<false, false, ExtendPaths><<<persistent_grid(ctx), kTraceBlock, 0, ctx->stream>>>(*scene, p, 0u, count, cursor, nullptr);
-  ctx->kernelLaunches++;
-  RTC_CUDA(cudaGetLastError());
+  ExtendPaths p = { queue, wf.rayOrg, wf.rayDir, wf.hit, wf.hitInst };
+  if (int rc = countWork ? launch_k_trace<false, true, ExtendPaths, false>(ctx, scene, p, 0u, count, cursor, ctx->d_launchCounts)
+                         : launch_k_trace<false, false, ExtendPaths, false>(ctx, scene, p, 0u, count, cursor, nullptr)) return rc;
   return profile_end(ctx);
 }
 
 int launch_connect(rtc_context* ctx, const SceneDesc* scene, const WavefrontBuffers& wf, const uint32_t* count, uint32_t* cursor, bool countWork)
 {
   if (int rc = profile_begin(ctx, RTC_KERNEL_CONNECT)) return rc;
-  ConnectPaths p = { wf.shadowQueue, wf.shadowOrg, wf.shadowDir, wf.shadowContrib, wf.radiance, 0u };
-  if (countWork) k_trace<true, true, ConnectPaths><<<persistent_grid(ctx), kTraceBlock, 0, ctx->stream>>>(*scene, p, 0u, count, cursor, ctx->d_launchCounts + 4);
-  else           k_trace<true, false, ConnectPaths><<<persistent_grid(ctx), kTraceBlock, 0, ctx->stream>>>(*scene, p, 0u, count, cursor, nullptr);
-  ctx->kernelLaunches++;
-  RTC_CUDA(cudaGetLastError());
+  ConnectPaths p = { wf.shadowQueue, wf.shadowOrg, wf.shadowDir, wf.shadowContrib, wf.radiance };
+  if (int rc = countWork ? launch_k_trace<true, true, ConnectPaths, false>(ctx, scene, p, 0u, count, cursor, ctx->d_launchCounts + kTraceCountWords)
+                         : launch_k_trace<true, false, ConnectPaths, false>(ctx, scene, p, 0u, count, cursor, nullptr)) return rc;
   return profile_end(ctx);
 }
 
@@ -208,11 +250,9 @@ int launch_connect(rtc_context* ctx, const SceneDesc* scene, const WavefrontBuff
 int launch_extend_after(rtc_context* ctx, const SceneDesc* scene, const WavefrontBuffers& wf, const uint32_t* queue, const uint32_t* count, uint32_t* cursor)
 {
   if (int rc = profile_begin(ctx, RTC_KERNEL_EXTEND)) return rc;
-  ExtendPathsAfter p = { queue, wf.rayOrg, wf.rayDir, wf.hit, wf.hitInst, 0u, make_float4(0.f, 0.f, 0.f, 0.f), 0u };
+  ExtendPathsAfter p = { queue, wf.rayOrg, wf.rayDir, wf.hit, wf.hitInst };
   RTC_CUDA(cudaMemsetAsync(cursor, 0, sizeof(uint32_t), ctx->stream));
-  k_trace<false, false, ExtendPathsAfter, true><<<persistent_grid(ctx), kTraceBlock, 0, ctx->stream>>>(*scene, p, 0u, count, cursor, nullptr);
-  ctx->kernelLaunches++;
-  RTC_CUDA(cudaGetLastError());
+  if (int rc = launch_k_trace<false, false, ExtendPathsAfter, true>(ctx, scene, p, 0u, count, cursor, nullptr)) return rc;
   return profile_end(ctx);
 }
 
@@ -224,16 +264,14 @@ int launch_connect_closest(rtc_context* ctx, const SceneDesc* scene, const Wavef
   RTC_CUDA(cudaMemsetAsync(cursor, 0, sizeof(uint32_t), ctx->stream));
   if (after)
   {
-    ConnectClosest<true> p = { queue, wf.shadowOrg, wf.shadowDir, wf.hit, wf.hitInst, 0u, make_float4(0.f, 0.f, 0.f, 0.f), 0u };
-    k_trace<false, false, ConnectClosest<true>, true><<<persistent_grid(ctx), kTraceBlock, 0, ctx->stream>>>(*scene, p, 0u, count, cursor, nullptr);
+    ConnectClosest<true> p = { queue, wf.shadowOrg, wf.shadowDir, wf.hit, wf.hitInst };
+    if (int rc = launch_k_trace<false, false, ConnectClosest<true>, true>(ctx, scene, p, 0u, count, cursor, nullptr)) return rc;
   }
   else
   {
-    ConnectClosest<false> p = { queue, wf.shadowOrg, wf.shadowDir, wf.hit, wf.hitInst, 0u, make_float4(0.f, 0.f, 0.f, 0.f), 0u };
-    k_trace<false, false, ConnectClosest<false>, false><<<persistent_grid(ctx), kTraceBlock, 0, ctx->stream>>>(*scene, p, 0u, count, cursor, nullptr);
+    ConnectClosest<false> p = { queue, wf.shadowOrg, wf.shadowDir, wf.hit, wf.hitInst };
+    if (int rc = launch_k_trace<false, false, ConnectClosest<false>, false>(ctx, scene, p, 0u, count, cursor, nullptr)) return rc;
   }
-  ctx->kernelLaunches++;
-  RTC_CUDA(cudaGetLastError());
   return profile_end(ctx);
 }
 

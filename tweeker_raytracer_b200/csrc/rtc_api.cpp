@@ -140,8 +140,8 @@ int rtc_context_create(int deviceOrdinal, rtc_context** out)
   RTC_CUDA(cudaMalloc(&ctx->d_stats, 8 * sizeof(uint64_t)));
   RTC_CUDA(cudaMemset(ctx->d_stats, 0, 8 * sizeof(uint64_t)));
   RTC_CUDA(cudaMalloc(&ctx->d_cursor, 4 * sizeof(uint32_t)));
-  RTC_CUDA(cudaMalloc(&ctx->d_launchCounts, 8 * sizeof(unsigned long long)));
-  RTC_CUDA(cudaMemset(ctx->d_launchCounts, 0, 8 * sizeof(unsigned long long)));
+  RTC_CUDA(cudaMalloc(&ctx->d_launchCounts, 3 * kTraceCountWords * sizeof(unsigned long long)));
+  RTC_CUDA(cudaMemset(ctx->d_launchCounts, 0, 3 * kTraceCountWords * sizeof(unsigned long long)));
   *out = ctx;
   return 0;
 }
@@ -159,6 +159,7 @@ int rtc_context_destroy(rtc_context* ctx)
   cudaFree(ctx->d_stats);
   cudaFree(ctx->d_launchCounts);
   cudaFree(ctx->d_cursor);
+  cudaFree(ctx->d_poolScratch);
   for (rtc_context::ProfileSpan& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
   cudaEventDestroy(ctx->evA); cudaEventDestroy(ctx->evB);
@@ -437,7 +438,7 @@ int rtc_ias_build(rtc_context* ctx, const rtc_instance_desc* instances, uint32_t
     if (g.numTris == 0) { for (int k = 0; k < 3; ++k) { b.lo[k] = 0.0f; b.hi[k] = 0.0f; } }
   }
   WideBvh bvh;
-  build_wide_bvh_host(boxes.data(), numInstances, bvh);
+  build_wide_bvh_host(boxes.data(), numInstances, bvh, getenv("RTC_TLAS_LEAF") ? (uint32_t)atoi(getenv("RTC_TLAS_LEAF")) : 1u);
 
   auto upload = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
     cudaError_t e = cudaMalloc(dst, bytes ? bytes : 16);
@@ -591,17 +592,33 @@ int rtc_launch_counts_get(rtc_context* ctx, rtc_trace_counts out[2])
 {
   if (!out) RTC_FAIL("out is null");
   RTC_CUDA(cudaSetDevice(ctx->device));
-  unsigned long long h[8];
+  unsigned long long h[2 * kTraceCountWords];
   RTC_CUDA(cudaMemcpyAsync(h, ctx->d_launchCounts, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
   RTC_CUDA(cudaStreamSynchronize(ctx->stream));
-  for (int k = 0; k < 2; ++k) { out[k].nodes = h[4 * k]; out[k].tris = h[4 * k + 1]; out[k].instances = h[4 * k + 2]; out[k].rays = h[4 * k + 3]; }
+  for (int k = 0; k < 2; ++k)
+  {
+    const unsigned long long* c = h + kTraceCountWords * k;
+    out[k].nodes = c[0]; out[k].tris = c[1]; out[k].instances = c[2]; out[k].rays = c[3];
+  }
+  return 0;
+}
+
+int rtc_launch_pass_stats_get(rtc_context* ctx, rtc_pass_stats out[2])
+{
+  if (!out) RTC_FAIL("out is null");
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  unsigned long long h[2 * kTraceCountWords];
+  RTC_CUDA(cudaMemcpyAsync(h, ctx->d_launchCounts, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  RTC_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < 2; ++k)
+    for (int j = 0; j < 4; ++j) { out[k].passes[j] = h[kTraceCountWords * k + 4 + j]; out[k].lanes[j] = h[kTraceCountWords * k + 8 + j]; }
   return 0;
 }
 
 int rtc_launch_counts_reset(rtc_context* ctx)
 {
   RTC_CUDA(cudaSetDevice(ctx->device));
-  RTC_CUDA(cudaMemsetAsync(ctx->d_launchCounts, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  RTC_CUDA(cudaMemsetAsync(ctx->d_launchCounts, 0, 2 * kTraceCountWords * sizeof(unsigned long long), ctx->stream));
   return 0;
 }
 
@@ -685,8 +702,8 @@ int rtc_trace_count(rtc_context* ctx, uint64_t topObject, uint64_t rays, uint64_
   if (!s) RTC_FAIL("unknown topObject");
   if (!out) RTC_FAIL("out is null");
   RTC_CUDA(cudaSetDevice(ctx->device));
-  unsigned long long* d = reinterpret_cast<unsigned long long*>(ctx->d_stats + 4);
-  RTC_CUDA(cudaMemsetAsync(d, 0, 4 * sizeof(uint64_t), ctx->stream));
+  unsigned long long* d = ctx->d_launchCounts + 2 * kTraceCountWords;
+  RTC_CUDA(cudaMemsetAsync(d, 0, kTraceCountWords * sizeof(uint64_t), ctx->stream));
   if (int rc = launch_trace_count(ctx, &s->desc, (const rtc_ray*)(uintptr_t)rays, numRays, anyHit, d)) return rc;
   uint64_t h[4];
   RTC_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));

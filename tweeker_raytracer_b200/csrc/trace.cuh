@@ -15,6 +15,9 @@
 #ifndef RTC_I2F_AXES
 #define RTC_I2F_AXES 1            // number of axes (0, 1 or 2; swept with tools/sweep_i2f.sh: 1 and 2 are +0.4 %) whose plane bytes are converted by I2F.U8 instead of PRMT
 #endif
+#ifndef RTC_RESTORE_WORLD
+#define RTC_RESTORE_WORLD 1       // world-space box constants restored from shared memory when an instance is left
+#endif
 #ifndef RTC_FETCH_THRESHOLD
 #define RTC_FETCH_THRESHOLD 8     // refill a warp when at least this many lanes have finished their ray
 #endif
@@ -211,6 +214,11 @@ __device__ __forceinline__ uint32_t xor_permute8(uint32_t h, uint32_t x)
 struct TraceCounts { uint32_t nodes, tris, insts; };
 
 #define RTC_SM_STACK 8        // traversal stack entries per thread kept in shared memory
+#if RTC_RESTORE_WORLD
+#define RTC_SM_RAY_WORDS 15   // float columns per thread behind the stack (Traversal::smRay)
+#else
+#define RTC_SM_RAY_WORDS 11
+#endif
 #define RTC_LM_STACK 32       // overflow entries in local memory (never reached by the in-scope scenes)
 
 // Rays whose traversal stack ran out of its 40 entries (the dropped subtree may hide a hit).  Never non-zero for the 8-wide
@@ -234,7 +242,8 @@ struct Traversal
   // World ray origin/direction (needed only when an instance is entered or left) and the barycentric numerators of the
   // best hit (written once per accepted hit) live in shared memory, column-major like the stack: nine registers less,
   // which is what lets more CTAs fit on the SM.  Slots: 0-2 origin, 3-5 direction, 6 V, 7 W, 8 det, 9-10 triangle array of the
-  // current GAS (pointer bits).
+  // current GAS (pointer bits), 11-13 world 1/d and 14 the world octant word (restored when an instance is left instead of
+  // recomputing three reciprocals).
   float* smRay;               // this thread's column: slot k at smRay[k * BLOCK]
   float tmin, tlimit;
   float hitT;                 // best t so far (the barycentric divisions are postponed to result(): same operands, same bits)
@@ -288,6 +297,9 @@ struct Traversal
     if (!(tlimit > tmin)) return false;
     sp = 0; blasBase = -1; curInst = 0;
     box_setup(br, o.x, o.y, o.z, d.x, d.y, d.z);
+#if RTC_RESTORE_WORLD
+    smRay[11 * BLOCK] = br.idx; smRay[12 * BLOCK] = br.idy; smRay[13 * BLOCK] = br.idz; smRay[14 * BLOCK] = __uint_as_float(br.octinv);
+#endif
     nodes = sc.tlasNodes;
     nodeGroup = make_uint2(0u, 0x80000000u);
     triGroup = make_uint2(0u, 0u);
@@ -394,7 +406,12 @@ struct Traversal
       {
         blasBase = -1;   // leave the instance: back to the world-space ray
         nodes = sc.tlasNodes;
+#if RTC_RESTORE_WORLD
+        br.ox = smRay[0]; br.oy = smRay[BLOCK]; br.oz = smRay[2 * BLOCK];
+        br.idx = smRay[11 * BLOCK]; br.idy = smRay[12 * BLOCK]; br.idz = smRay[13 * BLOCK]; br.octinv = __float_as_uint(smRay[14 * BLOCK]);
+#else
         box_setup(br, smRay[0], smRay[BLOCK], smRay[2 * BLOCK], smRay[3 * BLOCK], smRay[4 * BLOCK], smRay[5 * BLOCK]);
+#endif
       }
       if (sp == 0) return false;
       nodeGroup = pop();
@@ -405,7 +422,8 @@ struct Traversal
 
 // Persistent-warp driver: every lane owns one ray at a time; lanes whose ray has finished take the next ray index from a
 // global cursor (one atomicAdd per warp and refill), so short rays do not leave their lanes idle while the longest ray of
-// the warp finishes.  Policy supplies load(i, org, dir) -> bool (false: skip this index) and store(i, traversal).
+// the warp finishes.  Policy (stateless, shared with trace_pool.cuh) supplies load(i, org, dir, tag) -> bool (false: skip this
+// index; tag = the policy's per-ray word, e.g. the path id), store(tag, hit) and, for SKIP kernels, skip_key(tag, t, inst, prim).
 template <bool ANY, bool COUNT, int BLOCK, bool SKIP, class Policy>
 __device__ __forceinline__ void trace_stream(const SceneDesc& sc, uint32_t n, uint32_t* __restrict__ cursor, Policy& policy, uint2* smem,
                                              unsigned long long* __restrict__ countsOut)
@@ -417,7 +435,7 @@ __device__ __forceinline__ void trace_stream(const SceneDesc& sc, uint32_t n, ui
   tr.lmStack = overflow;
   const uint32_t lane = threadIdx.x & 31u;
   bool active = false, exhausted = false;
-  uint32_t index = 0;
+  uint32_t tag = 0;
   unsigned long long cNodes = 0, cTris = 0, cInsts = 0, cRays = 0;
   for (;;)
   {
@@ -432,15 +450,15 @@ __device__ __forceinline__ void trace_stream(const SceneDesc& sc, uint32_t n, ui
       if (base + want >= n) exhausted = true;
       if (!active)
       {
-        index = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+        const uint32_t index = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
         if (index < n)
         {
           float4 o, d;
-          if (policy.load(index, o, d))
+          if (policy.load(index, o, d, tag))
           {
-            if constexpr (SKIP) policy.load_skip(tr.skipT, tr.skipInst, tr.skipPrim);
+            if constexpr (SKIP) policy.skip_key(tag, tr.skipT, tr.skipInst, tr.skipPrim);
             if (tr.begin(sc, o, d)) active = true;
-            else { policy.store(index, tr); if (COUNT) cRays++; }
+            else { policy.store(tag, tr.result()); if (COUNT) cRays++; }
           }
         }
       }
@@ -450,7 +468,7 @@ __device__ __forceinline__ void trace_stream(const SceneDesc& sc, uint32_t n, ui
     {
       if (!tr.step(sc))
       {
-        policy.store(index, tr);
+        policy.store(tag, tr.result());
         if (COUNT) { cNodes += tr.counts.nodes; cTris += tr.counts.tris; cInsts += tr.counts.insts; cRays++; }
         active = false;
       }
