@@ -17,11 +17,18 @@ def test_reference_arm_prints_the_contract_line(built):
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
-    assert d["impl"] == "reference" and d["metric"] == "rtigo3_geometry_1080p_samples_per_s" and d["unit"] == "Msamples/s"
+    assert d["impl"] == "reference" and d["metric"] == "rtigo3_geometry_192x108_samples_per_s" and d["unit"] == "Msamples/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "192x108" in d["config"]["workload"]
+    # both arms build `config` with the same function: same keys, same spp per step (the driver compares the two lines)
+    sys.path.insert(0, H.ROOT)
+    import bench
+    args = bench.parse_args(["--resolution", "192 108"])
+    assert d["config"] == bench.path_config(args, 1)
+    assert bench.metric_name(bench.parse_args([])) == "rtigo3_geometry_1080p_samples_per_s"
+    assert bench.parse_args(["--config", "c1"]).resolution == "512 512" and bench.parse_args(["--config", "c4"]).scene == "rtigo3_instances"
 
 
 def test_reference_arm_is_silent_on_other_ranks(built):

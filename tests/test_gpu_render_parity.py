@@ -221,3 +221,29 @@ def test_converged_frames_reach_40_db_against_the_reference(cuda_device, tmp_pat
     want = golden[key]
     a, b = np.clip(got[..., :3], 0.0, 1.0), np.clip(want[..., :3], 0.0, 1.0)
     assert H.psnr(a, b) >= 40.0, H.psnr(a, b)
+
+
+def test_coalesced_render_calls_equal_single_launches(cuda_device, tmp_path):
+    """The reference's calling pattern -- `unsigned int render()` once per iteration (Application.cpp:500-503) -- is coalesced
+    into batched launches behind the unchanged signature; the frame must not depend on where the batches fall."""
+    frames = []
+    for limit in (1, 4, 0):          # every call launches / batches of four / the default limit
+        app = host.App(H.write_system(tmp_path, "rtigo3_cornell_box", resolution="96 64", samplesSqrt=3), H.scene_path("rtigo3_cornell_box"))
+        try:
+            if limit:
+                app.set_coalesce(limit)
+            assert app.render_calls(5) == 5            # iterations "done" are counted at once, launched lazily
+            before = app.stats().kernelLaunches         # stats() is an observation point: it flushes
+            assert before > 0
+            assert app.render_calls(4) == 9
+            assert app.render_calls(3) == 9            # the budget is samplesSqrt^2
+            frames.append(app.frame())
+            if not limit:
+                ref = H.oracle_scene(app)
+                w, h = app.resolution
+                want = ref.render(H.oracle_sys(app), app.info.miss, w, h, iter_count=9).reshape(h, w, 4)
+        finally:
+            app.close()
+    assert_frames_identical(frames[0], want)
+    assert_frames_identical(frames[1], want)
+    assert_frames_identical(frames[2], want)

@@ -1,8 +1,8 @@
 #!/bin/bash
 # Rebuilds the traversal kernels with different ray-pool knobs on the GPU box and runs a short bench for each.
-# usage: tools/sweep_pool.sh "<defs 1>" "<defs 2>" ...   e.g. "-DRTC_TRACE_POOL=0" "-DRTC_POOL_K=3 -DRTC_POOL_BLOCKS=3 -DRTC_POOL_STACK=2"
+# usage: [RTC_TRACE_DRIVER=pool] tools/sweep_pool.sh "<defs 1>" "<defs 2>" ...   e.g. "" "-DRTC_POOL_K=3 -DRTC_POOL_BLOCKS=3 -DRTC_POOL_STACK=2"
 # BENCH_ARGS overrides the bench flags (default: 4 steps of 32 spp).
-BENCH_ARGS=${BENCH_ARGS:---steps 4 --warmup 3 --spp-per-step 32 --no-cpu-baseline}
+BENCH_ARGS=${BENCH_ARGS:---steps 4 --warmup 3 --spp-per-step 32 --no-cpu-baseline --no-ncu --no-probes}
 for cfg in "$@"; do
   touch tweeker_raytracer_b200/csrc/kernels_trace.cu tweeker_raytracer_b200/csrc/kernels_shade.cu
   make -s -j4 core host TRACE_DEFS="$cfg" > /tmp/sweep_build.log 2>&1 || { echo "build failed for $cfg"; tail -5 /tmp/sweep_build.log; continue; }

@@ -386,7 +386,7 @@ struct DeviceFree
 // with negative values ~leafIndex, root first.
 void build_binary_sah_host(const PrimBox* prims, uint32_t numPrims, std::vector<int2>& children, std::vector<PrimBox>& boxes);
 
-int build_gas_gpu(rtc_context* ctx, GasRecord& rec)
+static int build_gas_gpu_impl(rtc_context* ctx, GasRecord& rec)
 {
   const uint32_t n = rec.numTris;
   if (n == 0) RTC_FAIL("build_gas_gpu needs at least one triangle");
@@ -534,10 +534,108 @@ int build_gas_gpu(rtc_context* ctx, GasRecord& rec)
   {
     void* exact = nullptr;
     RTC_CUDA(cudaMalloc(&exact, (size_t)rec.numNodes * sizeof(Node8)));
-    RTC_CUDA(cudaMemcpyAsync(exact, rec.d_nodes, (size_t)rec.numNodes * sizeof(Node8), cudaMemcpyDeviceToDevice, st));
-    RTC_CUDA(cudaStreamSynchronize(st));
+    cudaError_t e = cudaMemcpyAsync(exact, rec.d_nodes, (size_t)rec.numNodes * sizeof(Node8), cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cudaFree(exact); return rtc_set_error(__FILE__, __LINE__, "shrink node array", (int)e, cudaGetErrorString(e)); }
     RTC_CUDA(cudaFree(rec.d_nodes));
     rec.d_nodes = exact;
   }
+  return 0;
+}
+
+// The outputs are allocated half-way through the build: a failure after that point must not leak them.
+int build_gas_gpu(rtc_context* ctx, GasRecord& rec)
+{
+  const int rc = build_gas_gpu_impl(ctx, rec);
+  if (rc != 0)
+  {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(rec.d_nodes); cudaFree(rec.d_tris);
+    rec.d_nodes = nullptr; rec.d_tris = nullptr;
+    cudaGetLastError();
+  }
+  return rc;
+}
+
+// ---- instance level: tight world bounds of every instance from its transformed vertices -------------------------
+// The reference hands OptiX the instance transform and lets the driver bound the instance (Device.cpp:1427-1443,
+// optixAccelBuild over OPTIX_BUILD_INPUT_TYPE_INSTANCES :1471-1482).  The first version here bounded the eight transformed
+// corners of the GAS box, which is loose for rotated instances (a torus rotated by 45 degrees: +40 % per axis) and made
+// rays enter instances they cannot hit; an instance entry costs about three node visits.  One CTA per instance now
+// transforms every vertex of the instance's GAS and reduces min/max.
+namespace {
+
+struct InstanceBoundsIn
+{
+  float transform[12];
+  const uint8_t* verts; uint32_t stride, numVerts;
+  uint32_t pad;
+};
+
+__global__ void __launch_bounds__(kB)
+k_instance_bounds(const InstanceBoundsIn* __restrict__ in, PrimBox* __restrict__ out)
+{
+  const InstanceBoundsIn& I = in[blockIdx.x];
+  float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+  for (uint32_t v = threadIdx.x; v < I.numVerts; v += blockDim.x)
+  {
+    const float* p = reinterpret_cast<const float*>(I.verts + (size_t)v * I.stride);
+    const float x = p[0], y = p[1], z = p[2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+    {
+      const float* m = I.transform + 4 * r;
+      const float w = fmaf(m[0], x, fmaf(m[1], y, fmaf(m[2], z, m[3])));
+      lo[r] = fminf(lo[r], w); hi[r] = fmaxf(hi[r], w);
+    }
+  }
+  __shared__ float sLo[3][kB / 32], sHi[3][kB / 32];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+  {
+    for (int off = 16; off; off >>= 1)
+    {
+      lo[r] = fminf(lo[r], __shfl_down_sync(0xffffffffu, lo[r], off));
+      hi[r] = fmaxf(hi[r], __shfl_down_sync(0xffffffffu, hi[r], off));
+    }
+    if ((threadIdx.x & 31) == 0) { sLo[r][threadIdx.x >> 5] = lo[r]; sHi[r][threadIdx.x >> 5] = hi[r]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3)
+  {
+    float a = sLo[threadIdx.x][0], b = sHi[threadIdx.x][0];
+    for (int w = 1; w < kB / 32; ++w) { a = fminf(a, sLo[threadIdx.x][w]); b = fmaxf(b, sHi[threadIdx.x][w]); }
+    out[blockIdx.x].lo[threadIdx.x] = a; out[blockIdx.x].hi[threadIdx.x] = b;
+  }
+}
+
+} // namespace
+
+// boxes[i] = exact (unpadded) world bounds of the vertices of instance i; instances of an empty GAS get an inverted box
+int instance_bounds_gpu(rtc_context* ctx, const rtc_instance_desc* instances, uint32_t numInstances, PrimBox* boxes)
+{
+  if (numInstances == 0) return 0;
+  std::vector<InstanceBoundsIn> in(numInstances);
+  for (uint32_t i = 0; i < numInstances; ++i)
+  {
+    const GasRecord& g = ctx->gas[instances[i].gas];
+    for (int k = 0; k < 12; ++k) in[i].transform[k] = instances[i].transform[k];
+    in[i].verts = reinterpret_cast<const uint8_t*>((uintptr_t)g.attributes); in[i].stride = g.strideBytes;
+    in[i].numVerts = g.numTris ? g.numVerts : 0u; in[i].pad = 0u;
+  }
+  InstanceBoundsIn* d_in = nullptr; PrimBox* d_out = nullptr;
+  RTC_CUDA(cudaMalloc(&d_in, sizeof(InstanceBoundsIn) * numInstances));
+  if (cudaMalloc(&d_out, sizeof(PrimBox) * numInstances) != cudaSuccess) { cudaFree(d_in); RTC_FAIL("cudaMalloc failed"); }
+  cudaError_t e = cudaMemcpyAsync(d_in, in.data(), sizeof(InstanceBoundsIn) * numInstances, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess)
+  {
+    k_instance_bounds<<<numInstances, kB, 0, ctx->stream>>>(d_in, d_out);
+    ctx->kernelLaunches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(boxes, d_out, sizeof(PrimBox) * numInstances, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_in); cudaFree(d_out);
+  if (e != cudaSuccess) return rtc_set_error(__FILE__, __LINE__, "instance_bounds_gpu", (int)e, cudaGetErrorString(e));
   return 0;
 }

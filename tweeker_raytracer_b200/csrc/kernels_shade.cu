@@ -232,31 +232,25 @@ constexpr int kPrimaryBlock = 128;
 #define RTC_POOL_BLOCKS 4
 #endif
 
-#if RTC_TRACE_POOL
 template <bool COUNT>
 __global__ void __launch_bounds__(kPrimaryBlock, RTC_POOL_BLOCKS)
-k_extend_primary(const SceneDesc sc, const ExtendPrimary policy, uint32_t n, uint32_t* __restrict__ cursor, unsigned long long* __restrict__ counts,
-                 uint2* __restrict__ overflow)
+k_extend_primary_pool(const SceneDesc sc, const ExtendPrimary policy, uint32_t n, uint32_t* __restrict__ cursor, unsigned long long* __restrict__ counts,
+                      uint2* __restrict__ overflow)
 {
   extern __shared__ uint32_t poolWords[];
   const uint32_t warp = threadIdx.x >> 5;
   const size_t warpGlobal = (size_t)blockIdx.x * (kPrimaryBlock / 32) + warp;
   rtpool::trace_pool<false, COUNT, false>(sc, n, cursor, policy, poolWords + warp * rtpool::warp_words(false, false), overflow + warpGlobal * rtpool::kOverflowPerWarp, counts);
 }
-constexpr int kPrimaryBlocksPerSM = RTC_POOL_BLOCKS;
-constexpr size_t kPrimarySmem = (size_t)(kPrimaryBlock / 32) * rtpool::warp_bytes(false, false);
-#else
+constexpr size_t kPrimaryPoolSmem = (size_t)(kPrimaryBlock / 32) * rtpool::warp_bytes(false, false);
+
 template <bool COUNT>
 __global__ void __launch_bounds__(kPrimaryBlock, RTC_TRACE_MIN_BLOCKS)
-k_extend_primary(const SceneDesc sc, ExtendPrimary policy, uint32_t n, uint32_t* __restrict__ cursor, unsigned long long* __restrict__ counts,
-                 uint2* __restrict__)
+k_extend_primary(const SceneDesc sc, const ExtendPrimary policy, uint32_t n, uint32_t* __restrict__ cursor, unsigned long long* __restrict__ counts)
 {
   __shared__ uint2 smem[RTC_SM_STACK * kPrimaryBlock + (RTC_SM_RAY_WORDS * kPrimaryBlock + 1) / 2];
   trace_stream<false, COUNT, kPrimaryBlock, false>(sc, n, cursor, policy, smem, counts);
 }
-constexpr int kPrimaryBlocksPerSM = RTC_TRACE_MIN_BLOCKS;
-constexpr size_t kPrimarySmem = 0;
-#endif
 
 __device__ __forceinline__ float3 xf_vector(const float4 r0, const float4 r1, const float4 r2, float3 v)
 {
@@ -853,9 +847,11 @@ k_tonemap(const __grid_constant__ rt_TonemapperParams p, const float4* __restric
 
 } // namespace
 
-int ensure_wavefront(rtc_context* ctx, uint64_t capacity)
+// *outOfMemory (optional) tells the caller that the failure was the allocation itself, so it can retry with a smaller batch.
+int ensure_wavefront(rtc_context* ctx, uint64_t capacity, bool* outOfMemory)
 {
   WavefrontBuffers& wf = ctx->wf;
+  if (outOfMemory) *outOfMemory = false;
   if (wf.capacity >= capacity) return 0;
   if (wf.base) { RTC_CUDA(cudaStreamSynchronize(ctx->stream)); RTC_CUDA(cudaFree(wf.base)); wf = WavefrontBuffers(); }
   // one allocation, carved into 256-byte aligned SoA arrays
@@ -879,7 +875,11 @@ int ensure_wavefront(rtc_context* ctx, uint64_t capacity)
   const uint64_t oBins = off; off += align(4 * n) * SHADE_NUM_CLASSES;
   const uint64_t oCnt = off; off += align(4 * kNumCounters);
   void* base = nullptr;
-  RTC_CUDA(cudaMalloc(&base, off));
+  {
+    const cudaError_t e = cudaMalloc(&base, off);
+    if (e == cudaErrorMemoryAllocation && outOfMemory) { *outOfMemory = true; cudaGetLastError(); }      // clear the sticky error: the caller retries
+    if (e != cudaSuccess) return rtc_set_error(__FILE__, __LINE__, "cudaMalloc(wavefront state)", (int)e, cudaGetErrorString(e));
+  }
   char* b = static_cast<char*>(base);
   wf.base = base; wf.capacity = capacity;
   wf.rayOrg = (float4*)(b + oRayOrg); wf.rayDir = (float4*)(b + oRayDir); wf.hit = (float4*)(b + oHit); wf.hitInst = (uint32_t*)(b + oHitInst);
@@ -952,6 +952,7 @@ int launch_shade_classes(rtc_context* ctx, int grid, const WfArgs& a, const Scen
   launch_shade_class<SHADE_BRDF_GGX>(ctx, s[SHADE_BRDF_GGX], grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
   launch_shade_class<SHADE_BSDF_GGX>(ctx, s[SHADE_BSDF_GGX], grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
   launch_shade_class<SHADE_OTHER>(ctx, s[SHADE_OTHER], grid, a, sc, bins, binStride, binCounts, qOut, countOut, shadowQueue, shadowCount, tex, deferRR, primary);
+  RTC_CUDA(cudaGetLastError());      // a failed launch surfaces here, not in an unrelated later call
   if (concurrent)
   {
     for (int k = 0; k < 6; ++k)
@@ -1048,7 +1049,16 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
   if (const char* env = getenv("RTC_MAX_PATHS")) { const long long v = atoll(env); if (v > 0) maxPaths = (uint64_t)v; }
   uint64_t perBatch = maxPaths / pixels; if (perBatch < 1) perBatch = 1; if (perBatch > (uint64_t)iterCount) perBatch = (uint64_t)iterCount;
   if (pixels * perBatch > 0x7fffffffull) RTC_FAIL("launch too large");
-  if (int rc = ensure_wavefront(ctx, pixels * perBatch)) return rc;
+  // 320 B of wavefront state per path: the batch shrinks (down to one iteration) when the device cannot hold it -- other
+  // contexts on the same GPU, a smaller GPU, memory held by the caller -- instead of failing the launch
+  for (;;)
+  {
+    bool oom = false;
+    const int rc = ensure_wavefront(ctx, pixels * perBatch, &oom);
+    if (rc == 0) break;
+    if (!oom || perBatch == 1) return rc;
+    perBatch = (perBatch + 1) / 2;
+  }
   // Material textures (off in every BASELINE configuration, like the reference's GUI default): `cutout` switches to the ordered
   // any-hit processing, which synchronises with the host between rounds; `tex` selects the texture-aware shade kernels.
   const bool cutout = scene->numCutout > 0;
@@ -1082,15 +1092,22 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
       {
         if (int rc = profile_begin(ctx, RTC_KERNEL_EXTEND)) return rc;
         ExtendPrimary policy = { a };
-        const int gridTrace = ctx->numSMs * kPrimaryBlocksPerSM;
-        uint2* overflow = nullptr;
-#if RTC_TRACE_POOL
-        if (int rc = ensure_pool_scratch(ctx, (size_t)gridTrace * (kPrimaryBlock / 32), &overflow)) return rc;
-        RTC_CUDA(cudaFuncSetAttribute(k_extend_primary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrimarySmem));
-        RTC_CUDA(cudaFuncSetAttribute(k_extend_primary<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrimarySmem));
-#endif
-        if (countWork) k_extend_primary<true><<<gridTrace, kPrimaryBlock, kPrimarySmem, ctx->stream>>>(scene->desc, policy, a.numPaths, cnt + 128, ctx->d_launchCounts, overflow);
-        else           k_extend_primary<false><<<gridTrace, kPrimaryBlock, kPrimarySmem, ctx->stream>>>(scene->desc, policy, a.numPaths, cnt + 128, nullptr, overflow);
+        if (ctx->traceDriver == RTC_DRIVER_POOL)
+        {
+          const int gridTrace = ctx->numSMs * RTC_POOL_BLOCKS;
+          uint2* overflow = nullptr;
+          if (int rc = ensure_pool_scratch(ctx, (size_t)gridTrace * (kPrimaryBlock / 32), &overflow)) return rc;
+          RTC_CUDA(cudaFuncSetAttribute(k_extend_primary_pool<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrimaryPoolSmem));
+          RTC_CUDA(cudaFuncSetAttribute(k_extend_primary_pool<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrimaryPoolSmem));
+          if (countWork) k_extend_primary_pool<true><<<gridTrace, kPrimaryBlock, kPrimaryPoolSmem, ctx->stream>>>(scene->desc, policy, a.numPaths, cnt + 128, ctx->d_launchCounts, overflow);
+          else           k_extend_primary_pool<false><<<gridTrace, kPrimaryBlock, kPrimaryPoolSmem, ctx->stream>>>(scene->desc, policy, a.numPaths, cnt + 128, nullptr, overflow);
+        }
+        else
+        {
+          const int gridTrace = ctx->numSMs * RTC_TRACE_MIN_BLOCKS;
+          if (countWork) k_extend_primary<true><<<gridTrace, kPrimaryBlock, 0, ctx->stream>>>(scene->desc, policy, a.numPaths, cnt + 128, ctx->d_launchCounts);
+          else           k_extend_primary<false><<<gridTrace, kPrimaryBlock, 0, ctx->stream>>>(scene->desc, policy, a.numPaths, cnt + 128, nullptr);
+        }
         ctx->kernelLaunches++;
         RTC_CUDA(cudaGetLastError());
         if (int rc = profile_end(ctx)) return rc;

@@ -133,12 +133,11 @@ struct ConnectClosest
 
 // ---- kernels ---------------------------------------------------------------------------------------------------------
 
-#if RTC_TRACE_POOL
-
+// Both drivers are compiled; rtc_context::traceDriver picks one per launch (environment RTC_TRACE_DRIVER=lane|pool, default lane).
 template <bool ANY, bool COUNT, class Policy, bool SKIP = false>
 __global__ void __launch_bounds__(kTraceBlock, RTC_POOL_BLOCKS)
-k_trace(const SceneDesc sc, const Policy policy, uint32_t n, const uint32_t* __restrict__ nPtr, uint32_t* __restrict__ cursor,
-        unsigned long long* __restrict__ counts, uint2* __restrict__ overflow)
+k_trace_pool(const SceneDesc sc, const Policy policy, uint32_t n, const uint32_t* __restrict__ nPtr, uint32_t* __restrict__ cursor,
+             unsigned long long* __restrict__ counts, uint2* __restrict__ overflow)
 {
   extern __shared__ uint32_t poolWords[];
   const uint32_t count = nPtr ? *nPtr : n;      // the wavefront keeps its queue lengths on the device
@@ -147,37 +146,33 @@ k_trace(const SceneDesc sc, const Policy policy, uint32_t n, const uint32_t* __r
   rtpool::trace_pool<ANY, COUNT, SKIP>(sc, count, cursor, policy, poolWords + warp * rtpool::warp_words(ANY, SKIP), overflow + warpGlobal * rtpool::kOverflowPerWarp, counts);
 }
 
-inline int persistent_grid(const rtc_context* ctx) { return ctx->numSMs * RTC_POOL_BLOCKS; }
-constexpr size_t trace_smem(bool any, bool skip) { return (size_t)(kTraceBlock / 32) * rtpool::warp_bytes(any, skip); }
-
-#else
-
 template <bool ANY, bool COUNT, class Policy, bool SKIP = false>
 __global__ void __launch_bounds__(kTraceBlock, SKIP ? 4 : RTC_TRACE_MIN_BLOCKS)
-k_trace(const SceneDesc sc, Policy policy, uint32_t n, const uint32_t* __restrict__ nPtr, uint32_t* __restrict__ cursor,
-        unsigned long long* __restrict__ counts, uint2* __restrict__)
+k_trace(const SceneDesc sc, const Policy policy, uint32_t n, const uint32_t* __restrict__ nPtr, uint32_t* __restrict__ cursor,
+        unsigned long long* __restrict__ counts)
 {
   __shared__ uint2 smem[RTC_SM_STACK * kTraceBlock + (RTC_SM_RAY_WORDS * kTraceBlock + 1) / 2];     // stack columns, then the float columns (trace.cuh smRay)
   const uint32_t count = nPtr ? *nPtr : n;
   trace_stream<ANY, COUNT, kTraceBlock, SKIP>(sc, count, cursor, policy, smem, counts);
 }
 
-inline int persistent_grid(const rtc_context* ctx) { return ctx->numSMs * RTC_TRACE_MIN_BLOCKS; }
-constexpr size_t trace_smem(bool, bool) { return 0; }
-
-#endif
-
 template <bool ANY, bool COUNT, class Policy, bool SKIP>
 int launch_k_trace(rtc_context* ctx, const SceneDesc* scene, const Policy& p, uint32_t n, const uint32_t* nPtr, uint32_t* cursor, unsigned long long* counts)
 {
-  auto kernel = k_trace<ANY, COUNT, Policy, SKIP>;
-  const int grid = persistent_grid(ctx);
-  uint2* overflow = nullptr;
-#if RTC_TRACE_POOL
-  if (int rc = ensure_pool_scratch(ctx, (size_t)grid * (kTraceBlock / 32), &overflow)) return rc;
-  RTC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem(ANY, SKIP)));
-#endif
-  kernel<<<grid, kTraceBlock, trace_smem(ANY, SKIP), ctx->stream>>>(*scene, p, n, nPtr, cursor, counts, overflow);
+  if (ctx->traceDriver == RTC_DRIVER_POOL)
+  {
+    auto kernel = k_trace_pool<ANY, COUNT, Policy, SKIP>;
+    const int grid = ctx->numSMs * RTC_POOL_BLOCKS;
+    const size_t smem = (size_t)(kTraceBlock / 32) * rtpool::warp_bytes(ANY, SKIP);
+    uint2* overflow = nullptr;
+    if (int rc = ensure_pool_scratch(ctx, (size_t)grid * (kTraceBlock / 32), &overflow)) return rc;
+    RTC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<grid, kTraceBlock, smem, ctx->stream>>>(*scene, p, n, nPtr, cursor, counts, overflow);
+  }
+  else
+  {
+    k_trace<ANY, COUNT, Policy, SKIP><<<ctx->numSMs * RTC_TRACE_MIN_BLOCKS, kTraceBlock, 0, ctx->stream>>>(*scene, p, n, nPtr, cursor, counts);
+  }
   ctx->kernelLaunches++;
   RTC_CUDA(cudaGetLastError());
   return 0;

@@ -109,19 +109,17 @@ int rtc_version(void) { return 100; }
 
 const char* rtc_last_error(void) { return g_lastError.c_str(); }
 
-int rtc_context_create(int deviceOrdinal, rtc_context** out)
+int rtc_context_destroy(rtc_context* ctx);
+
+static int context_init(rtc_context* ctx, int deviceOrdinal)
 {
-  if (!out) RTC_FAIL("out is null");
-  *out = nullptr;
-  int count = 0;
-  RTC_CUDA(cudaGetDeviceCount(&count));
-  if (deviceOrdinal < 0 || deviceOrdinal >= count) RTC_FAIL("device ordinal out of range (no CUDA device, no rendering: this core has no CPU path)");
-  RTC_CUDA(cudaSetDevice(deviceOrdinal));
-  rtc_context* ctx = new rtc_context();
   ctx->device = deviceOrdinal;
   cudaDeviceProp prop;
   RTC_CUDA(cudaGetDeviceProperties(&prop, deviceOrdinal));
   ctx->numSMs = prop.multiProcessorCount;
+  // traversal driver: one ray per lane (default) or the per-warp ray pool; both are compiled, RTC_TRACE_DRIVER=lane|pool picks
+  ctx->traceDriver = RTC_DRIVER_LANE;
+  if (const char* e = getenv("RTC_TRACE_DRIVER")) ctx->traceDriver = (e[0] == 'p' || e[0] == '1') ? RTC_DRIVER_POOL : RTC_DRIVER_LANE;
   RTC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   {
     // keep freed build scratch in the device's default memory pool instead of returning it to the OS at every synchronise
@@ -142,15 +140,35 @@ int rtc_context_create(int deviceOrdinal, rtc_context** out)
   RTC_CUDA(cudaMalloc(&ctx->d_cursor, 4 * sizeof(uint32_t)));
   RTC_CUDA(cudaMalloc(&ctx->d_launchCounts, 3 * kTraceCountWords * sizeof(unsigned long long)));
   RTC_CUDA(cudaMemset(ctx->d_launchCounts, 0, 3 * kTraceCountWords * sizeof(unsigned long long)));
+  return 0;
+}
+
+int rtc_context_create(int deviceOrdinal, rtc_context** out)
+{
+  if (!out) RTC_FAIL("out is null");
+  *out = nullptr;
+  int count = 0;
+  RTC_CUDA(cudaGetDeviceCount(&count));
+  if (deviceOrdinal < 0 || deviceOrdinal >= count) RTC_FAIL("device ordinal out of range (no CUDA device, no rendering: this core has no CPU path)");
+  RTC_CUDA(cudaSetDevice(deviceOrdinal));
+  rtc_context* ctx = new rtc_context();
+  if (const int rc = context_init(ctx, deviceOrdinal))
+  {
+    const std::string why = rtc_last_error();      // the destroy below must not clobber the reason
+    rtc_context_destroy(ctx);
+    g_lastError = why;
+    return rc;
+  }
   *out = ctx;
   return 0;
 }
+
 
 int rtc_context_destroy(rtc_context* ctx)
 {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (SceneRecord* s : ctx->scenes) free_scene(s);
   for (GasRecord& g : ctx->gas) { cudaFree(g.d_nodes); cudaFree(g.d_tris); }
   if (ctx->wf.base) cudaFree(ctx->wf.base);
@@ -162,11 +180,11 @@ int rtc_context_destroy(rtc_context* ctx)
   cudaFree(ctx->d_poolScratch);
   for (rtc_context::ProfileSpan& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
-  cudaEventDestroy(ctx->evA); cudaEventDestroy(ctx->evB);
-  cudaEventDestroy(ctx->evTimerA); cudaEventDestroy(ctx->evTimerB);
+  for (cudaEvent_t e : { ctx->evA, ctx->evB, ctx->evTimerA, ctx->evTimerB }) if (e) cudaEventDestroy(e);
   for (int k = 0; k < 6; ++k) { if (ctx->shadeStreams[k]) cudaStreamDestroy(ctx->shadeStreams[k]); if (ctx->shadeJoin[k]) cudaEventDestroy(ctx->shadeJoin[k]); }
   if (ctx->shadeFork) cudaEventDestroy(ctx->shadeFork);
-  cudaStreamDestroy(ctx->stream);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  cudaGetLastError();
   delete ctx;
   return 0;
 }
@@ -416,23 +434,46 @@ int rtc_ias_build(rtc_context* ctx, const rtc_instance_desc* instances, uint32_t
     std::memcpy(&inst[4u * i + 3], w, 16);
     gi[i].attributes = g.attributes; gi[i].indices = g.indices; gi[i].materialIndex = d.materialIndex; gi[i].lightIndex = d.lightIndex;
 
-    // world bounds of the transformed GAS box, padded: the object-space ray is a ROUNDED transform of the
-    // world ray, so a hit found in object space may lie a few ulps outside the exact world-space box
+  }
+  // World bounds per instance: exact bounds of the transformed vertices (device kernel), padded -- the object-space ray is a
+  // ROUNDED transform of the world ray, so a hit found in object space may lie a few ulps outside the exact world-space box.
+  // RTC_INSTANCE_BOUNDS=box falls back to the eight transformed corners of the GAS box (the round-1 bounds, looser for
+  // rotated instances).
+  const bool tight = !(getenv("RTC_INSTANCE_BOUNDS") && getenv("RTC_INSTANCE_BOUNDS")[0] == 'b');
+  if (tight) { if (int rc = instance_bounds_gpu(ctx, instances, numInstances, boxes.data())) { delete rec; return rc; } }
+  for (uint32_t i = 0; i < numInstances; ++i)
+  {
+    const rtc_instance_desc& d = instances[i];
+    const GasRecord& g = ctx->gas[d.gas];
     PrimBox& b = boxes[i];
-    for (int k = 0; k < 3; ++k) { b.lo[k] = std::numeric_limits<float>::infinity(); b.hi[k] = -b.lo[k]; }
     const double ext = std::fabs((double)g.hi[0] - g.lo[0]) + std::fabs((double)g.hi[1] - g.lo[1]) + std::fabs((double)g.hi[2] - g.lo[2]);
-    for (int corner = 0; corner < 8; ++corner)
+    if (tight)
     {
-      const double x = (corner & 1) ? g.hi[0] : g.lo[0], y = (corner & 2) ? g.hi[1] : g.lo[1], z = (corner & 4) ? g.hi[2] : g.lo[2];
       for (int r = 0; r < 3; ++r)
       {
         const float* m = &d.transform[4 * r];
-        const double wv = m[0] * x + m[1] * y + m[2] * z + m[3];
         const double scale = std::fabs((double)m[0]) + std::fabs((double)m[1]) + std::fabs((double)m[2]);
-        const double pad = (std::fabs(wv) + ext * scale) * 1.0e-5;
-        const float lo = std::nextafterf((float)(wv - pad), -std::numeric_limits<float>::infinity());
-        const float hi = std::nextafterf((float)(wv + pad), std::numeric_limits<float>::infinity());
-        b.lo[r] = std::fmin(b.lo[r], lo); b.hi[r] = std::fmax(b.hi[r], hi);
+        const double padLo = (std::fabs((double)b.lo[r]) + ext * scale) * 1.0e-5, padHi = (std::fabs((double)b.hi[r]) + ext * scale) * 1.0e-5;
+        b.lo[r] = std::nextafterf((float)((double)b.lo[r] - padLo), -std::numeric_limits<float>::infinity());
+        b.hi[r] = std::nextafterf((float)((double)b.hi[r] + padHi), std::numeric_limits<float>::infinity());
+      }
+    }
+    else
+    {
+      for (int k = 0; k < 3; ++k) { b.lo[k] = std::numeric_limits<float>::infinity(); b.hi[k] = -b.lo[k]; }
+      for (int corner = 0; corner < 8; ++corner)
+      {
+        const double x = (corner & 1) ? g.hi[0] : g.lo[0], y = (corner & 2) ? g.hi[1] : g.lo[1], z = (corner & 4) ? g.hi[2] : g.lo[2];
+        for (int r = 0; r < 3; ++r)
+        {
+          const float* m = &d.transform[4 * r];
+          const double wv = m[0] * x + m[1] * y + m[2] * z + m[3];
+          const double scale = std::fabs((double)m[0]) + std::fabs((double)m[1]) + std::fabs((double)m[2]);
+          const double pad = (std::fabs(wv) + ext * scale) * 1.0e-5;
+          const float lo = std::nextafterf((float)(wv - pad), -std::numeric_limits<float>::infinity());
+          const float hi = std::nextafterf((float)(wv + pad), std::numeric_limits<float>::infinity());
+          b.lo[r] = std::fmin(b.lo[r], lo); b.hi[r] = std::fmax(b.hi[r], hi);
+        }
       }
     }
     if (g.numTris == 0) { for (int k = 0; k < 3; ++k) { b.lo[k] = 0.0f; b.hi[k] = 0.0f; } }

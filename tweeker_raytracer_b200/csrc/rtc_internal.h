@@ -150,9 +150,12 @@ struct rtc_context
   cudaEvent_t  shadeFork = nullptr, shadeJoin[6] = {};
   unsigned long long* d_launchCounts = nullptr;   // 3 x kTraceCountWords: extend, connect, rtc_trace_count
   uint32_t* d_cursor = nullptr;                   // ray cursor of the query kernels (rtc_trace_*)
+  int    traceDriver = 0;                         // RTC_DRIVER_LANE or RTC_DRIVER_POOL: which traversal driver the launches use
   void*  d_poolScratch = nullptr;                 // global part of the ray pool's traversal stacks (trace_pool.cuh), grown on demand
   size_t poolScratchBytes = 0;
 };
+
+enum { RTC_DRIVER_LANE = 0, RTC_DRIVER_POOL = 1 };     // trace.cuh trace_stream / trace_pool.cuh trace_pool
 
 // work counters of one traversal kernel: {nodes, tris, insts, rays}, then the ray pool's passes and occupied lanes per phase (N, T, I, F)
 constexpr int kTraceCountWords = 12;
@@ -165,6 +168,9 @@ int profile_end(rtc_context* ctx);
 constexpr uint32_t kGpuBuildThreshold = 1u << 20;
 // bvh_build_gpu.cu: Morton LBVH on the device, straight into rec.d_nodes / rec.d_tris; fills numNodes, lo, hi
 int build_gas_gpu(rtc_context* ctx, GasRecord& rec);
+
+// bvh_build_gpu.cu: exact world bounds of every instance's transformed vertices (one CTA per instance)
+int instance_bounds_gpu(rtc_context* ctx, const rtc_instance_desc* instances, uint32_t numInstances, PrimBox* boxes);
 
 // error plumbing (rtc_api.cpp)
 int rtc_set_error(const char* file, int line, const char* call, int code, const char* text);
@@ -189,7 +195,7 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
                      int accumFirst, bool countWork);
 int launch_composite(rtc_context* ctx, const rt_CompositorData& args);
 int launch_tonemap(rtc_context* ctx, const rt_TonemapperParams& p, const float4* rgba, uint8_t* rgb, uint64_t n);
-int ensure_wavefront(rtc_context* ctx, uint64_t capacity);
+int ensure_wavefront(rtc_context* ctx, uint64_t capacity, bool* outOfMemory = nullptr);
 int ensure_pool_scratch(rtc_context* ctx, size_t warps, uint2** out);
 int read_stack_overflows(rtc_context* ctx, uint64_t* out);
 int read_stack_overflows_primary(rtc_context* ctx, uint64_t* out);   // the counter of the primary-ray extend kernel (kernels_shade.cu)

@@ -20,9 +20,6 @@
 
 #include "trace.cuh"
 
-#ifndef RTC_TRACE_POOL
-#define RTC_TRACE_POOL 0          // which driver the traversal kernels use: 0 one ray per lane (trace.cuh), 1 the ray pool below
-#endif
 #ifndef RTC_POOL_K
 #define RTC_POOL_K 2              // ray slots per lane
 #endif

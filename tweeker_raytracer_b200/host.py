@@ -56,7 +56,7 @@ assert C.sizeof(SystemData) == 192 and C.sizeof(CompositorData) == 56
 
 SYMBOLS = ["rth_last_error", "rth_app_create", "rth_app_destroy", "rth_app_info", "rth_app_geometry", "rth_app_instance",
            "rth_app_materials", "rth_app_lights", "rth_app_camera", "rth_app_system_data", "rth_app_tonemapper",
-           "rth_app_environment", "rth_app_render", "rth_app_synchronize", "rth_app_frame", "rth_app_local_frame", "rth_app_restart",
+           "rth_app_environment", "rth_app_render", "rth_app_render_calls", "rth_app_set_coalesce", "rth_app_synchronize", "rth_app_frame", "rth_app_local_frame", "rth_app_restart",
            "rth_app_set_composite", "rth_app_save_system", "rth_app_set_camera", "rth_app_update_material", "rth_app_update_light_emission", "rth_app_benchmark", "rth_app_screenshot", "rth_app_tonemap", "rth_app_context", "rth_app_stats",
            "rth_app_update_material_textures", "rth_app_picture", "rth_process_group_id", "rth_app_join_group", "rth_app_group_reduce_mean", "rth_sample_range"]
 
@@ -99,6 +99,12 @@ def lib():
         L.rth_app_update_material_textures.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.rth_app_picture.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_void_p)]
         L.rth_app_update_light_emission.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.rth_app_render.argtypes = [C.c_void_p, C.c_uint]
+        L.rth_app_render.restype = C.c_uint
+        L.rth_app_render_calls.argtypes = [C.c_void_p, C.c_uint]
+        L.rth_app_render_calls.restype = C.c_uint
+        L.rth_app_set_coalesce.argtypes = [C.c_void_p, C.c_uint]
+        L.rth_app_set_coalesce.restype = C.c_uint
         L.rth_app_benchmark.argtypes = [C.c_void_p]
         L.rth_app_benchmark.restype = C.c_double
         L.rth_app_screenshot.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
@@ -260,6 +266,14 @@ class App:
     # ---- device side
     def render(self, count=1):
         return self.L.rth_app_render(self.h, count)
+
+    def render_calls(self, calls):
+        """`calls` times the reference's `unsigned int Raytracer::render()` (one iteration per call; coalesced by the Raytracer)."""
+        return self.L.rth_app_render_calls(self.h, calls)
+
+    def set_coalesce(self, limit):
+        """Raytracer::setCoalesceLimit: iterations render() may hold back before one batched launch (1 = none); returns the previous limit."""
+        return self.L.rth_app_set_coalesce(self.h, limit)
 
     def synchronize(self):
         if self.L.rth_app_synchronize(self.h) != 0:

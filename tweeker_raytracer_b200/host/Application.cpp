@@ -1,7 +1,13 @@
 // Application.cpp -- headless re-hosting of rtigo3's Application; see Application.h.
 #include "Application.h"
 
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <cctype>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -100,7 +106,11 @@ Application::Application(Options const& options, bool hostOnly)
     m_state.epsilonFactor = m_epsilonFactor;
     m_state.envRotation   = m_environmentRotation;
     m_state.clockFactor   = m_clockFactor;
-    if (m_raytracer) m_raytracer->initState(m_state);
+    if (m_raytracer)
+    {
+      if (0 < m_coalesce) m_raytracer->setCoalesceLimit((unsigned int)m_coalesce);
+      m_raytracer->initState(m_state);
+    }
 
     m_scene = std::make_shared<sg::Group>(m_idGroup++);
     createCameras();
@@ -149,20 +159,37 @@ bool Application::joinProcessGroup(int rank, int world, const char id[128])
   catch (std::exception const& e) { m_lastError = e.what(); std::cerr << e.what() << std::endl; return false; }
 }
 
+// Rendezvous of `rtigo3_b200` launched torchrun-style (RTIGO3_PROCESS_GROUP=1): rank 0 hands the 128-byte NCCL id to the
+// other ranks through a file.  The file is private to the job: its name carries a nonce (TORCHELASTIC_RUN_ID when the
+// launcher sets one, else MASTER_PORT + the launcher's pid, which all ranks share), it is created with O_EXCL | O_NOFOLLOW
+// and mode 0600 after any stale file of that name was unlinked, and it starts with a magic word + the nonce, which the
+// readers verify together with the owner (a stale or foreign file is never taken for this job's id).
 bool Application::joinProcessGroupFromEnvironment()
 {
   const int world = envInt("WORLD_SIZE", 1), rank = envInt("RANK", 0);
   if (envInt("RTIGO3_PROCESS_GROUP", 0) != 1 || world < 2) return false;
-  std::string file = "/tmp/rtigo3_nccl_id_" + std::to_string(envInt("MASTER_PORT", 0));
+  std::string nonce;
+  if (const char* run = std::getenv("TORCHELASTIC_RUN_ID")) nonce = run;
+  nonce += "_" + std::to_string(envInt("MASTER_PORT", 0)) + "_" + std::to_string((long)getppid());
+  for (char& c : nonce) if (!(std::isalnum((unsigned char)c) || c == '_' || c == '-')) c = '_';
+  const char* dir = std::getenv("XDG_RUNTIME_DIR");
+  std::string file = std::string(dir && *dir ? dir : "/tmp") + "/rtigo3_nccl_id_" + std::to_string((long)geteuid()) + "_" + nonce;
   if (const char* f = std::getenv("RTIGO3_NCCL_ID_FILE")) file = f;
+  struct Header { char magic[8]; char nonce[56]; } want;
+  std::memset(&want, 0, sizeof(want));
+  std::memcpy(want.magic, "RTIGO3ID", 8);
+  std::strncpy(want.nonce, nonce.c_str(), sizeof(want.nonce) - 1);
   char id[128];
   if (rank == 0)
   {
     makeProcessGroupId(id);
     const std::string tmp = file + ".tmp";
-    FILE* fp = std::fopen(tmp.c_str(), "wb");
-    if (!fp || std::fwrite(id, 1, sizeof(id), fp) != sizeof(id)) { m_lastError = "cannot write " + tmp; if (fp) std::fclose(fp); return false; }
-    std::fclose(fp);
+    ::unlink(file.c_str());
+    ::unlink(tmp.c_str());
+    const int fd = ::open(tmp.c_str(), O_CREAT | O_EXCL | O_WRONLY | O_NOFOLLOW, 0600);
+    bool ok = fd >= 0 && ::write(fd, &want, sizeof(want)) == (ssize_t)sizeof(want) && ::write(fd, id, sizeof(id)) == (ssize_t)sizeof(id);
+    if (fd >= 0) ok = (::close(fd) == 0) && ok;
+    if (!ok) { m_lastError = "cannot write " + tmp; std::cerr << "ERROR: " << m_lastError << std::endl; return false; }
     if (std::rename(tmp.c_str(), file.c_str()) != 0) { m_lastError = "cannot rename " + tmp; return false; }
   }
   else
@@ -171,17 +198,22 @@ bool Application::joinProcessGroupFromEnvironment()
     bool got = false;
     for (int attempt = 0; attempt < 2400 && !got; ++attempt)
     {
-      if (FILE* fp = std::fopen(file.c_str(), "rb"))
+      const int fd = ::open(file.c_str(), O_RDONLY | O_NOFOLLOW);
+      if (fd >= 0)
       {
-        got = std::fread(id, 1, sizeof(id), fp) == sizeof(id);
-        std::fclose(fp);
+        struct stat st;
+        Header have;
+        got = ::fstat(fd, &st) == 0 && st.st_uid == geteuid() && S_ISREG(st.st_mode)
+           && ::read(fd, &have, sizeof(have)) == (ssize_t)sizeof(have) && std::memcmp(&have, &want, sizeof(want)) == 0
+           && ::read(fd, id, sizeof(id)) == (ssize_t)sizeof(id);
+        ::close(fd);
       }
       if (!got) { struct timespec ts = { 0, 50 * 1000 * 1000 }; nanosleep(&ts, nullptr); }
     }
     if (!got) { m_lastError = "timed out waiting for " + file; std::cerr << "ERROR: " << m_lastError << std::endl; return false; }
   }
   const bool ok = joinProcessGroup(rank, world, id);
-  if (rank == 0 && ok) std::remove(file.c_str());   // every rank has read it once ncclCommInitRank returned
+  if (rank == 0) ::unlink(file.c_str());   // every rank has read it once ncclCommInitRank returned (or the join failed: do not leave it behind)
   return ok;
 }
 
@@ -248,6 +280,7 @@ bool Application::saveSystemDescription(std::string const& filename, std::string
     << "brightness " << m_tonemapperGUI.brightness << '\n';
   if (m_compositeMode) d << "composite " << m_compositeMode << '\n';
   if (m_batch != 1) d << "batchIterations " << m_batch << '\n';
+  if (m_coalesce != 0) d << "coalesceIterations " << m_coalesce << '\n';
   if (m_fileAlbedo != "./NVIDIA_Logo.jpg") d << "textureAlbedo " << m_fileAlbedo << '\n';
   if (m_fileCutout != "./slots_alpha.png") d << "textureCutout " << m_fileCutout << '\n';
   std::string path = filename;
@@ -364,7 +397,8 @@ bool Application::screenshot(const bool tonemap, std::string* writtenPath)
     std::ostringstream path;
     const std::time_t now = std::time(nullptr);
     std::tm tmv; localtime_r(&now, &tmv);
-    path << m_prefixScreenshot << "_" << m_raytracer->m_iterationIndex << "spp_" << std::put_time(&tmv, "%Y%m%d_%H%M%S");
+    // in a process group the combined frame holds every rank's samples: world x the local count
+    path << m_prefixScreenshot << "_" << m_raytracer->m_iterationIndex * (unsigned int)std::max(1, m_raytracer->getWorld()) << "spp_" << std::put_time(&tmv, "%Y%m%d_%H%M%S");
     bool ok = false;
     std::string file;
     const bool writer = m_raytracer->getRank() == 0;    // in a process group fetching the frame is a collective; rank 0 owns the result
@@ -563,6 +597,7 @@ bool Application::loadSystemDescription(std::string const& filename)
   keywords["textureCutout"] = [&]() { parser.getNextLine(token); m_fileCutout = token; };
   keywords["composite"] = [&]() { m_compositeMode = nextInt(); };
   keywords["batchIterations"] = [&]() { m_batch = std::max(1, nextInt()); };
+  keywords["coalesceIterations"] = [&]() { m_coalesce = std::max(0, nextInt()); };
 
   while ((tokenType = parser.getNextToken(token)) != PTT_EOF)
   {

@@ -116,6 +116,7 @@ private:
   TonemapperGUI m_tonemapperGUI;
   int   m_compositeMode = 0;     // extension keyword "composite": 0 peer copies, 1 NCCL reduce (local-copy strategy)
   int   m_batch = 1;             // extension keyword "batchIterations": iterations per enqueue in benchmark()
+  int   m_coalesce = 0;          // extension keyword "coalesceIterations": Raytracer::setCoalesceLimit (0 = its default, 1 = every render() launches)
 
   Camera m_camera;
   DeviceState m_state;

@@ -1,6 +1,8 @@
 // Device.cpp -- base class of the per-GPU devices; see Device.h for the mapping onto the reference.
 #include "Device.h"
 
+#include <algorithm>
+
 #include <cmath>
 #include <cstring>
 
@@ -198,7 +200,9 @@ void Device::initScene(std::shared_ptr<sg::Group> root, const unsigned int numGe
 {
   activateContext();
   synchronizeStream();
-  m_geometryData.resize(numGeometries);
+  // a second initScene replaces the scene: the previous instance level is released (geometries already built are kept and reused)
+  if (m_systemData.topObject) { RTC_CHECK(rtc_scene_destroy(m_context, m_systemData.topObject)); m_systemData.topObject = 0; }
+  m_geometryData.resize(std::max<size_t>(numGeometries, m_geometryData.size()));
   m_instances.clear();
   float matrix[12] = { 1, 0, 0, 0,  0, 1, 0, 0,  0, 0, 1, 0 };
   InstanceData data;

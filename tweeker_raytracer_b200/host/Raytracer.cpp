@@ -1,7 +1,10 @@
 #include "Raytracer.h"
 
 #include <cstring>
+#include <exception>
 #include <iostream>
+#include <string>
+#include <thread>
 
 #include "NcclComposite.h"
 
@@ -15,6 +18,13 @@ Raytracer::Raytracer(RendererStrategy strategy, const int interop, const unsigne
 
 Raytracer::~Raytracer()
 {
+  // Launches are asynchronous (render(count) enqueues without a sync) and the multi-GPU strategies share one frame: every
+  // device must be idle before the first one is deleted and frees it.  Pending, never-observed iterations are dropped.
+  m_pendingCount = 0;
+  for (Device* device : m_activeDevices)
+  {
+    try { device->activateContext(); device->synchronizeStream(); } catch (std::exception const& e) { std::cerr << e.what() << std::endl; }
+  }
   if (m_processGroup && !m_activeDevices.empty())
   {
     rtc_context* ctx = m_activeDevices[0]->getContext();
@@ -31,6 +41,11 @@ void Raytracer::joinProcessGroup(const int rank, const int world, const char id[
   if (world < 1 || rank < 0 || world <= rank) throw std::runtime_error("ERROR: joinProcessGroup() rank/world out of range");
   if (m_activeDevices.size() != 1) throw std::runtime_error("ERROR: joinProcessGroup() needs exactly one active device per process (strategy 0)");
   if (m_processGroup) throw std::runtime_error("ERROR: joinProcessGroup() called twice");
+  // The ranks' running averages are combined with an unweighted mean, which is only the mean of all samples while every
+  // rank renders the same number of iterations: a sample count the ranks cannot share equally is refused, not truncated.
+  if (m_samplesPerPixel % (unsigned int)world != 0u)
+    throw std::runtime_error("ERROR: joinProcessGroup() samplesSqrt^2 = " + std::to_string(m_samplesPerPixel) + " is not divisible by the " + std::to_string(world) + " ranks");
+  flush();
   m_processGroup = ncclProcessGroupJoin(rank, world, id, m_activeDevices[0]->m_ordinal);
   m_rank = rank;
   m_world = world;
@@ -41,11 +56,13 @@ void Raytracer::joinProcessGroup(const int rank, const int world, const char id[
 void Raytracer::reduceMeanToRoot(const uint64_t src, const uint64_t dst, const size_t count)
 {
   if (!m_processGroup) throw std::runtime_error("ERROR: reduceMeanToRoot() without joinProcessGroup()");
+  flush();
   ncclProcessGroupReduceMean(m_processGroup, src, dst, count, rtc_context_stream(m_activeDevices[0]->getContext()));
 }
 
 const void* Raytracer::getLocalOutputBufferHost()
 {
+  flush();
   return m_activeDevices.empty() ? nullptr : m_activeDevices[0]->getOutputBufferHost();
 }
 
@@ -157,6 +174,7 @@ void Raytracer::disablePeerAccess()
 
 void Raytracer::synchronize()
 {
+  flush();
   for (Device* device : m_activeDevices) { device->activateContext(); device->synchronizeStream(); }
 }
 
@@ -166,19 +184,32 @@ void Raytracer::initLights(std::vector<LightDefinition> const& lights) { for (De
 void Raytracer::initMaterials(std::vector<MaterialGUI> const& materialsGUI) { for (Device* d : m_activeDevices) d->initMaterials(materialsGUI); }
 void Raytracer::initScene(std::shared_ptr<sg::Group> root, const unsigned int numGeometries) { for (Device* d : m_activeDevices) d->initScene(root, numGeometries); }
 
+static unsigned int defaultCoalesceLimit(DeviceState const& state)
+{
+  const unsigned long long pixels = (unsigned long long)state.resolution.x * (unsigned long long)state.resolution.y;
+  unsigned long long n = pixels ? (64ull << 20) / pixels : 1ull;      // the core keeps up to 64 Mi paths in flight per launch
+  if (n < 1) n = 1;
+  if (n > 64) n = 64;
+  return (unsigned int)n;
+}
+
 void Raytracer::initState(DeviceState const& state)
 {
   m_samplesPerPixel = (unsigned int)(state.samplesSqrt * state.samplesSqrt);
+  if (!m_coalesceExplicit) m_coalesceLimit = defaultCoalesceLimit(state);
   for (Device* d : m_activeDevices) d->setState(state);
   applySeedOffsets();
 }
 
 // Every update restarts the accumulation (Raytracer.cpp:331-367).
-void Raytracer::updateCamera(const int idCamera, CameraDefinition const& camera) { for (Device* d : m_activeDevices) d->updateCamera(idCamera, camera); m_iterationIndex = 0; }
-void Raytracer::updateLight(const int idLight, LightDefinition const& light) { for (Device* d : m_activeDevices) d->updateLight(idLight, light); m_iterationIndex = 0; }
-void Raytracer::updateMaterial(const int idMaterial, MaterialGUI const& src) { for (Device* d : m_activeDevices) d->updateMaterial(idMaterial, src); m_iterationIndex = 0; }
+void Raytracer::updateCamera(const int idCamera, CameraDefinition const& camera) { flush(); for (Device* d : m_activeDevices) d->updateCamera(idCamera, camera); m_iterationIndex = 0; }
+void Raytracer::updateLight(const int idLight, LightDefinition const& light) { flush(); for (Device* d : m_activeDevices) d->updateLight(idLight, light); m_iterationIndex = 0; }
+void Raytracer::updateMaterial(const int idMaterial, MaterialGUI const& src) { flush(); for (Device* d : m_activeDevices) d->updateMaterial(idMaterial, src); m_iterationIndex = 0; }
 void Raytracer::updateState(DeviceState const& state)
 {
+  // a new resolution makes the owner free and reallocate the shared frame: no device may still be writing to the old one
+  synchronize();
+  if (!m_coalesceExplicit) m_coalesceLimit = defaultCoalesceLimit(state);
   m_samplesPerPixel = (unsigned int)(state.samplesSqrt * state.samplesSqrt);
   for (Device* d : m_activeDevices) d->setState(state);
   applySeedOffsets();
@@ -187,7 +218,7 @@ void Raytracer::updateState(DeviceState const& state)
 
 unsigned int Raytracer::render(const unsigned int count) { return renderAll(count); }
 
-// All devices work on the same iteration indices; the first device called allocates shared buffers.
+// render(): count the iterations; enqueue them as one batch once the coalescing limit is reached (see Raytracer.h).
 unsigned int Raytracer::renderAll(const unsigned int count)
 {
   const unsigned int budget = getSamplesPerPixelLocal();    // == m_samplesPerPixel unless this process is one rank of several
@@ -195,15 +226,45 @@ unsigned int Raytracer::renderAll(const unsigned int count)
   {
     unsigned int n = budget - m_iterationIndex;
     if (count < n) n = count;
-    void* buffer = nullptr;
-    for (Device* device : m_activeDevices) device->renderIterations(m_iterationIndex, n, &buffer);
+    if (m_pendingCount == 0) m_pendingFirst = m_iterationIndex;
+    m_pendingCount += n;
     m_iterationIndex += n;
+    if (m_coalesceLimit <= m_pendingCount) flush();
   }
   return m_iterationIndex;
 }
 
+// All devices work on the same iteration indices.  The first device called allocates the shared buffers (the `void**
+// buffer` protocol of Device::render, DeviceMultiGPUPeerAccess.cpp:110-125), so it is driven first; the others only enqueue
+// kernels on their own streams and are driven by one host thread each -- with 8 GPUs a single thread issuing ~2000 launches
+// per device and batch was what bounded the tile partition at 4K (profiles/c5_4k_r1.md).
+void Raytracer::flush()
+{
+  if (m_pendingCount == 0) return;
+  const unsigned int first = m_pendingFirst, n = m_pendingCount;
+  m_pendingCount = 0;
+  void* buffer = nullptr;
+  if (m_activeDevices.empty()) return;
+  m_activeDevices[0]->renderIterations(first, n, &buffer);
+  const size_t others = m_activeDevices.size() - 1;
+  if (others == 1) m_activeDevices[1]->renderIterations(first, n, &buffer);
+  else if (1 < others)
+  {
+    std::vector<std::thread> workers;
+    std::vector<std::exception_ptr> errors(others);
+    for (size_t i = 0; i < others; ++i)
+      workers.emplace_back([this, i, first, n, buffer, &errors]() {
+        void* shared = buffer;
+        try { m_activeDevices[i + 1]->renderIterations(first, n, &shared); } catch (...) { errors[i] = std::current_exception(); }
+      });
+    for (std::thread& t : workers) t.join();
+    for (std::exception_ptr& e : errors) if (e) std::rethrow_exception(e);
+  }
+}
+
 void Raytracer::getStats(rtc_stats& total)
 {
+  flush();
   std::memset(&total, 0, sizeof(total));
   for (Device* device : m_activeDevices)
   {
@@ -246,6 +307,7 @@ RaytracerMultiGPUPeerAccess::RaytracerMultiGPUPeerAccess(const int devicesMask, 
 
 RaytracerMultiGPUPeerAccess::~RaytracerMultiGPUPeerAccess()
 {
+  m_pendingCount = 0;      // never-observed iterations are dropped
   try { synchronize(); disablePeerAccess(); } catch (std::exception const& e) { std::cerr << e.what() << std::endl; }
 }
 
@@ -272,6 +334,7 @@ RaytracerMultiGPULocalCopy::RaytracerMultiGPULocalCopy(const int devicesMask, co
 
 RaytracerMultiGPULocalCopy::~RaytracerMultiGPULocalCopy()
 {
+  m_pendingCount = 0;      // never-observed iterations are dropped
   try
   {
     synchronize();
@@ -290,6 +353,7 @@ RaytracerMultiGPULocalCopy::~RaytracerMultiGPULocalCopy()
 // the result is the same, so each device is composited once here.
 void RaytracerMultiGPULocalCopy::composite()
 {
+  flush();
   if (m_compositeMode == COMPOSITE_NCCL_REDUCE && 1 < m_activeDevices.size()) { compositeNccl(); return; }
   synchronize();
   for (Device* device : m_activeDevices) m_activeDevices[0]->compositor(device);

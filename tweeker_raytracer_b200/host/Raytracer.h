@@ -43,6 +43,16 @@ public:
 
   virtual unsigned int render() = 0;                 // one iteration; returns the iterations done so far
   virtual unsigned int render(const unsigned int count);   // up to `count` iterations in one enqueue
+
+  // Coalescing behind the unchanged `unsigned int render()` (apps/rtigo3/inc/Raytracer.h:79; Application::benchmark calls it
+  // once per iteration, Application.cpp:500-503).  The reference's render() only ENQUEUES an asynchronous optixLaunch, so
+  // nothing is observable before synchronize() / getOutputBufferHost() / updateDisplayTexture() / an update*().  render()
+  // therefore just counts iterations; they are enqueued as ONE batched launch when `limit` of them are pending or at the
+  // next of those observation points.  limit 1 = every call launches.  The default comes from initState(): as many
+  // iterations as fit the wavefront budget of 64 Mi paths (32 at 1080p), at most 64.
+  void setCoalesceLimit(const unsigned int limit) { flush(); m_coalesceLimit = limit ? limit : 1u; m_coalesceExplicit = true; }
+  unsigned int getCoalesceLimit() const { return m_coalesceLimit; }
+  void flush();                                      // enqueue the pending iterations on all devices
   virtual void updateDisplayTexture() = 0;
   virtual const void* getOutputBufferHost() = 0;
 
@@ -58,7 +68,7 @@ public:
   const void* getLocalOutputBufferHost();
   int getRank() const { return m_rank; }
   int getWorld() const { return m_world; }
-  // iterations this process renders: samplesPerPixel / world (at least 1)
+  // iterations this process renders: samplesPerPixel / world (joinProcessGroup refuses a count the ranks cannot share equally)
   unsigned int getSamplesPerPixelLocal() const { return samplesPerRank(m_samplesPerPixel, m_world); }
   static unsigned int samplesPerRank(const unsigned int samplesPerPixel, const int world)
   {
@@ -84,6 +94,9 @@ public:
 protected:
   template <class DeviceType> void createDevices(const int devicesMask, const int miss, const bool onlyFirst);
   unsigned int renderAll(const unsigned int count);
+  unsigned int m_pendingFirst = 0, m_pendingCount = 0;   // iterations counted by render() but not yet enqueued
+  unsigned int m_coalesceLimit = 1;
+  bool         m_coalesceExplicit = false;
   const void* combineProcessGroup();     // the collective behind getOutputBufferHost() when m_world > 1
   void applySeedOffsets();
 
@@ -100,8 +113,8 @@ class RaytracerSingleGPU : public Raytracer
 public:
   RaytracerSingleGPU(const int devicesMask, const int miss, const int interop, const unsigned int tex, const unsigned int pbo);
   unsigned int render() override { return renderAll(1); }
-  void updateDisplayTexture() override { m_activeDevices[0]->updateDisplayTexture(); }
-  const void* getOutputBufferHost() override { return (m_processGroup != nullptr) ? combineProcessGroup() : m_activeDevices[0]->getOutputBufferHost(); }
+  void updateDisplayTexture() override { flush(); m_activeDevices[0]->updateDisplayTexture(); }
+  const void* getOutputBufferHost() override { flush(); return (m_processGroup != nullptr) ? combineProcessGroup() : m_activeDevices[0]->getOutputBufferHost(); }
 };
 
 class RaytracerMultiGPUZeroCopy : public Raytracer
@@ -109,7 +122,7 @@ class RaytracerMultiGPUZeroCopy : public Raytracer
 public:
   RaytracerMultiGPUZeroCopy(const int devicesMask, const int miss, const int interop, const unsigned int tex, const unsigned int pbo);
   unsigned int render() override { return renderAll(1); }
-  void updateDisplayTexture() override {}
+  void updateDisplayTexture() override { flush(); }
   const void* getOutputBufferHost() override;
 };
 
@@ -119,7 +132,7 @@ public:
   RaytracerMultiGPUPeerAccess(const int devicesMask, const int miss, const int interop, const unsigned int tex, const unsigned int pbo);
   ~RaytracerMultiGPUPeerAccess() override;
   unsigned int render() override { return renderAll(1); }
-  void updateDisplayTexture() override {}
+  void updateDisplayTexture() override { flush(); }
   const void* getOutputBufferHost() override;
 };
 

@@ -148,6 +148,22 @@ int rth_app_update_light_emission(void* h, int index, const float emission[3])
 
 // --- device side (needs a GPU) ---
 unsigned int rth_app_render(void* h, unsigned int count) { return static_cast<Application*>(h)->render(count); }
+// the reference's calling pattern: `calls` times the unchanged `unsigned int Raytracer::render()` (one iteration per call)
+unsigned int rth_app_render_calls(void* h, unsigned int calls)
+{
+  Raytracer* rt = static_cast<Application*>(h)->getRaytracer();
+  unsigned int it = 0;
+  try { for (unsigned int k = 0; k < calls; ++k) it = rt->render(); } catch (std::exception const& e) { g_error = e.what(); }
+  return it;
+}
+// Raytracer::setCoalesceLimit (1 = every render() launches); returns the previous limit
+unsigned int rth_app_set_coalesce(void* h, unsigned int limit)
+{
+  Raytracer* rt = static_cast<Application*>(h)->getRaytracer();
+  const unsigned int before = rt->getCoalesceLimit();
+  try { rt->setCoalesceLimit(limit); } catch (std::exception const& e) { g_error = e.what(); }
+  return before;
+}
 int rth_app_synchronize(void* h)
 {
   try { static_cast<Application*>(h)->getRaytracer()->synchronize(); return 0; } catch (std::exception const& e) { g_error = e.what(); return -1; }
