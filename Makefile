@@ -48,7 +48,7 @@ $(LIB)/rtigo3_b200: $(HOST)/main.cpp $(LIB)/librtigo3host.so
 	g++ $(CXXFLAGS) -I$(HOST) -o $@ $(HOST)/main.cpp -L$(LIB) -lrtigo3host -lrtcore -Wl,-rpath,'$$ORIGIN' -Wl,-rpath-link,/usr/local/cuda/lib64
 
 oracle: oracle/_build/liborc.so
-oracle/_build/liborc.so: oracle/rt_oracle.c oracle/rt_oracle.h include/rtigo3_abi.h include/rt_portable_math.h
+oracle/_build/liborc.so: oracle/rt_oracle.c oracle/wide_bvh.inc oracle/rt_oracle.h include/rtigo3_abi.h include/rt_portable_math.h
 	mkdir -p oracle/_build
 	gcc -O2 -ffp-contract=off -mfma -fPIC -shared -Iinclude -Ioracle -Wall -Wno-misleading-indentation -o $@ oracle/rt_oracle.c -lm -lpthread
 

@@ -73,7 +73,7 @@ typedef struct {
   uint32_t numInstances;
   uint32_t numTlasNodes;
   uint32_t numGas;           /* distinct GAS referenced */
-  uint32_t reserved;
+  uint32_t numTlasLeaves;    /* instance-level leaf slots (one instance id each) */
   double   gasBuildMs;       /* sum of the build times of the referenced GAS */
   double   iasBuildMs;
 } rtc_scene_info;
@@ -158,6 +158,18 @@ int rtc_scene_set_albedo_textures(rtc_context* ctx, uint64_t topObject, int enab
  */
 int rtc_texture_create(rtc_context* ctx, uint32_t width, uint32_t height, const float* rgba, uint64_t* handle);
 int rtc_texture_destroy(rtc_context* ctx, uint64_t handle);
+/*
+ * Export of the acceleration structure to host memory, for tools and for the test oracle, which traverses the IDENTICAL wide BVH
+ * to reproduce the work counters of rtc_trace_count / rtc_launch_counts_get.  Synchronous.
+ *   rtc_scene_export: tlasNodes = numTlasNodes x 80 B wide nodes, tlasLeaves = numTlasLeaves instance ids,
+ *                     worldToObject = numInstances x 12 floats, instanceGas = numInstances GAS handles; any pointer may be null.
+ *   rtc_gas_info / rtc_gas_export: nodes = numNodes x 80 B, tris = numTris x 12 floats in leaf order
+ *                     (v0.xyz, primitive id bits, v1.xyz, 0, v2.xyz, 0).
+ * Node layout: csrc/rtc_internal.h Node8.
+ */
+int rtc_scene_export(rtc_context* ctx, uint64_t topObject, void* tlasNodes, uint32_t* tlasLeaves, float* worldToObject, uint32_t* instanceGas);
+int rtc_gas_info(rtc_context* ctx, uint32_t gas, uint64_t* numNodes, uint64_t* numTris);
+int rtc_gas_export(rtc_context* ctx, uint32_t gas, void* nodes, float* tris);
 /* Copies out the 3x4 world->object matrix of one instance. */
 int rtc_instance_inverse(rtc_context* ctx, uint64_t topObject, uint32_t instance, float out[12]);
 

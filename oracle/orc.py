@@ -304,5 +304,32 @@ def tonemap(params, rgba):
     return out
 
 
+class WideScene(C.Structure):
+    _fields_ = [("tlasNodes", C.c_void_p), ("tlasLeaves", C.c_void_p), ("worldToObject", C.c_void_p), ("instGas", C.c_void_p),
+                ("gasNodes", C.c_void_p), ("gasTris", C.c_void_p), ("numInstances", C.c_uint32)]
+
+
+def wide_trace(export, rays, any_hit=False, variant="pinned"):
+    """Scalar traversal of the PRODUCT's exported wide BVH (core.Context.scene_export) in the product's own order of operations
+    (oracle/wide_bvh.inc): returns (hits, (nodes, tris, instances)) -- the work counters the GPU's counting kernels must equal."""
+    L = lib(variant)
+    handles = sorted(export["gas"])
+    slot = {g: k for k, g in enumerate(handles)}
+    inst_gas = np.ascontiguousarray([slot[int(g)] for g in export["instance_gas"]], dtype=np.uint32)
+    keep = [np.ascontiguousarray(export["gas"][g][0]) for g in handles], [np.ascontiguousarray(export["gas"][g][1]) for g in handles]
+    node_ptrs = (C.c_void_p * max(len(handles), 1))(*[a.ctypes.data for a in keep[0]])
+    tri_ptrs = (C.c_void_p * max(len(handles), 1))(*[a.ctypes.data for a in keep[1]])
+    tn, tl, w2o = (np.ascontiguousarray(export[k]) for k in ("tlas_nodes", "tlas_leaves", "world_to_object"))
+    ws = WideScene(tn.ctypes.data, tl.ctypes.data, w2o.ctypes.data, inst_gas.ctypes.data, C.cast(node_ptrs, C.c_void_p), C.cast(tri_ptrs, C.c_void_p),
+                   len(export["instance_gas"]))
+    rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+    hits = np.zeros(len(rays), dtype=HIT_DTYPE)
+    counts = (C.c_uint64 * 3)()
+    L.orc_wide_trace.argtypes = [C.POINTER(WideScene), C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.POINTER(C.c_uint64)]
+    L.orc_wide_trace.restype = None
+    L.orc_wide_trace(C.byref(ws), _ptr(rays), len(rays), 1 if any_hit else 0, _ptr(hits), counts)
+    return hits, (int(counts[0]), int(counts[1]), int(counts[2]))
+
+
 def online_cores():
     return lib().orc_online_cores()

@@ -1560,3 +1560,5 @@ void orc_tonemap(const rt_TonemapperParams* p, const float* rgba, uint8_t* rgb, 
     }
   }
 }
+
+#include "wide_bvh.inc"

@@ -103,3 +103,23 @@ def hits_equal(a, b):
 def psnr(a, b, peak=1.0):
     mse = float(np.mean((np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)) ** 2))
     return 99.0 if mse == 0 else 10.0 * np.log10(peak * peak / mse)
+
+
+def random_rgbe(w, h, seed):
+    """Seeded Radiance RGBE texels [h, w, 4] uint8: mostly dark, a few very bright, three black rows and a black column band."""
+    rng = np.random.default_rng(seed)
+    img = np.zeros((h, w, 4), dtype=np.uint8)
+    img[..., :3] = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    img[..., 3] = (128 + np.round(rng.random((h, w)) ** 4 * 6 - 3)).astype(np.uint8)       # exponents 2^-3 .. 2^3
+    img[h // 3 - 1:h // 3 + 2] = 0                # three black rows: the middle one stays black after the 3x3 filter -> "equal distribution" branch
+    img[:, w // 2:w // 2 + 3] = 0                 # a black band next to bright texels: what its Gaussian filter is there for
+    return img
+
+
+def write_rgbe_hdr(path, rgbe):
+    """Flat (not run-length encoded) Radiance .hdr file, top row first, from RGBE bytes [h, w, 4]."""
+    h, w = rgbe.shape[:2]
+    with open(path, "wb") as f:
+        f.write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n" % (h, w))
+        f.write(np.ascontiguousarray(rgbe, dtype=np.uint8).tobytes())
+    return path

@@ -1,6 +1,7 @@
 """Host side (no GPU): tokenizer, the two description formats, tessellators, index semantics, tile partition."""
 import ctypes as C
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -246,3 +247,41 @@ def test_save_system_description_round_trip(built, tmp_path):
     assert bytes(app.tonemapper()) == bytes(again.tonemapper())
     app.close()
     again.close()
+
+
+# ---- the environment CDF builder against the reference's own Texture::calculateSphericalCDF ------------------------------
+def _env_case(tmp_path, key):
+    if key.startswith("procedural"):
+        spec = "procedural " + key.split("_")[1].replace("x", " ")
+    else:
+        spec = H.write_rgbe_hdr(os.path.join(str(tmp_path), "random.hdr"), H.random_rgbe(48, 24, 20261018))
+    app = load(tmp_path, name="rtigo3_geometry", miss=2, envMap=spec, resolution="8 8")
+    env = app.environment()
+    app.close()
+    return env
+
+
+@pytest.mark.parametrize("key", ["procedural_64x32", "procedural_256x128", "random_48x24"])
+def test_environment_cdf_equals_reference_golden(built, tmp_path, key):
+    """host/EnvMap.cpp restates Texture.cpp:1500-1645; tests/golden/reference_envcdf.npz holds the outputs of the reference's own
+    function (compiled where it lies, tests/golden/make_golden_envcdf.py) on the same texels: bit-exact."""
+    gold = np.load(os.path.join(H.ROOT, "tests", "golden", "reference_envcdf.npz"))
+    texels, cdf_u, cdf_v, integral = _env_case(tmp_path, key)
+    assert texels.tobytes() == gold[key + "_texels"].tobytes()          # same input (procedural sky / .hdr reader)
+    assert cdf_u.tobytes() == gold[key + "_cdf_u"].tobytes()
+    assert cdf_v.tobytes() == gold[key + "_cdf_v"].tobytes()
+    assert np.float32(integral).tobytes() == gold[key + "_integral"].tobytes()
+    if key == "random_48x24":
+        equal = np.arange(49, dtype=np.float32) / np.float32(48)                # a row that is black after filtering: equal distribution
+        assert any(np.array_equal(row, equal) for row in cdf_u)
+
+
+def test_environment_cdf_equals_live_reference(built, tmp_path):
+    """Container only: the same comparison against oracle/_ref/libreftex.so built from /root/reference right now."""
+    if not os.path.isdir("/root/reference/apps/rtigo3/src"):
+        pytest.skip("/root/reference is not mounted here")
+    sys.path.insert(0, os.path.join(H.ROOT, "tests", "golden"))
+    import make_golden_envcdf
+    texels, cdf_u, cdf_v, integral = _env_case(tmp_path, "random_48x24")
+    u, v, i = make_golden_envcdf.reference_cdf(texels)
+    assert cdf_u.tobytes() == u.tobytes() and cdf_v.tobytes() == v.tobytes() and np.float32(integral).tobytes() == np.float32(i).tobytes()

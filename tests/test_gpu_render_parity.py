@@ -247,3 +247,15 @@ def test_coalesced_render_calls_equal_single_launches(cuda_device, tmp_path):
     assert_frames_identical(frames[0], want)
     assert_frames_identical(frames[1], want)
     assert_frames_identical(frames[2], want)
+
+
+def test_geometry_scene_hdr_file_environment_bit_exact(cuda_device, tmp_path):
+    """`miss 2` with the environment read from a Radiance .hdr FILE (reference: Texture.cpp:1300-1377 through
+    DevIL; here host/ImageIO.cpp), importance sampled through the CDFs the host builds from it (pinned against the reference's
+    own builder in test_cpu_host_loader.py), rendered on the GPU and compared with the oracle bit for bit."""
+    path = H.write_rgbe_hdr(str(tmp_path / "sky.hdr"), H.random_rgbe(64, 32, 7))
+    got, want, stats, st = render_both(tmp_path, "rtigo3_geometry", 4, batch=4, resolution="160 90", samplesSqrt=2, miss=2,
+                                       envMap=path, envRotation=0.35)
+    assert_frames_identical(got, want)
+    assert stats.radianceRays == st.radianceRays and stats.shadowRays == st.shadowRays
+    assert np.isfinite(got).all() and got[..., :3].mean() > 0.01

@@ -29,7 +29,7 @@ SYMBOLS = [
     "rtc_launch", "rtc_launch_ex", "rtc_launch_counts_get", "rtc_launch_counts_reset", "rtc_timer_start", "rtc_timer_stop",
     "rtc_profile_enable", "rtc_profile_get", "rtc_trace_closest", "rtc_trace_any", "rtc_trace_count", "rtc_generate_primary",
     "rtc_composite", "rtc_tonemap", "rtc_stats_get", "rtc_stats_reset",
-    "rtc_launch_pass_stats_get", "rtc_probe_gather", "rtc_probe_pipes",
+    "rtc_launch_pass_stats_get", "rtc_probe_gather", "rtc_probe_pipes", "rtc_scene_export", "rtc_gas_info", "rtc_gas_export",
 ]
 
 
@@ -40,7 +40,7 @@ class Stats(C.Structure):
 
 class SceneInfo(C.Structure):
     _fields_ = [("numNodes", C.c_uint64), ("numTris", C.c_uint64), ("numInstances", C.c_uint32), ("numTlasNodes", C.c_uint32),
-                ("numGas", C.c_uint32), ("reserved", C.c_uint32), ("gasBuildMs", C.c_double), ("iasBuildMs", C.c_double)]
+                ("numGas", C.c_uint32), ("numTlasLeaves", C.c_uint32), ("gasBuildMs", C.c_double), ("iasBuildMs", C.c_double)]
 
 
 class TraceCounts(C.Structure):
@@ -111,6 +111,9 @@ def lib():
         L.rtc_composite.argtypes = [C.c_void_p, C.c_void_p]
         L.rtc_tonemap.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]
         L.rtc_stats_get.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.rtc_scene_export.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rtc_gas_info.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.rtc_gas_export.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.rtc_launch_pass_stats_get.argtypes = [C.c_void_p, C.POINTER(PassStats)]
         L.rtc_probe_gather.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_double)]
         L.rtc_probe_pipes.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
@@ -258,6 +261,27 @@ class Context:
         out = (TraceCounts * 2)()
         _check(self.L.rtc_launch_counts_get(self.h, out))
         return out[0], out[1]
+
+    def scene_export(self, top):
+        """The acceleration structure as host arrays: dict(tlas_nodes [n, 80] u1, tlas_leaves u4, world_to_object [n, 12] f4,
+        instance_gas u4, gas {handle: (nodes [m, 80] u1, tris [t, 12] f4)})."""
+        info = self.scene_info(top)
+        nodes = np.zeros((info.numTlasNodes, 80), dtype=np.uint8)
+        leaves = np.zeros(max(info.numTlasLeaves, 1), dtype=np.uint32)
+        w2o = np.zeros((info.numInstances, 12), dtype=np.float32)
+        inst_gas = np.zeros(max(info.numInstances, 1), dtype=np.uint32)
+        _check(self.L.rtc_scene_export(self.h, int(top), nodes.ctypes.data_as(C.c_void_p), leaves.ctypes.data_as(C.c_void_p),
+                                       w2o.ctypes.data_as(C.c_void_p), inst_gas.ctypes.data_as(C.c_void_p)))
+        gas = {}
+        for g in sorted(set(int(v) for v in inst_gas[:info.numInstances])):
+            nn, nt = C.c_uint64(0), C.c_uint64(0)
+            _check(self.L.rtc_gas_info(self.h, g, C.byref(nn), C.byref(nt)))
+            gn = np.zeros((nn.value, 80), dtype=np.uint8)
+            gt = np.zeros((max(nt.value, 1), 12), dtype=np.float32)
+            _check(self.L.rtc_gas_export(self.h, g, gn.ctypes.data_as(C.c_void_p), gt.ctypes.data_as(C.c_void_p)))
+            gas[g] = (gn, gt[:nt.value])
+        return {"tlas_nodes": nodes, "tlas_leaves": leaves[:info.numTlasLeaves], "world_to_object": w2o,
+                "instance_gas": inst_gas[:info.numInstances], "gas": gas}
 
     def launch_pass_stats(self):
         """(extend, connect): {phase: (passes, slots processed, mean lanes per pass)} of the ray pool during count_work launches."""

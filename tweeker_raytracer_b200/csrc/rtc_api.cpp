@@ -414,6 +414,7 @@ int rtc_ias_build(rtc_context* ctx, const rtc_instance_desc* instances, uint32_t
   std::vector<rt_GeometryInstanceData> gi(numInstances);
   SceneRecord* rec = new SceneRecord();
   rec->inverses.resize((size_t)numInstances * 12u);
+  rec->instGas.resize(numInstances);
   std::set<uint32_t> distinct;
   for (uint32_t i = 0; i < numInstances; ++i)
   {
@@ -422,6 +423,7 @@ int rtc_ias_build(rtc_context* ctx, const rtc_instance_desc* instances, uint32_t
     if (d.gas >= ctx->gas.size() || ctx->gas[d.gas].d_nodes == nullptr) { delete rec; RTC_FAIL("bad gas handle in instance"); }
     const GasRecord& g = ctx->gas[d.gas];
     distinct.insert(d.gas);
+    rec->instGas[i] = d.gas;
     float* inv = &rec->inverses[(size_t)i * 12u];
     invert_3x4(d.transform, inv);
     for (int r = 0; r < 3; ++r)
@@ -519,7 +521,7 @@ int rtc_scene_info_get(rtc_context* ctx, uint64_t topObject, rtc_scene_info* inf
   if (!s) RTC_FAIL("unknown topObject");
   std::memset(info, 0, sizeof(*info));
   info->numNodes = s->totalNodes; info->numTris = s->totalTris; info->numInstances = s->desc.numInstances;
-  info->numTlasNodes = s->desc.numTlasNodes; info->numGas = s->numGas; info->gasBuildMs = s->gasBuildMs; info->iasBuildMs = s->iasBuildMs;
+  info->numTlasNodes = s->desc.numTlasNodes; info->numTlasLeaves = s->desc.numTlasLeaves; info->numGas = s->numGas; info->gasBuildMs = s->gasBuildMs; info->iasBuildMs = s->iasBuildMs;
   return 0;
 }
 
@@ -592,6 +594,38 @@ int rtc_texture_destroy(rtc_context* ctx, uint64_t handle)
       return 0;
     }
   RTC_FAIL("unknown texture handle");
+}
+
+int rtc_scene_export(rtc_context* ctx, uint64_t topObject, void* tlasNodes, uint32_t* tlasLeaves, float* worldToObject, uint32_t* instanceGas)
+{
+  SceneRecord* s = find_scene(ctx, topObject);
+  if (!s) RTC_FAIL("unknown topObject");
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  RTC_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (tlasNodes) RTC_CUDA(cudaMemcpy(tlasNodes, s->d_tlasNodes, (size_t)s->desc.numTlasNodes * sizeof(Node8), cudaMemcpyDeviceToHost));
+  if (tlasLeaves && s->desc.numTlasLeaves) RTC_CUDA(cudaMemcpy(tlasLeaves, s->d_tlasLeaves, (size_t)s->desc.numTlasLeaves * 4u, cudaMemcpyDeviceToHost));
+  if (worldToObject) std::memcpy(worldToObject, s->inverses.data(), s->inverses.size() * sizeof(float));
+  if (instanceGas) std::memcpy(instanceGas, s->instGas.data(), s->instGas.size() * sizeof(uint32_t));
+  return 0;
+}
+
+int rtc_gas_info(rtc_context* ctx, uint32_t gas, uint64_t* numNodes, uint64_t* numTris)
+{
+  if (gas >= ctx->gas.size() || ctx->gas[gas].d_nodes == nullptr) RTC_FAIL("bad gas handle");
+  if (numNodes) *numNodes = ctx->gas[gas].numNodes;
+  if (numTris) *numTris = ctx->gas[gas].numTris;
+  return 0;
+}
+
+int rtc_gas_export(rtc_context* ctx, uint32_t gas, void* nodes, float* tris)
+{
+  if (gas >= ctx->gas.size() || ctx->gas[gas].d_nodes == nullptr) RTC_FAIL("bad gas handle");
+  const GasRecord& g = ctx->gas[gas];
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  RTC_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (nodes) RTC_CUDA(cudaMemcpy(nodes, g.d_nodes, (size_t)g.numNodes * sizeof(Node8), cudaMemcpyDeviceToHost));
+  if (tris && g.numTris) RTC_CUDA(cudaMemcpy(tris, g.d_tris, (size_t)g.numTris * 12u * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 int rtc_instance_inverse(rtc_context* ctx, uint64_t topObject, uint32_t instance, float out[12])

@@ -93,6 +93,7 @@ struct SceneRecord
   uint32_t numCutout = 0;                  // instances using the cutout hit records: > 0 selects the ordered any-hit path
   bool     albedoTextures = false;         // MaterialDefinition.textureAlbedo may be non-zero: selects the textured shade kernels
   std::vector<float> inverses;             // 12 floats per instance (host copy of the world->object matrices)
+  std::vector<uint32_t> instGas;           // GAS handle per instance
   uint64_t totalNodes = 0, totalTris = 0;  // unique GAS nodes / triangles referenced + instance level
   uint32_t numGas = 0;
   double   gasBuildMs = 0.0, iasBuildMs = 0.0;

@@ -106,17 +106,23 @@ struct BoxRay
   uint32_t octinv;           // 7 ^ octant, octant bit2 = dx<0, bit1 = dy<0, bit0 = dz<0
 };
 
+// EXACT = false: rcp.approx (the timed kernels; the box test only has to be conservative and its 2^-17 padding covers the
+// approximation).  EXACT = true: IEEE reciprocal -- the counting kernels, whose node / triangle / instance counters the scalar
+// oracle reproduces ray by ray on the exported BVH (oracle/wide_bvh.inc); rcp.approx has no portable definition.
+template <bool EXACT>
 __device__ __forceinline__ float fast_rcp(float d)
 {
   if (fabsf(d) < 0x1p-80f) d = copysignf(0x1p-80f, d);
+  if (EXACT) return __frcp_rn(d);
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
   return r;
 }
 
+template <bool EXACT = false>
 __device__ __forceinline__ void box_setup(BoxRay& b, float ox, float oy, float oz, float dx, float dy, float dz)
 {
-  b.idx = fast_rcp(dx); b.idy = fast_rcp(dy); b.idz = fast_rcp(dz);
+  b.idx = fast_rcp<EXACT>(dx); b.idy = fast_rcp<EXACT>(dy); b.idz = fast_rcp<EXACT>(dz);
   b.ox = ox; b.oy = oy; b.oz = oz;
   const uint32_t oct = ((dx < 0.0f) ? 4u : 0u) | ((dy < 0.0f) ? 2u : 0u) | ((dz < 0.0f) ? 1u : 0u);
   b.octinv = 7u ^ oct;
@@ -296,7 +302,7 @@ struct Traversal
     if (COUNT) { counts.nodes = 0; counts.tris = 0; counts.insts = 0; }
     if (!(tlimit > tmin)) return false;
     sp = 0; blasBase = -1; curInst = 0;
-    box_setup(br, o.x, o.y, o.z, d.x, d.y, d.z);
+    box_setup<COUNT>(br, o.x, o.y, o.z, d.x, d.y, d.z);
 #if RTC_RESTORE_WORLD
     smRay[11 * BLOCK] = br.idx; smRay[12 * BLOCK] = br.idy; smRay[13 * BLOCK] = br.idz; smRay[14 * BLOCK] = __uint_as_float(br.octinv);
 #endif
@@ -361,7 +367,7 @@ struct Traversal
         orr.dy = __fmaf_rn(r1.x, wdx, __fmaf_rn(r1.y, wdy, __fmul_rn(r1.z, wdz)));
         orr.dz = __fmaf_rn(r2.x, wdx, __fmaf_rn(r2.y, wdy, __fmul_rn(r2.z, wdz)));
         shear_setup(orr);
-        box_setup(br, oox, ooy, ooz, orr.dx, orr.dy, orr.dz);
+        box_setup<COUNT>(br, oox, ooy, ooz, orr.dx, orr.dy, orr.dz);
         curInst = inst;
         blasBase = sp;
         nodes = reinterpret_cast<const uint4*>(((unsigned long long)__float_as_uint(r3.y) << 32) | __float_as_uint(r3.x));
@@ -410,7 +416,7 @@ struct Traversal
         br.ox = smRay[0]; br.oy = smRay[BLOCK]; br.oz = smRay[2 * BLOCK];
         br.idx = smRay[11 * BLOCK]; br.idy = smRay[12 * BLOCK]; br.idz = smRay[13 * BLOCK]; br.octinv = __float_as_uint(smRay[14 * BLOCK]);
 #else
-        box_setup(br, smRay[0], smRay[BLOCK], smRay[2 * BLOCK], smRay[3 * BLOCK], smRay[4 * BLOCK], smRay[5 * BLOCK]);
+        box_setup<COUNT>(br, smRay[0], smRay[BLOCK], smRay[2 * BLOCK], smRay[3 * BLOCK], smRay[4 * BLOCK], smRay[5 * BLOCK]);
 #endif
       }
       if (sp == 0) return false;

@@ -348,7 +348,7 @@ __device__ __forceinline__ void trace_pool(const SceneDesc& sc, uint32_t n, uint
         orr.dz = __fmaf_rn(r2.x, wdx, __fmaf_rn(r2.y, wdy, __fmul_rn(r2.z, wdz)));
         shear_setup(orr);
         BoxRay br;
-        box_setup(br, oox, ooy, ooz, orr.dx, orr.dy, orr.dz);
+        box_setup<COUNT>(br, oox, ooy, ooz, orr.dx, orr.dy, orr.dz);
         p.f(W_OORG, slot) = oox; p.f(W_OORG + 1, slot) = ooy; p.f(W_OORG + 2, slot) = ooz;
         p.f(W_OINV, slot) = br.idx; p.f(W_OINV + 1, slot) = br.idy; p.f(W_OINV + 2, slot) = br.idz;
         p.f(W_SHEAR, slot) = orr.Sx; p.f(W_SHEAR + 1, slot) = orr.Sy; p.f(W_SHEAR + 2, slot) = orr.Sz;
@@ -402,7 +402,7 @@ __device__ __forceinline__ void trace_pool(const SceneDesc& sc, uint32_t n, uint
             else
             {
               BoxRay br;
-              box_setup(br, o.x, o.y, o.z, d.x, d.y, d.z);
+              box_setup<COUNT>(br, o.x, o.y, o.z, d.x, d.y, d.z);
               p.f(W_WORG, slot) = o.x; p.f(W_WORG + 1, slot) = o.y; p.f(W_WORG + 2, slot) = o.z;
               p.f(W_WINV, slot) = br.idx; p.f(W_WINV + 1, slot) = br.idy; p.f(W_WINV + 2, slot) = br.idz;
               p.f(W_WDIR, slot) = d.x; p.f(W_WDIR + 1, slot) = d.y; p.f(W_WDIR + 2, slot) = d.z;
