@@ -370,7 +370,7 @@ def ncu_measure(args):
     if not os.path.exists(ncu):
         return None, "ncu not found"
     log = os.path.join(tempfile.mkdtemp(), "ncu_child.csv")
-    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,smsp__thread_inst_executed.sum,gpu__time_duration.sum",
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,smsp__inst_executed.sum,smsp__thread_inst_executed.sum,gpu__time_duration.sum",
            "--clock-control", "none", "-k", "regex:k_trace|k_extend_primary", "--csv", "--log-file", log,
            sys.executable, os.path.abspath(__file__), "--ncu-child", "--config", args.config, "--scene", args.scene, "--resolution", args.resolution,
            "--spp-per-step", str(args.spp_per_step), "--instances", str(args.instances)]
@@ -402,6 +402,7 @@ def ncu_measure(args):
         if sel:
             res[key] = {"launches": len(sel),
                         "dram_bytes_per_launch": sum(l.get("dram__bytes_read.sum", 0) + l.get("dram__bytes_write.sum", 0) for l in sel) / len(sel),
+                        "l2_bytes_per_launch": sum(l.get("lts__t_bytes.sum", 0) for l in sel) / len(sel),
                         "warp_inst_per_launch": sum(l.get("smsp__inst_executed.sum", 0) for l in sel) / len(sel),
                         "thread_inst_per_warp_inst": sum(l.get("smsp__thread_inst_executed.sum", 0) for l in sel) / max(sum(l.get("smsp__inst_executed.sum", 0) for l in sel), 1)}
     return (res, "ncu child run of one step in this bench run (dram__bytes_read.sum + dram__bytes_write.sum, smsp__inst_executed.sum per launch)") if res else (None, "no traversal kernels in the ncu log")
@@ -409,9 +410,9 @@ def ncu_measure(args):
 
 def probes(ctx):
     """Roofline denominators measured now, on this GPU (csrc/probes.cu)."""
-    return {"l2_gather_gbs": ctx.probe_gather(32 << 20), "hbm_gather_gbs": ctx.probe_gather(8 << 30),
+    return {"l2_gather_gbs": ctx.probe_gather(32 << 20), "hbm_gather_16B_gbs": ctx.probe_gather(8 << 30),
             "fp32_tflops": ctx.probe_pipes(0), "issue_gwarpinst_per_s": ctx.probe_pipes(1),
-            "how": "rtc_probe_gather: random 16-byte LDG.128 gathers over a 32 MB (L2-resident) and an 8 GB working set; rtc_probe_pipes: independent FFMA chains, and FFMA + LOP3 alternating"}
+            "how": "rtc_probe_gather: random 16-byte LDG.128 gathers over a 32 MB (L2-resident) working set, and over 8 GB (every 16-byte gather costs a 32-byte sector and mostly a TLB miss: a floor, not a roofline); rtc_probe_pipes: independent FFMA chains, and FFMA + LOP3 alternating"}
 
 
 def main():
@@ -481,9 +482,12 @@ def main():
         # the one exchange step of the path: ncclReduce(mean) of the per-rank running averages over NVLink, on the render stream
         app.group_reduce_mean(frame.data_ptr(), combined.data_ptr() if rank == 0 else 0, pixels * 4)
 
+    from tweeker_raytracer_b200 import partition
+
     def step(s, count_work=False):
         # sample-range partition: rank r of n renders iteration indices (s*n + r)*S .. +S as samples s*S.. of its own average
-        ctx.launch_ex(sysd, w, h, core.RAYGEN_FULL_FRAME, app.info.miss, (s * n + rank) * S, S, s * S, count_work)
+        first, count, accum = partition.bench_step_range(s, rank, n, S_total, args.scaling)
+        ctx.launch_ex(sysd, w, h, core.RAYGEN_FULL_FRAME, app.info.miss, first, count, accum, count_work)
 
     def barrier():
         torch.cuda.synchronize()
@@ -554,26 +558,36 @@ def main():
     con_ms, con_launches = prof["connect"]
     peak, peak_src = measured_peak()
     achieved = ext_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
-    fractions = {"hbm": achieved / peak}
+    # Two kinds of fractions.  ALGORITHMIC: the bytes / flops the algorithm needs per second over a peak -- how the work compares
+    # with what the memory system or the FP32 pipe could stream; above 1 against the L2 gather probe simply means that L1 serves
+    # most node fetches.  PHYSICAL (from the ncu child run of one step): what the kernel really moved or issued over the
+    # same peaks; `bound` is the largest physical fraction, i.e. the resource the kernel actually saturates.
+    fractions = {"hbm_algorithmic": achieved / peak}
     peaks = {"hbm_gbs": peak}
     if not args.no_probes and rank == 0:
         pr = probes(ctx)
         peaks.update(pr)
-        fractions["l2"] = achieved / pr["l2_gather_gbs"]
-        fractions["fp32"] = (ext_flops / (ext_ms * 1e-3) / 1e12) / pr["fp32_tflops"] if ext_ms > 0 else 0.0
+        fractions["l2_algorithmic"] = achieved / pr["l2_gather_gbs"]
+        fractions["fp32_algorithmic"] = (ext_flops / (ext_ms * 1e-3) / 1e12) / pr["fp32_tflops"] if ext_ms > 0 else 0.0
     traffic, traffic_src, ncu_res = None, "not measured (--no-ncu or N > 1)", None
+    physical = {}
     if rank == 0 and n == 1 and not args.no_ncu:
         ncu_res, traffic_src = ncu_measure(args)
-        if ncu_res and "extend" in ncu_res:
-            traffic = ncu_res["extend"]["dram_bytes_per_launch"]
-            if "issue_gwarpinst_per_s" in peaks and ext_ms > 0:
-                # executed warp instructions of the step's extend launches (ncu child) / the device time of the same launches here
-                fractions["issue"] = (ncu_res["extend"]["warp_inst_per_launch"] * ncu_res["extend"]["launches"] / (ext_ms / K * 1e-3) / 1e9) / peaks["issue_gwarpinst_per_s"]
-    bound = max(fractions, key=fractions.get)
+        if ncu_res and "extend" in ncu_res and ext_ms > 0:
+            e = ncu_res["extend"]
+            traffic = e["dram_bytes_per_launch"]
+            step_s = ext_ms / K * 1e-3                # device time of one step's extend launches in THIS run (not under ncu)
+            physical["dram"] = e["dram_bytes_per_launch"] * e["launches"] / step_s / 1e9 / peak
+            if "l2_gather_gbs" in peaks:
+                physical["l2"] = e["l2_bytes_per_launch"] * e["launches"] / step_s / 1e9 / peaks["l2_gather_gbs"]
+            if "issue_gwarpinst_per_s" in peaks:
+                physical["issue"] = e["warp_inst_per_launch"] * e["launches"] / step_s / 1e9 / peaks["issue_gwarpinst_per_s"]
+            fractions.update(physical)
+    bound = max(physical, key=physical.get) if physical else "hbm"
     roofline = {"bound": bound, "kernel": "k_trace<ANY=0, ExtendPaths> + k_extend_primary (closest-hit traversal of the radiance rays)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "fractions": fractions, "peaks": peaks,
-                "fractions_note": "hbm and l2: ALGORITHMIC bytes per second over the HBM copy peak / the L2 gather probe; fp32: algorithmic flops (192 per node, 60 per triangle, 36 per instance) over the FFMA probe; issue: executed warp instructions (ncu child) over the issue probe.  The BVH lives in L2, so `traffic` (real DRAM bytes) is far below the algorithmic bytes: the kernel is bound by instruction issue at partial SIMD occupancy, not by HBM",
+                "fractions_note": "*_algorithmic: algorithmic bytes (or flops: 192 per node, 60 per triangle, 36 per instance) per second over the HBM copy peak / the L2 gather probe / the FFMA probe (`frac` is hbm_algorithmic, the contract's figure).  dram, l2, issue: PHYSICAL -- DRAM bytes, L2 bytes and executed warp instructions of the step's extend launches (ncu child) over the same peaks; `bound` is the largest of them.  The BVH lives in L2/L1, so real DRAM traffic is a small fraction of the algorithmic bytes: the kernel is bound by instruction issue at partial SIMD occupancy",
                 "algorithmic_bytes_per_launch": ext_bytes / max(ext_launches, 1),
                 "avg_launch_ms": ext_ms / max(ext_launches, 1), "launches": int(ext_launches),
                 "per_ray": {"nodes": ext.nodes / max(ext.rays, 1), "tris": ext.tris / max(ext.rays, 1), "instances": ext.instances / max(ext.rays, 1),
@@ -825,13 +839,12 @@ def run_rays(args, rank, local_rank, world):
     flops_ray = (F_NODE * counts.nodes + F_TRI * counts.tris + F_INST * counts.instances) / max(counts.rays, 1)
     peak, peak_src = measured_peak()
     achieved = per_ray * nrays * K / (ms * 1e-3) / 1e9
-    fractions, peaks = {"hbm": achieved / peak}, {"hbm_gbs": peak}
+    fractions, peaks = {"hbm_algorithmic": achieved / peak}, {"hbm_gbs": peak}
     if not args.no_probes and rank == 0:
         pr = probes(ctx)
         peaks.update(pr)
-        fractions["l2"] = achieved / pr["l2_gather_gbs"]
-        fractions["hbm_gather"] = achieved / pr["hbm_gather_gbs"]
-        fractions["fp32"] = flops_ray * nrays * K / (ms * 1e-3) / 1e12 / pr["fp32_tflops"]
+        fractions["l2_algorithmic"] = achieved / pr["l2_gather_gbs"]
+        fractions["fp32_algorithmic"] = flops_ray * nrays * K / (ms * 1e-3) / 1e12 / pr["fp32_tflops"]
     bvh_mb = (info.numNodes * 80 + info.numTris * 48) / 1e6
     # end to end: rays from pinned host memory, hits back to host memory, every step (a bounded set of 2^24 rays)
     ne = min(nrays, 1 << 24)
@@ -862,7 +875,7 @@ def run_rays(args, rank, local_rank, world):
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": ne * 32, "d2h_bytes_per_step": ne * (20 if mode == "closest" else 4),
                         "path": "rtc_upload (pinned host rays) + rtc_trace_%s + rtc_download (hits) of %d rays per step" % (mode, ne)},
                 "gpu_launches": launches, "clocks": sampler.summary(),
-                "roofline": {"bound": max(fractions, key=fractions.get), "kernel": "k_trace<ANY=%d, Query%s>" % (mode == "any", "Closest" if mode == "closest" else "Any"),
+                "roofline": {"bound": "hbm" if bvh_mb > 126.0 else "l2", "kernel": "k_trace<ANY=%d, Query%s>" % (mode == "any", "Closest" if mode == "closest" else "Any"),
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                              "fractions": fractions, "peaks": peaks,
                              "per_ray": {"nodes": counts.nodes / max(counts.rays, 1), "tris": counts.tris / max(counts.rays, 1), "bytes": per_ray, "flops": flops_ray}}}

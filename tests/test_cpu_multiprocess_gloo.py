@@ -94,3 +94,24 @@ def test_sample_range_matches_host_library(built):
         assert len(set(covered)) == len(covered)
         if spp % world == 0:
             assert sorted(covered) == list(range(spp))
+
+
+def test_bench_step_ranges_weak_and_strong():
+    """bench.py's partition of a timed step: disjoint iteration indices per rank; under strong scaling the ranks of a step
+    together draw exactly the one-GPU step's seed iterations, so the combined frame holds the same samples for every N."""
+    from tweeker_raytracer_b200 import partition
+    for world in (1, 2, 4, 8):
+        for scaling in ("weak", "strong"):
+            seen = []
+            for step in range(3):
+                per_step = []
+                for rank in range(world):
+                    first, count, accum = partition.bench_step_range(step, rank, world, 32, scaling)
+                    assert count == (32 // world if scaling == "strong" else 32) and accum == step * count
+                    per_step += list(range(first, first + count))
+                if scaling == "strong":
+                    assert sorted(per_step) == list(range(step * 32, (step + 1) * 32))
+                seen += per_step
+            assert len(seen) == len(set(seen))
+    with pytest.raises(ValueError):
+        partition.bench_step_range(0, 0, 3, 32, "strong")

@@ -14,6 +14,7 @@
 // the primary-ray extend kernel generates its rays with the shading arithmetic of this translation unit (see ExtendPrimary)
 #define RTC_STACK_OVERFLOW_COUNTER g_rtcStackOverflowsPrimary
 #include "trace_pool.cuh"
+#include "trace_packet.cuh"
 
 #include <cstdlib>
 
@@ -243,6 +244,17 @@ k_extend_primary_pool(const SceneDesc sc, const ExtendPrimary policy, uint32_t n
   rtpool::trace_pool<false, COUNT, false>(sc, n, cursor, policy, poolWords + warp * rtpool::warp_words(false, false), overflow + warpGlobal * rtpool::kOverflowPerWarp, counts);
 }
 constexpr size_t kPrimaryPoolSmem = (size_t)(kPrimaryBlock / 32) * rtpool::warp_bytes(false, false);
+
+// Packet traversal of the primary rays (trace_packet.cuh): a warp = one 8x4 pixel tile = one shared traversal.
+#ifndef RTC_PACKET_BLOCKS
+#define RTC_PACKET_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(kPrimaryBlock, RTC_PACKET_BLOCKS)
+k_extend_primary_packet(const SceneDesc sc, const ExtendPrimary policy, uint32_t n, uint32_t* __restrict__ cursor)
+{
+  __shared__ uint2 stacks[(kPrimaryBlock / 32) * RTC_PACKET_STACK];
+  trace_packets(sc, n, cursor, policy, stacks + (threadIdx.x >> 5) * RTC_PACKET_STACK);
+}
 
 template <bool COUNT>
 __global__ void __launch_bounds__(kPrimaryBlock, RTC_TRACE_MIN_BLOCKS)
@@ -1092,7 +1104,12 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
       {
         if (int rc = profile_begin(ctx, RTC_KERNEL_EXTEND)) return rc;
         ExtendPrimary policy = { a };
-        if (ctx->traceDriver == RTC_DRIVER_POOL)
+        if (ctx->primaryPackets && !countWork)
+        {
+          // the counting pass keeps the per-ray kernel: its counters are the per-ray work the scalar oracle reproduces
+          k_extend_primary_packet<<<ctx->numSMs * RTC_PACKET_BLOCKS, kPrimaryBlock, 0, ctx->stream>>>(scene->desc, policy, a.numPaths, cnt + 128);
+        }
+        else if (ctx->traceDriver == RTC_DRIVER_POOL)
         {
           const int gridTrace = ctx->numSMs * RTC_POOL_BLOCKS;
           uint2* overflow = nullptr;

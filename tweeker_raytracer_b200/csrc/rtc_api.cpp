@@ -119,6 +119,7 @@ static int context_init(rtc_context* ctx, int deviceOrdinal)
   ctx->numSMs = prop.multiProcessorCount;
   // traversal driver: one ray per lane (default) or the per-warp ray pool; both are compiled, RTC_TRACE_DRIVER=lane|pool picks
   ctx->traceDriver = RTC_DRIVER_LANE;
+  if (const char* e = getenv("RTC_PRIMARY_PACKETS")) ctx->primaryPackets = atoi(e) != 0;
   if (const char* e = getenv("RTC_TRACE_DRIVER")) ctx->traceDriver = (e[0] == 'p' || e[0] == '1') ? RTC_DRIVER_POOL : RTC_DRIVER_LANE;
   RTC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   {

@@ -151,6 +151,7 @@ struct rtc_context
   cudaEvent_t  shadeFork = nullptr, shadeJoin[6] = {};
   unsigned long long* d_launchCounts = nullptr;   // 3 x kTraceCountWords: extend, connect, rtc_trace_count
   uint32_t* d_cursor = nullptr;                   // ray cursor of the query kernels (rtc_trace_*)
+  bool   primaryPackets = false;                  // primary rays by packet traversal (trace_packet.cuh); RTC_PRIMARY_PACKETS=0 turns it off
   int    traceDriver = 0;                         // RTC_DRIVER_LANE or RTC_DRIVER_POOL: which traversal driver the launches use
   void*  d_poolScratch = nullptr;                 // global part of the ray pool's traversal stacks (trace_pool.cuh), grown on demand
   size_t poolScratchBytes = 0;

@@ -18,6 +18,9 @@
 #ifndef RTC_RESTORE_WORLD
 #define RTC_RESTORE_WORLD 1       // world-space box constants restored from shared memory when an instance is left
 #endif
+#ifndef RTC_LEAF_THRESHOLD
+#define RTC_LEAF_THRESHOLD 0      // > 0: hold lanes with a pending leaf group back until this many lanes of the warp have one (trace_stream)
+#endif
 #ifndef RTC_FETCH_THRESHOLD
 #define RTC_FETCH_THRESHOLD 8     // refill a warp when at least this many lanes have finished their ray
 #endif
@@ -312,8 +315,13 @@ struct Traversal
     return true;
   }
 
-  // returns true while the ray needs more steps
-  __device__ __forceinline__ bool step(const SceneDesc& sc)
+  // A step = node_phase (visit one wide node, or take a popped leaf group) + leaf_phase (test the triangles / enter the
+  // instance the leaf group holds) + advance (pop the next group, leave the instance, or finish).  The driver may run the
+  // three for all lanes in every iteration (step) or hold lanes with a pending leaf group back until enough of them have
+  // one (trace_stream, RTC_LEAF_THRESHOLD).
+  __device__ __forceinline__ bool has_leaves() const { return triGroup.y != 0u; }
+
+  __device__ __forceinline__ void node_phase()
   {
     if (nodeGroup.y & 0xff000000u)
     {
@@ -344,7 +352,11 @@ struct Traversal
       triGroup = nodeGroup;
       nodeGroup = make_uint2(0u, 0u);
     }
+  }
 
+  // returns false when the ray is finished (ANY: first hit)
+  __device__ __forceinline__ bool leaf_phase(const SceneDesc& sc)
+  {
     while (triGroup.y)
     {
       const uint32_t idx = (uint32_t)__ffs((int)triGroup.y) - 1u;
@@ -405,7 +417,12 @@ struct Traversal
         }
       }
     }
+    return true;
+  }
 
+  // returns false when the traversal is complete
+  __device__ __forceinline__ bool advance(const SceneDesc& sc)
+  {
     if (!(nodeGroup.y & 0xff000000u))
     {
       if (blasBase >= 0 && sp == blasBase)
@@ -423,6 +440,14 @@ struct Traversal
       nodeGroup = pop();
     }
     return true;
+  }
+
+  // returns true while the ray needs more steps
+  __device__ __forceinline__ bool step(const SceneDesc& sc)
+  {
+    node_phase();
+    if (!leaf_phase(sc)) return false;
+    return advance(sc);
   }
 };
 
@@ -470,6 +495,32 @@ __device__ __forceinline__ void trace_stream(const SceneDesc& sc, uint32_t n, ui
       }
     }
     else if (idle == 0xffffffffu) break;      // nothing running and nothing left to fetch
+#if RTC_LEAF_THRESHOLD > 0
+    // Lanes whose node visit produced a leaf group (triangles to test or an instance to enter) are HELD BACK -- they skip
+    // node visits -- until RTC_LEAF_THRESHOLD lanes of the warp hold one (or a quarter of the running lanes, or nobody can
+    // visit a node any more); then all of them run the leaf phase together.  Nothing is reordered inside a ray; the leaf
+    // phase, which a warp used to run in almost every iteration for the ~3 lanes that had just found a leaf, runs every
+    // second or third iteration for 8+ lanes instead.
+    bool running = active;
+    if (active && !tr.has_leaves()) tr.node_phase();
+    const bool held = active && tr.has_leaves();
+    const uint32_t heldLanes = __ballot_sync(0xffffffffu, held), activeLanes = ~idle;
+    if (heldLanes)
+    {
+      const uint32_t nHeld = (uint32_t)__popc(heldLanes), nActive = (uint32_t)__popc(activeLanes);
+      if (nHeld >= RTC_LEAF_THRESHOLD || nHeld * 4u >= nActive)
+      {
+        if (held) running = tr.leaf_phase(sc);
+      }
+    }
+    if (running && !tr.has_leaves()) running = tr.advance(sc);
+    if (active && !running)
+    {
+      policy.store(tag, tr.result());
+      if (COUNT) { cNodes += tr.counts.nodes; cTris += tr.counts.tris; cInsts += tr.counts.insts; cRays++; }
+      active = false;
+    }
+#else
     if (active)
     {
       if (!tr.step(sc))
@@ -479,6 +530,7 @@ __device__ __forceinline__ void trace_stream(const SceneDesc& sc, uint32_t n, ui
         active = false;
       }
     }
+#endif
   }
   if (COUNT)
   {

@@ -51,3 +51,20 @@ def sample_range(step, rank, world, spp_per_step, samples_per_pixel):
 def combine_scale(world):
     """Factor applied after the sum-reduce of the per-rank running averages."""
     return 1.0 / world
+
+
+def bench_step_range(step, rank, world, spp_per_step, scaling="weak"):
+    """(first seed iteration, count, first accumulation index) of `rank` in bench.py's timed step `step`.
+
+    weak  : every rank renders spp_per_step iterations per step (total work grows with the number of GPUs);
+    strong: the step's spp_per_step iterations are split, spp_per_step / world per rank (total work is fixed), so the
+            ranks of step s together draw exactly the seed iterations [s * spp_per_step, (s + 1) * spp_per_step) of the
+            one-GPU step -- the combined frame holds the same samples whatever the number of GPUs.
+    Either way the ranks' iteration indices are disjoint and each rank accumulates its own running average from index 0."""
+    if scaling == "strong":
+        if spp_per_step % world != 0:
+            raise ValueError("strong scaling needs spp_per_step divisible by the number of ranks")
+        count = spp_per_step // world
+    else:
+        count = spp_per_step
+    return (step * world + rank) * count, count, step * count
