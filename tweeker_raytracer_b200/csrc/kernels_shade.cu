@@ -17,6 +17,7 @@
 #include "trace_packet.cuh"
 
 #include <cstdlib>
+#include <cstring>
 
 namespace {
 
@@ -697,10 +698,24 @@ k_cutout_radiance(const __grid_constant__ WfArgs a, const SceneDesc sc, const ui
 // __anyhit__shadow / __anyhit__shadow_cutout on the closest candidate of every shadow ray in queueIn.  No candidate left: the
 // light is visible, the contribution is added (closesthit.cu:289-299).  Ignored: queueOut (re-trace past it).  Once the ray
 // is resolved, a postponed Russian roulette is played and the survivor appended to the next extend queue.
+// where the survivors of a postponed Russian roulette go (the next depth's extend queue); device-resident so that the
+// kernels of the any-hit rounds have the same arguments at every depth (they are replayed from a CUDA graph)
+struct CutoutNext { uint32_t* queue; uint32_t* count; };
+
+__global__ void k_set_cutout_next(CutoutNext* next, uint32_t* queue, uint32_t* count) { next->queue = queue; next->count = count; }
+
+// loop condition of the any-hit rounds: another round is needed while the last one ignored a candidate
+__global__ void k_cutout_condition(cudaGraphConditionalHandle handle, const uint32_t* __restrict__ ignored)
+{
+  cudaGraphSetConditional(handle, *ignored != 0u ? 1u : 0u);
+}
+
 __global__ void __launch_bounds__(kBlock)
 k_cutout_shadow(const __grid_constant__ WfArgs a, const SceneDesc sc, const uint32_t* __restrict__ queueIn, const uint32_t* __restrict__ countIn,
-                uint32_t* __restrict__ queueOut, uint32_t* __restrict__ countOut, uint32_t* __restrict__ queueNext, uint32_t* __restrict__ countNext)
+                uint32_t* __restrict__ queueOut, uint32_t* __restrict__ countOut, const CutoutNext* __restrict__ next)
 {
+  uint32_t* __restrict__ queueNext = next->queue;
+  uint32_t* __restrict__ countNext = next->count;
   const uint32_t n = *countIn;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride)
@@ -991,7 +1006,7 @@ int ensure_cutout_buffers(rtc_context* ctx, uint64_t capacity)
   return 0;
 }
 
-// reads one device counter back (the ordered any-hit rounds need to know when no candidate was ignored any more)
+// reads one device counter back (host-synchronised rounds, RTC_CUTOUT_GRAPH=0)
 int read_counter(rtc_context* ctx, const uint32_t* d_counter, uint32_t* out)
 {
   RTC_CUDA(cudaMemcpyAsync(out, d_counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -999,10 +1014,129 @@ int read_counter(rtc_context* ctx, const uint32_t* d_counter, uint32_t* out)
   return 0;
 }
 
+inline CutoutNext* cutout_next(const WavefrontBuffers& wf) { return reinterpret_cast<CutoutNext*>(wf.cutCounters + 16); }
+
+// ---- the any-hit rounds as a device-side loop -------------------------------------------------------------------------------
+// The rounds "play the any-hit program on the closest candidates -> re-trace the ignored ones" repeat until no candidate was
+// ignored.  Round 1 reads the depth's own queue and is launched normally; the remaining rounds are a CUDA graph with a
+// conditional WHILE node whose body holds two rounds (the ping-pong of the two scratch queues makes every kernel argument
+// static) and whose condition is set on the device from the ignored-candidate counter (cudaGraphSetConditional).  No host
+// synchronisation: a launch of a scene with cutout materials is as asynchronous as any other.  One graph pair per wavefront
+// allocation / scene / SystemData, rebuilt when one of them changes.
+struct CutoutGraph
+{
+  cudaGraphExec_t radiance = nullptr, shadow = nullptr;
+  cudaGraph_t radianceGraph = nullptr, shadowGraph = nullptr;
+  const void* wfBase = nullptr; const void* cutBase = nullptr; const void* scene = nullptr;
+  rt_SystemData sys{};
+  int grid = 0;
+};
+
+int build_cutout_loop(rtc_context* ctx, const SceneRecord* scene, const WfArgs& a, int grid, bool shadow, cudaGraph_t* outGraph, cudaGraphExec_t* outExec)
+{
+  const WavefrontBuffers& wf = ctx->wf;
+  cudaGraph_t graph = nullptr;
+  RTC_CUDA(cudaGraphCreate(&graph, 0));
+  cudaGraphConditionalHandle handle;
+  RTC_CUDA(cudaGraphConditionalHandleCreate(&handle, graph, 0, cudaGraphCondAssignDefault));
+  // root: the condition from round 1's counter
+  cudaGraphNode_t condKernel = nullptr;
+  {
+    cudaKernelNodeParams kp{};
+    const uint32_t* counter = wf.cutCounters + 0;
+    void* args[2] = { &handle, &counter };
+    kp.func = (void*)k_cutout_condition; kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.kernelParams = args;
+    RTC_CUDA(cudaGraphAddKernelNode(&condKernel, graph, nullptr, 0, &kp));
+  }
+  cudaGraphNodeParams wp{};
+  wp.type = cudaGraphNodeTypeConditional;
+  wp.conditional.handle = handle; wp.conditional.type = cudaGraphCondTypeWhile; wp.conditional.size = 1;
+  cudaGraphNode_t whileNode = nullptr;
+  RTC_CUDA(cudaGraphAddNode(&whileNode, graph, &condKernel, 1, &wp));
+  cudaGraph_t body = wp.conditional.phGraph_out[0];
+  // body: two rounds, captured from the ordinary launch code
+  const bool wasProfiling = ctx->profiling;
+  ctx->profiling = false;                       // event pairs cannot be timed from inside a graph; the caller brackets the whole loop
+  RTC_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+  int rc = 0;
+  for (int o = 0; o < 2 && rc == 0; ++o)
+  {
+    // re-trace the candidates round o ignored, then play the any-hit program on what they found: ignored ones -> queue 1 - o
+    const int p = 1 - o;
+    if (shadow) rc = launch_connect_closest(ctx, &scene->desc, wf, wf.cutQueue[o], wf.cutCounters + o, wf.cutCounters + 2, true);
+    else        rc = launch_extend_after(ctx, &scene->desc, wf, wf.cutQueue[o], wf.cutCounters + o, wf.cutCounters + 2);
+    if (rc == 0 && cudaMemsetAsync(wf.cutCounters + p, 0, sizeof(uint32_t), ctx->stream) != cudaSuccess) rc = -1;
+    if (rc == 0)
+    {
+      if (shadow) k_cutout_shadow<<<grid, kBlock, 0, ctx->stream>>>(a, scene->desc, wf.cutQueue[o], wf.cutCounters + o, wf.cutQueue[p], wf.cutCounters + p, cutout_next(wf));
+      else        k_cutout_radiance<<<grid, kBlock, 0, ctx->stream>>>(a, scene->desc, wf.cutQueue[o], wf.cutCounters + o, wf.cutQueue[p], wf.cutCounters + p);
+    }
+  }
+  if (rc == 0) k_cutout_condition<<<1, 1, 0, ctx->stream>>>(handle, wf.cutCounters + 0);
+  cudaGraph_t captured = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(ctx->stream, &captured);
+  ctx->profiling = wasProfiling;
+  if (rc != 0 || e != cudaSuccess)
+  {
+    cudaGraphDestroy(graph);
+    cudaGetLastError();
+    if (rc != 0) return rc;
+    return rtc_set_error(__FILE__, __LINE__, "cudaStreamEndCapture(any-hit rounds)", (int)e, cudaGetErrorString(e));
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+  if (ei != cudaSuccess) { cudaGraphDestroy(graph); return rtc_set_error(__FILE__, __LINE__, "cudaGraphInstantiate(any-hit rounds)", (int)ei, cudaGetErrorString(ei)); }
+  *outGraph = graph; *outExec = exec;
+  return 0;
+}
+
+void destroy_cutout_graph(CutoutGraph* g)
+{
+  if (!g) return;
+  if (g->radiance) cudaGraphExecDestroy(g->radiance);
+  if (g->shadow) cudaGraphExecDestroy(g->shadow);
+  if (g->radianceGraph) cudaGraphDestroy(g->radianceGraph);
+  if (g->shadowGraph) cudaGraphDestroy(g->shadowGraph);
+  *g = CutoutGraph();
+}
+
+int ensure_cutout_graph(rtc_context* ctx, const SceneRecord* scene, const WfArgs& a, int grid)
+{
+  CutoutGraph* g = static_cast<CutoutGraph*>(ctx->cutoutGraph);
+  if (!g) { g = new CutoutGraph(); ctx->cutoutGraph = g; }
+  const WavefrontBuffers& wf = ctx->wf;
+  if (g->radiance && g->wfBase == wf.base && g->cutBase == wf.cutBase && g->scene == scene && g->grid == grid && std::memcmp(&g->sys, &a.sys, sizeof(rt_SystemData)) == 0)
+    return 0;
+  RTC_CUDA(cudaStreamSynchronize(ctx->stream));      // an old graph may still be running
+  destroy_cutout_graph(g);
+  if (int rc = build_cutout_loop(ctx, scene, a, grid, false, &g->radianceGraph, &g->radiance)) { destroy_cutout_graph(g); return rc; }
+  if (int rc = build_cutout_loop(ctx, scene, a, grid, true, &g->shadowGraph, &g->shadow)) { destroy_cutout_graph(g); return rc; }
+  g->wfBase = wf.base; g->cutBase = wf.cutBase; g->scene = scene; g->grid = grid; g->sys = a.sys;
+  return 0;
+}
+
+bool cutout_graph_enabled()
+{
+  static const bool on = []() { const char* e = getenv("RTC_CUTOUT_GRAPH"); return e && atoi(e) != 0; }();
+  return on;
+}
+
 // After extend: play __anyhit__radiance_cutout on the closest candidates, re-trace the ignored ones, repeat until none is ignored.
 int resolve_radiance_candidates(rtc_context* ctx, const SceneRecord* scene, const WfArgs& a, int grid, const uint32_t* queue, const uint32_t* count)
 {
   const WavefrontBuffers& wf = ctx->wf;
+  if (cutout_graph_enabled())
+  {
+    if (int rc = ensure_cutout_graph(ctx, scene, a, grid)) return rc;
+    RTC_CUDA(cudaMemsetAsync(wf.cutCounters + 0, 0, sizeof(uint32_t), ctx->stream));
+    if (int rc = profile_begin(ctx, RTC_KERNEL_SHADE)) return rc;
+    k_cutout_radiance<<<grid, kBlock, 0, ctx->stream>>>(a, scene->desc, queue, count, wf.cutQueue[0], wf.cutCounters + 0);
+    if (int rc = profile_end(ctx)) return rc;
+    if (int rc = profile_begin(ctx, RTC_KERNEL_EXTEND)) return rc;       // the whole loop (re-traces dominate) as one span
+    RTC_CUDA(cudaGraphLaunch(static_cast<CutoutGraph*>(ctx->cutoutGraph)->radiance, ctx->stream));
+    ctx->kernelLaunches += 6;                                            // one body execution; further rounds are not counted
+    return profile_end(ctx);
+  }
   for (int round = 0;; ++round)
   {
     const int o = round & 1;
@@ -1025,13 +1159,26 @@ int resolve_shadow_candidates(rtc_context* ctx, const SceneRecord* scene, const 
 {
   const WavefrontBuffers& wf = ctx->wf;
   const uint32_t* queue = wf.shadowQueue; const uint32_t* count = shadowCount;
+  k_set_cutout_next<<<1, 1, 0, ctx->stream>>>(cutout_next(wf), queueNext, countNext);
   if (int rc = launch_connect_closest(ctx, &scene->desc, wf, queue, count, wf.cutCounters + 2, false)) return rc;
+  if (cutout_graph_enabled())
+  {
+    if (int rc = ensure_cutout_graph(ctx, scene, a, grid)) return rc;
+    RTC_CUDA(cudaMemsetAsync(wf.cutCounters + 0, 0, sizeof(uint32_t), ctx->stream));
+    if (int rc = profile_begin(ctx, RTC_KERNEL_SHADE)) return rc;
+    k_cutout_shadow<<<grid, kBlock, 0, ctx->stream>>>(a, scene->desc, queue, count, wf.cutQueue[0], wf.cutCounters + 0, cutout_next(wf));
+    if (int rc = profile_end(ctx)) return rc;
+    if (int rc = profile_begin(ctx, RTC_KERNEL_CONNECT)) return rc;
+    RTC_CUDA(cudaGraphLaunch(static_cast<CutoutGraph*>(ctx->cutoutGraph)->shadow, ctx->stream));
+    ctx->kernelLaunches += 7;
+    return profile_end(ctx);
+  }
   for (int round = 0;; ++round)
   {
     const int o = round & 1;
     RTC_CUDA(cudaMemsetAsync(wf.cutCounters + o, 0, sizeof(uint32_t), ctx->stream));
     if (int rc = profile_begin(ctx, RTC_KERNEL_SHADE)) return rc;
-    k_cutout_shadow<<<grid, kBlock, 0, ctx->stream>>>(a, scene->desc, queue, count, wf.cutQueue[o], wf.cutCounters + o, queueNext, countNext);
+    k_cutout_shadow<<<grid, kBlock, 0, ctx->stream>>>(a, scene->desc, queue, count, wf.cutQueue[o], wf.cutCounters + o, cutout_next(wf));
     ctx->kernelLaunches++;
     if (int rc = profile_end(ctx)) return rc;
     uint32_t ignored = 0;
@@ -1043,6 +1190,13 @@ int resolve_shadow_candidates(rtc_context* ctx, const SceneRecord* scene, const 
 }
 
 } // namespace
+
+void release_cutout_graph(rtc_context* ctx)
+{
+  destroy_cutout_graph(static_cast<CutoutGraph*>(ctx->cutoutGraph));
+  delete static_cast<CutoutGraph*>(ctx->cutoutGraph);
+  ctx->cutoutGraph = nullptr;
+}
 
 int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uint32_t h, int raygen, int miss, int iterFirst, int iterCount,
                      int accumFirst, bool countWork)

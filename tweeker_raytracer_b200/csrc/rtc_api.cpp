@@ -170,6 +170,7 @@ int rtc_context_destroy(rtc_context* ctx)
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  release_cutout_graph(ctx);
   for (SceneRecord* s : ctx->scenes) free_scene(s);
   for (GasRecord& g : ctx->gas) { cudaFree(g.d_nodes); cudaFree(g.d_tris); }
   if (ctx->wf.base) cudaFree(ctx->wf.base);

@@ -153,6 +153,7 @@ struct rtc_context
   uint32_t* d_cursor = nullptr;                   // ray cursor of the query kernels (rtc_trace_*)
   bool   primaryPackets = false;                  // primary rays by packet traversal (trace_packet.cuh); RTC_PRIMARY_PACKETS=0 turns it off
   int    traceDriver = 0;                         // RTC_DRIVER_LANE or RTC_DRIVER_POOL: which traversal driver the launches use
+  void*  cutoutGraph = nullptr;                   // CutoutGraph (kernels_shade.cu): the device-side loop of the ordered any-hit rounds
   void*  d_poolScratch = nullptr;                 // global part of the ray pool's traversal stacks (trace_pool.cuh), grown on demand
   size_t poolScratchBytes = 0;
 };
@@ -199,5 +200,6 @@ int launch_composite(rtc_context* ctx, const rt_CompositorData& args);
 int launch_tonemap(rtc_context* ctx, const rt_TonemapperParams& p, const float4* rgba, uint8_t* rgb, uint64_t n);
 int ensure_wavefront(rtc_context* ctx, uint64_t capacity, bool* outOfMemory = nullptr);
 int ensure_pool_scratch(rtc_context* ctx, size_t warps, uint2** out);
+void release_cutout_graph(rtc_context* ctx);
 int read_stack_overflows(rtc_context* ctx, uint64_t* out);
 int read_stack_overflows_primary(rtc_context* ctx, uint64_t* out);   // the counter of the primary-ray extend kernel (kernels_shade.cu)
