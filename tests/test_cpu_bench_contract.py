@@ -48,3 +48,26 @@ def test_clock_sampler_without_a_gpu():
     summary = s.summary()
     assert set(summary) >= {"sm_mhz", "sm_max_mhz", "reasons", "samples", "source"}
     assert summary["source"] in ("nvml", "nvidia-smi")
+
+
+def test_parity_check_of_the_multi_gpu_arm_accepts_the_oracle_mean_and_rejects_a_wrong_frame(built, tmp_path):
+    """bench.py's untimed N > 1 parity step: the combined frame must be the mean over the ranks of the raw radiance of each
+    rank's first seed iteration (every rank accumulates from sample 0).  Exercised here with frames made by the oracle."""
+    import numpy as np
+    sys.path.insert(0, H.ROOT)
+    import bench
+    from tweeker_raytracer_b200 import host
+    app = host.App(H.write_system(tmp_path, "rtigo3_cornell_box", resolution="96 128", samplesSqrt=4), H.scene_path("rtigo3_cornell_box"), host_only=True)
+    world, local = 2, 8
+    w, h = app.resolution
+    ref, sysd = H.oracle_scene(app), H.oracle_sys(app)
+    xy = np.array([(x, y) for y in range(h) for x in range(w)], dtype=np.uint32)
+    frame = np.zeros((h, w, 4), dtype=np.float32)
+    frame[..., :3] = ((ref.path_radiance(sysd, app.info.miss, w, xy, 0) + ref.path_radiance(sysd, app.info.miss, w, xy, local)) * np.float32(0.5)).reshape(h, w, 3)
+    good = bench.parity_check(app, frame, world, local)
+    assert good["result"] == "pass" and good["rows"] == 2 and good["mismatches"] == 0
+    frame[64, 5, 1] += 0.01
+    assert bench.parity_check(app, frame, world, local)["result"] == "fail"
+    # the wrong partition (rank 1 starting at iteration 1 instead of `local`) is caught as well
+    assert bench.parity_check(app, frame, world, 1)["result"] == "fail"
+    app.close()

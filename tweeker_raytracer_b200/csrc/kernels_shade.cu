@@ -1117,7 +1117,7 @@ int ensure_cutout_graph(rtc_context* ctx, const SceneRecord* scene, const WfArgs
 
 bool cutout_graph_enabled()
 {
-  static const bool on = []() { const char* e = getenv("RTC_CUTOUT_GRAPH"); return e && atoi(e) != 0; }();
+  static const bool on = []() { const char* e = getenv("RTC_CUTOUT_GRAPH"); return !(e && atoi(e) == 0); }();      // RTC_CUTOUT_GRAPH=0: host-synchronised rounds
   return on;
 }
 

@@ -151,7 +151,7 @@ struct rtc_context
   cudaEvent_t  shadeFork = nullptr, shadeJoin[6] = {};
   unsigned long long* d_launchCounts = nullptr;   // 3 x kTraceCountWords: extend, connect, rtc_trace_count
   uint32_t* d_cursor = nullptr;                   // ray cursor of the query kernels (rtc_trace_*)
-  bool   primaryPackets = false;                  // primary rays by packet traversal (trace_packet.cuh); RTC_PRIMARY_PACKETS=0 turns it off
+  bool   primaryPackets = false;                  // primary rays by packet traversal (trace_packet.cuh): measured slower, RTC_PRIMARY_PACKETS=1 turns it on
   int    traceDriver = 0;                         // RTC_DRIVER_LANE or RTC_DRIVER_POOL: which traversal driver the launches use
   void*  cutoutGraph = nullptr;                   // CutoutGraph (kernels_shade.cu): the device-side loop of the ordered any-hit rounds
   void*  d_poolScratch = nullptr;                 // global part of the ray pool's traversal stacks (trace_pool.cuh), grown on demand

@@ -18,6 +18,9 @@
 #ifndef RTC_RESTORE_WORLD
 #define RTC_RESTORE_WORLD 1       // world-space box constants restored from shared memory when an instance is left
 #endif
+#ifndef RTC_TRI_MINMAX
+#define RTC_TRI_MINMAX 1          // mixed-sign test of the edge functions through FMNMX3 (see tri_test)
+#endif
 #ifndef RTC_LEAF_THRESHOLD
 #define RTC_LEAF_THRESHOLD 0      // > 0: hold lanes with a pending leaf group back until this many lanes of the warp have one (trace_stream)
 #endif
@@ -92,7 +95,13 @@ __device__ __forceinline__ bool tri_test(const ObjRay& r, float ox, float oy, fl
     V = (float)__dsub_rn(__dmul_rn((double)Ax, (double)Cy), __dmul_rn((double)Ay, (double)Cx));
     W = (float)__dsub_rn(__dmul_rn((double)Bx, (double)Ay), __dmul_rn((double)By, (double)Ax));
   }
+#if RTC_TRI_MINMAX
+  // "one edge function negative and one positive" as min < 0 < max: two 3-input min/max and two compares instead of six
+  // compares (identical for all non-NaN inputs; NaN edge functions need coordinates beyond 1e19)
+  if (fminf(fminf(U, V), W) < 0.0f && fmaxf(fmaxf(U, V), W) > 0.0f) return false;
+#else
   if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+#endif
   det = __fadd_rn(__fadd_rn(U, V), W);
   if (det == 0.0f) return false;
   const float Az = __fmul_rn(r.Sz, Akz), Bz = __fmul_rn(r.Sz, Bkz), Cz = __fmul_rn(r.Sz, Ckz);

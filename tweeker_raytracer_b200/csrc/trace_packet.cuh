@@ -15,11 +15,19 @@
 // (smallest t, ties -> smaller (instance, primitive)) does not depend on the order in which candidates are found, the box tests
 // are conservative per ray, and a ray only ever tests MORE triangles than it would alone (those of leaves its neighbours hit).
 // The price is the union: a packet visits every node any of its rays needs.  Incoherent rays must use trace_stream.
+//
+// MEASURED (round 2, profiles/sweeps_r2.md): bit-exact, but slower than the per-ray driver even on primary rays -- geometry
+// scene 2359 vs 2496 Msamples/s, Cornell box 742 vs 805, instanced stress scene 237 vs 360 -- because every visited node and
+// triangle costs a full-warp test whether one ray or all of them need it, and the 123 registers leave 16 warps per SM for a
+// loop that is one long dependent chain (uniform load -> test -> REDUX -> next).  Off by default (RTC_PRIMARY_PACKETS=1).
 #pragma once
 
 #include "trace.cuh"
 
 #define RTC_PACKET_STACK 64
+#ifndef RTC_PACKETS_PER_FETCH
+#define RTC_PACKETS_PER_FETCH 4      // packets a warp takes from the cursor with one atomicAdd
+#endif
 
 // every lane pushes the same (warp-uniform) entry; an overflow is counted like the per-ray stack's (rtc_stats::stackOverflows)
 __device__ __forceinline__ void packet_push(uint2* __restrict__ stack, uint32_t& sp, const uint2 v, const uint32_t lane)
@@ -34,11 +42,15 @@ __device__ __forceinline__ void trace_packets(const SceneDesc& sc, uint32_t n, u
                                               uint2* __restrict__ smStackWarp)
 {
   const uint32_t lane = threadIdx.x & 31u;
-  for (;;)
+  for (uint32_t fetched = RTC_PACKETS_PER_FETCH, chunk = 0;; ++fetched)
   {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(cursor, 32u);
-    base = __shfl_sync(0xffffffffu, base, 0);
+    if (fetched == RTC_PACKETS_PER_FETCH)
+    {
+      if (lane == 0) chunk = atomicAdd(cursor, 32u * RTC_PACKETS_PER_FETCH);
+      chunk = __shfl_sync(0xffffffffu, chunk, 0);
+      fetched = 0;
+    }
+    const uint32_t base = chunk + 32u * fetched;
     if (base >= n) break;
     const uint32_t index = base + lane;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(0.f, 0.f, 1.f, -1.f);
