@@ -12,6 +12,13 @@ for n in 2 4 8; do
   echo "== weak N=$n";   run $n --steps 8 --warmup 3 --no-ncu --no-probes > gpurun_out/bench_r2_${n}gpu_weak.json;   python tools/show_bench.py gpurun_out/bench_r2_${n}gpu_weak.json
   echo "== strong N=$n"; run $n --steps 8 --warmup 3 --scaling strong --no-ncu --no-probes > gpurun_out/bench_r2_${n}gpu_strong.json; python tools/show_bench.py gpurun_out/bench_r2_${n}gpu_strong.json
 done
+for n in 1 2 4 8; do
+  [ $n -le $N ] || continue
+  echo "== strong, the whole config per step (256 spp split over N=$n)"
+  if [ $n -eq 1 ]; then timeout 600 python bench.py --steps 2 --warmup 2 --spp-per-step 256 --scaling strong --no-ncu --no-probes --no-cpu-baseline 2>/dev/null | grep '^{' | tail -1 > gpurun_out/bench_r2_1gpu_strong256.json
+  else run $n --steps 2 --warmup 2 --spp-per-step 256 --scaling strong --no-ncu --no-probes > gpurun_out/bench_r2_${n}gpu_strong256.json; fi
+  python tools/show_bench.py gpurun_out/bench_r2_${n}gpu_strong256.json
+done
 echo "== c5 (4K) sample-range, N=$N"; run $N --config c5 --steps 8 --warmup 3 --spp-per-step 8 --no-ncu --no-probes > gpurun_out/bench_r2_${N}gpu_c5_weak.json; python tools/show_bench.py gpurun_out/bench_r2_${N}gpu_c5_weak.json
 echo "== c5 (4K) strong, 64 spp per step split over N=$N"; run $N --config c5 --steps 4 --warmup 2 --spp-per-step 64 --scaling strong --no-ncu --no-probes > gpurun_out/bench_r2_${N}gpu_c5_strong.json; python tools/show_bench.py gpurun_out/bench_r2_${N}gpu_c5_strong.json
 echo "== c5 tile partition (reference strategy 3 + NCCL composite), one process driving $N GPUs"
