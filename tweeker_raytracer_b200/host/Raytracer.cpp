@@ -82,7 +82,10 @@ const void* Raytracer::combineProcessGroup()
   rtc_context* ctx = device->getContext();
   SystemData const& sys = device->getSystemData();
   const size_t pixels = (size_t)sys.resolution.x * (size_t)sys.resolution.y;
-  if (device->getOutputBufferDevice() == 0) throw std::runtime_error("ERROR: getOutputBufferHost() before the first render()");
+  // A rank must never leave the collective to the others: a frame fetched before the first render() is the (zeroed) frame the
+  // first render would allocate, not an exception on this rank while the other ranks wait in ncclReduce.
+  if (device->getOutputBufferDevice() == 0) { void* buffer = nullptr; device->renderIterations(0, 0, &buffer); }
+  if (device->getOutputBufferDevice() == 0) throw std::runtime_error("ERROR: getOutputBufferHost() could not allocate the frame");
   if (m_rank == 0 && m_combinedPixels != pixels)
   {
     RTC_CHECK(rtc_synchronize(ctx));
