@@ -643,7 +643,7 @@ def main():
         app.render(1)
         fr = app.frame_view()
         if rank == 0:
-            parity = parity_check(app, fr, world, app.spp)
+            parity = parity_check(app, fr, world, app.spp // world)      # app.spp = samplesSqrt^2; a rank's share is spp / world
 
     line = None
     if rank == 0:

@@ -1,7 +1,8 @@
 // kernels_trace.cu -- the traversal kernels: ray queries (rtc_trace_*), and the wavefront integrator's
 // extend (closest hit of the radiance-ray queue) and connect (any hit of the shadow-ray queue).
-// All of them are persistent-warp kernels over trace_stream() (trace.cuh): one CTA of 128 threads per
-// resident slot, rays handed out through a device-side cursor.
+// All of them are persistent-warp kernels, one CTA of 128 threads per resident slot, rays handed out through a
+// device-side cursor, over one of two drivers chosen per launch (rtc_context::traceDriver): trace_stream() (trace.cuh,
+// one ray per lane, the default) or rtpool::trace_pool() (trace_pool.cuh, per-warp ray pool, RTC_TRACE_DRIVER=pool).
 // Built for sm_100a with FMA contraction ON: only the box tests may contract; the intersector in
 // trace.cuh pins its own rounding with intrinsics.
 #include "trace_pool.cuh"
@@ -10,7 +11,7 @@
 #define RTC_TRACE_MIN_BLOCKS 8      // one ray per lane: resident CTAs per SM the kernels are compiled for (register budget) and launched with
 #endif
 #ifndef RTC_POOL_BLOCKS
-#define RTC_POOL_BLOCKS 4           // ray pool: resident CTAs (4 warps each) per SM; bounded by shared memory (rtpool::kWarpBytes per warp)
+#define RTC_POOL_BLOCKS 4           // ray pool: resident CTAs (4 warps each) per SM; bounded by shared memory (rtpool::warp_bytes() per warp)
 #endif
 
 namespace {
