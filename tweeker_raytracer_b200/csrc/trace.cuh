@@ -25,7 +25,7 @@
 #define RTC_LEAF_THRESHOLD 0      // > 0: hold lanes with a pending leaf group back until this many lanes of the warp have one (trace_stream)
 #endif
 #ifndef RTC_FETCH_THRESHOLD
-#define RTC_FETCH_THRESHOLD 8     // refill a warp when at least this many lanes have finished their ray
+#define RTC_FETCH_THRESHOLD 12    // refill a warp when at least this many lanes have finished their ray (8: -1.3 %, 16: same; re-swept in round 2)
 #endif
 
 struct TraceHit
