@@ -218,6 +218,7 @@ struct CollapseParams
   const uint8_t* verts; uint32_t stride; const uint32_t* idx;
   Node8* nodes; float4* tris;
   uint32_t* nodeCount; uint32_t* triCount;
+  int leafMax;                // triangles per leaf child, 1..kLeafMax
 };
 
 __device__ __forceinline__ float half_area(const float4 lo, const float4 hi)
@@ -238,7 +239,7 @@ k_collapse_level(const CollapseParams P, const int2* __restrict__ work, uint32_t
   const uint32_t dst = (uint32_t)work[w].y;
   const int n = P.n;
   auto size_of = [&](int node) { return (node >= n - 1 && node < 2 * n - 1) ? 1 : (P.range[node].y - P.range[node].x + 1); };
-  auto is_leaf = [&](int node) { return size_of(node) <= (int)kLeafMax; };
+  auto is_leaf = [&](int node) { return size_of(node) <= P.leafMax; };
 
   int kids[8]; int nk = 0;
   if (is_leaf(src)) kids[nk++] = src;
@@ -505,6 +506,12 @@ static int build_gas_gpu_impl(rtc_context* ctx, GasRecord& rec)
   P.n = (int)n; P.child = A.child; P.range = A.range; P.boxLo = A.boxLo; P.boxHi = A.boxHi; P.order = A.order;
   P.verts = (const uint8_t*)(uintptr_t)rec.attributes; P.stride = rec.strideBytes; P.idx = (const uint32_t*)(uintptr_t)rec.indices;
   P.nodes = (Node8*)rec.d_nodes; P.tris = (float4*)rec.d_tris; P.nodeCount = d_counters + 2; P.triCount = d_counters + 3;
+  // One triangle per leaf child.  A triangle test costs a warp ~2.7x what a node visit costs (it runs for the 3-4 lanes that
+  // have just found a leaf, the node visit for 26-29), and the leaves of an LBVH over unstructured triangles are loose: single-
+  // triangle leaves trade 18 triangle tests per ray for a few more node visits -- 1 M / 10 M-triangle soups, incoherent closest
+  // hit: 1069 -> 1358 and 818 -> 1090 Mrays/s (leaves of <= 2: 1196 / 920).  RTC_GPU_LEAF_MAX=2|3 restores larger leaves.
+  P.leafMax = 1;
+  if (const char* e = std::getenv("RTC_GPU_LEAF_MAX")) { const int v = atoi(e); if (1 <= v && v <= (int)kLeafMax) P.leafMax = v; }
   const uint32_t one = 1u, zero = 0u;
   const int2 rootWork = make_int2(rootNode, 0);
   RTC_CUDA(cudaMemcpyAsync(d_counters + 2, &one, sizeof(uint32_t), cudaMemcpyHostToDevice, st));     // wide node 0 = root

@@ -67,7 +67,7 @@ struct WideBvh
 struct PrimBox { float lo[3], hi[3]; };
 
 // bvh_build_host.cpp: binned-SAH binary build, greedy collapse to 8-wide, octant slot assignment, quantisation.
-// leafMax: primitives per leaf child (1..3).  Triangles: 3.  Instances: 1 -- entering an instance costs about three node
+// leafMax: primitives per leaf child (1..3).  Triangles: 2 (rtc_gas_build).  Instances: 1 -- entering an instance costs about three node
 // visits (transform, shear constants, the GAS root), so a leaf box shared by two or three instances is never worth it
 // (geometry scene: 1.30 -> 1.06 instance entries per ray, +7.5 % samples/s).
 void build_wide_bvh_host(const PrimBox* prims, uint32_t numPrims, WideBvh& out, uint32_t leafMax = 3);
