@@ -1,4 +1,4 @@
-# usage (under gpurun --gpus N): bash tools/gpu_run_multi.sh N   -- multi-GPU tests, weak + strong scaling, 4K tile partition
+# usage (under gpurun --gpus N): bash tools/sessions_r2/gpu_run_multi.sh N   -- multi-GPU tests, weak + strong scaling, 4K tile partition
 cd $GRAFT_REPO_ROOT
 N=${1:-2}
 nvidia-smi -L | head -8

@@ -1,4 +1,4 @@
-# usage (under gpurun --gpus N): bash tools/gpu_run_multi_b.sh N -- strong scaling with the WHOLE config as one step (256 spp split
+# usage (under gpurun --gpus N): bash tools/sessions_r2/gpu_run_multi_b.sh N -- strong scaling with the WHOLE config as one step (256 spp split
 # over the ranks), and one weak line per N with the parity step
 cd $GRAFT_REPO_ROOT
 N=${1:-2}

@@ -1,4 +1,4 @@
-# usage (under gpurun --gpus 8): bash tools/gpu_run_multi_c.sh -- the 4- and 8-GPU lines of round 2 (every line with its parity step)
+# usage (under gpurun --gpus 8): bash tools/sessions_r2/gpu_run_multi_c.sh -- the 4- and 8-GPU lines of round 2 (every line with its parity step)
 cd $GRAFT_REPO_ROOT
 run() {
   local n=$1; shift
