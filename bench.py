@@ -910,7 +910,7 @@ def rays_cpu(args, ntris, kind, mode, rays, sample=400000, threads=0):
     else:
         s.trace_any(sub)
     dt = time.perf_counter() - t0
-    return {"value": sub.shape[0] / dt / 1e6, "unit": "Mrays/s", "cores": 1, "kind": "port",
+    return {"value": sub.shape[0] / dt / 1e6, "unit": "Mrays/s", "cores": 1, "kind": "port", "seconds": dt,
             "sample": "%d rays (every %d-th of the set) in %.2f s, oracle binary BVH, one thread" % (sub.shape[0], max(1, rays.shape[0] // sample), dt)}
 
 
@@ -921,14 +921,15 @@ def run_rays_reference(args):
         return
     nrays = int(float(args.rays))
     rays = rays_numpy(min(nrays, 1 << 22), kind, mode)
-    vals = []
+    vals, secs = [], 0.0
     base = None
     for _ in range(args.steps):
         base = rays_cpu(args, ntris, kind, mode, rays, sample=200000)
         vals.append(base["value"])
+        secs += base["seconds"]
     v = sum(vals) / len(vals)
     line = {"impl": "reference", "metric": "ray_microbenchmark_%s_mrays_per_s" % args.config.replace("-", "_"), "value": v, "unit": "Mrays/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 0.0, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": c3_config(args, ntris, kind, mode, nrays), "cpu_baseline": dict(base, value=v),
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
