@@ -461,11 +461,15 @@ static int build_gas_gpu_impl(rtc_context* ctx, GasRecord& rec)
   int rootNode = (n == 1) ? 0 : 0;            // binary root (for n == 1 the single leaf has id n-1 = 0)
   if (n > 8 * kLeafMax * 64)
   {
-    int limit = (int)(n / 2048u); if (limit < (int)kLeafMax) limit = (int)kLeafMax;
+    // subtrees of at most n / kCutDivisor triangles form the cut whose top is rebuilt with binned SAH on the host
+    uint32_t cutDivisor = 2048u;
+    if (const char* e = std::getenv("RTC_GPU_CUT_DIVISOR")) { const long v = atol(e); if (64 <= v && v <= 32768) cutDivisor = (uint32_t)v; }
+    int limit = (int)(n / cutDivisor); if (limit < (int)kLeafMax) limit = (int)kLeafMax;
     k_mark_cut<<<(unsigned)((numBinary + kB - 1) / kB), kB, 0, st>>>((int)n, limit, A.parent, A.range, d_cut, d_counters + 1, cutCapacity);
     RTC_CUDA(cudaMemcpyAsync(hostCounters, d_counters, sizeof(hostCounters), cudaMemcpyDeviceToHost, st));
     RTC_CUDA(cudaStreamSynchronize(st));
     const uint32_t cutCount = hostCounters[1];
+    if (verbose) std::fprintf(stderr, "build_gas_gpu[%u tris] cut of %u subtrees (<= %d triangles each, capacity %u)\n", n, cutCount, limit, cutCapacity);
     if (cutCount >= 2 && cutCount <= cutCapacity)
     {
       k_gather_boxes<<<(cutCount + kB - 1) / kB, kB, 0, st>>>(d_cut, cutCount, A.boxLo, A.boxHi, d_cutBoxes);
