@@ -1,6 +1,9 @@
 """GPU parity at BASELINE.json's full sizes, through properties that do not need the oracle to render a whole frame:
 rows of the full-resolution frame (the oracle renders a row subset in seconds), builder independence and idempotence on
 a million-triangle soup, closest-hit / any-hit consistency, and conservation of the ray statistics."""
+import os
+import sys
+
 import numpy as np
 import pytest
 
@@ -42,6 +45,39 @@ def test_cornell_config1_full_spec_rows_bit_exact(cuda_device):
         ref = H.oracle_scene(app)
         want = ref.render(H.oracle_sys(app), app.info.miss, 512, 512, iter_count=16, row_step=16).reshape(512, 512, 4)
         assert got[::16].tobytes() == want[::16].tobytes()
+    finally:
+        app.close()
+
+
+def test_instanced_stress_scene_config4_full_count_bit_exact(cuda_device, tmp_path):
+    # config 4 as specified: 10 000 instances of the 50 000-triangle torus over a floor (500 M instanced triangles, two GAS),
+    # at its real resolution; 4 of its 64 iterations; random rays through the lattice and 10 rows of the frame against the oracle
+    sys.path.insert(0, os.path.join(H.ROOT, "tools"))
+    import make_instances_scene
+    scene = os.path.join(str(tmp_path), "scene_rtigo3_instances.txt")
+    placed, dims = make_instances_scene.write_scene(scene)
+    assert placed == 10000
+    app = host.App(H.SCENES + "/system_rtigo3_instances.txt", scene)
+    try:
+        assert app.resolution == (1920, 1080)
+        assert app.info.numInstances == placed + 1 and app.info.numGeometries == 2
+        ctx = app.context(0)
+        top = app.system_data(0).topObject
+        info = ctx.scene_info(top)
+        assert info.numGas == 2 and info.numInstances == placed + 1
+        assert sum(len(app.geometry(g)[1]) for g in range(2)) >= 50_000          # x 10 000 instances = 500 M instanced triangles
+        ref = H.oracle_scene(app)
+        half = 0.5 * dims[0] * 2.4
+        rays = H.random_rays(200000, seed=4, lo=(-half, 0.05, -half), hi=(half, dims[1] * 2.4 + 2.0, half))
+        hits = ctx.trace_closest_host(top, rays)
+        assert H.hits_equal(hits, ref.trace_closest(rays))
+        assert (hits["inst"] != 0xffffffff).mean() > 0.5
+        assert app.render(4) == 4
+        got = app.frame()
+        want = ref.render(H.oracle_sys(app), app.info.miss, 1920, 1080, iter_count=4, row_step=108, row_offset=31).reshape(1080, 1920, 4)
+        rows = np.arange(31, 1080, 108)
+        assert got[rows].tobytes() == want[rows].tobytes()
+        assert app.stats().stackOverflows == 0
     finally:
         app.close()
 
