@@ -232,6 +232,16 @@ int rtc_tonemap(rtc_context* ctx, const rt_TonemapperParams* params, uint64_t rg
 int rtc_probe_gather(rtc_context* ctx, uint64_t bytes, uint32_t loadsPerThread, double* gigabytesPerSecond);
 int rtc_probe_pipes(rtc_context* ctx, int mode, double* rate);
 
+/*
+ * Test hook: out[i] = fn(x[i], y[i]) evaluated on the device by the shading translation unit, i.e. with the arithmetic the
+ * closest-hit / BSDF / light / miss replacements are compiled with (pinned transcendentals of include/rt_portable_math.h,
+ * IEEE division and square root, no FMA contraction).  The bits must equal the same header compiled for the host -- the
+ * definition the "bit-identical to the CPU oracle" parity claim rests on.  x, y, out: HOST arrays of n floats.  Synchronous.
+ */
+enum rtc_math_fn { RTC_MATH_SIN = 0, RTC_MATH_COS, RTC_MATH_ATAN, RTC_MATH_ATAN2, RTC_MATH_ACOS, RTC_MATH_EXP, RTC_MATH_LOG,
+                   RTC_MATH_POW, RTC_MATH_DIV, RTC_MATH_SQRT, RTC_MATH_MULADD, RTC_MATH_COUNT };
+int rtc_probe_math(rtc_context* ctx, int fn, const float* x, const float* y, float* out, uint32_t n);
+
 int rtc_stats_get(rtc_context* ctx, rtc_stats* out);   /* synchronises the context stream */
 int rtc_stats_reset(rtc_context* ctx);
 

@@ -123,3 +123,35 @@ def write_rgbe_hdr(path, rgbe):
         f.write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n" % (h, w))
         f.write(np.ascontiguousarray(rgbe, dtype=np.uint8).tobytes())
     return path
+
+
+PORTABLE_MATH_SRC = r"""
+#include "rt_portable_math.h"
+#include <math.h>
+#define W(name, expr) void name(const float* x, const float* y, float* o, int n) { for (int i = 0; i < n; ++i) o[i] = expr; }
+W(p_sin, rt_sinf(x[i])) W(p_cos, rt_cosf(x[i])) W(p_atan, rt_atanf(x[i])) W(p_atan2, rt_atan2f(x[i], y[i]))
+W(p_acos, rt_acosf(x[i])) W(p_exp, rt_expf(x[i])) W(p_log, rt_logf(x[i])) W(p_pow, rt_powf(x[i], y[i]))
+W(p_div, x[i] / y[i]) W(p_sqrt, sqrtf(x[i])) W(p_muladd, x[i] * y[i] + x[i])
+"""
+
+
+def portable_math_lib(tmpdir):
+    """include/rt_portable_math.h compiled for the host with the oracle's flags: the CPU side of the arithmetic both the oracle
+    and the shading kernels are defined by (tests/test_cpu_portable_math.py, tests/test_gpu_edge_cases.py)."""
+    import ctypes
+    import subprocess
+    src = os.path.join(str(tmpdir), "pm.c")
+    with open(src, "w") as f:
+        f.write(PORTABLE_MATH_SRC)
+    so = os.path.join(str(tmpdir), "pm.so")
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-o", so, src, "-lm"])
+    return ctypes.CDLL(so)
+
+
+def portable_math_call(lib, name, x, y=None):
+    import ctypes
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.ascontiguousarray(y if y is not None else np.zeros_like(x), dtype=np.float32)
+    o = np.zeros_like(x)
+    getattr(lib, "p_" + name)(x.ctypes.data_as(ctypes.c_void_p), y.ctypes.data_as(ctypes.c_void_p), o.ctypes.data_as(ctypes.c_void_p), len(x))
+    return o

@@ -1,38 +1,17 @@
 """include/rt_portable_math.h: the pinned transcendentals stay within a few ulp of libm on the ranges the path tracer
 uses.  Exercised through the two oracle builds (pinned vs libm) with a tiny C harness compiled on the fly."""
-import ctypes as C
-import os
-import subprocess
-
 import numpy as np
 import pytest
 
 import helpers as H
 
-SRC = r"""
-#include "rt_portable_math.h"
-#define W(name, expr) void name(const float* x, const float* y, float* o, int n) { for (int i = 0; i < n; ++i) o[i] = expr; }
-W(p_sin, rt_sinf(x[i])) W(p_cos, rt_cosf(x[i])) W(p_atan, rt_atanf(x[i])) W(p_atan2, rt_atan2f(x[i], y[i]))
-W(p_acos, rt_acosf(x[i])) W(p_exp, rt_expf(x[i])) W(p_log, rt_logf(x[i])) W(p_pow, rt_powf(x[i], y[i]))
-"""
-
-
 @pytest.fixture(scope="module")
 def pm(tmp_path_factory):
-    d = tmp_path_factory.mktemp("pm")
-    src = d / "pm.c"
-    src.write_text(SRC)
-    so = d / "pm.so"
-    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I" + os.path.join(H.ROOT, "include"), "-o", str(so), str(src), "-lm"])
-    return C.CDLL(str(so))
+    return H.portable_math_lib(tmp_path_factory.mktemp("pm"))
 
 
 def run(lib, name, x, y=None):
-    x = np.ascontiguousarray(x, dtype=np.float32)
-    y = np.ascontiguousarray(y if y is not None else np.zeros_like(x), dtype=np.float32)
-    o = np.zeros_like(x)
-    getattr(lib, name)(x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p), len(x))
-    return o
+    return H.portable_math_call(lib, name[2:], x, y)
 
 
 def ulps(a, b):
@@ -72,3 +51,15 @@ def test_exp_log_pow(pm):
         want = np.power(b.astype(np.float32).astype(np.float64), np.float32(e).astype(np.float64))
         assert np.max(np.abs(got - want) / np.maximum(want, 1e-3)) < 2e-6
     assert run(pm, "p_pow", [0.0, -1.0], [2.0, 2.0]).tolist() == [0.0, 0.0]
+
+
+def test_ieee_division_sqrt_and_uncontracted_multiply_add(pm):
+    # the three operations the shading kernels need compiler flags for (-prec-div, -prec-sqrt, -fmad=false) against float64
+    rng = np.random.default_rng(5)
+    a = rng.normal(size=200000).astype(np.float32) * np.float32(10.0) ** rng.integers(-10, 10, size=200000).astype(np.float32)
+    b = rng.normal(size=200000).astype(np.float32) * np.float32(10.0) ** rng.integers(-10, 10, size=200000).astype(np.float32)
+    b[b == 0] = 1.0
+    assert np.array_equal(run(pm, "p_div", a, b), (a.astype(np.float64) / b.astype(np.float64)).astype(np.float32))
+    assert np.array_equal(run(pm, "p_sqrt", np.abs(a)), np.sqrt(np.abs(a).astype(np.float64)).astype(np.float32))
+    two_roundings = ((a.astype(np.float64) * b.astype(np.float64)).astype(np.float32).astype(np.float64) + a.astype(np.float64)).astype(np.float32)
+    assert np.array_equal(run(pm, "p_muladd", a, b), two_roundings)

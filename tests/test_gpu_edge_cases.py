@@ -68,3 +68,44 @@ def test_roofline_probes_and_pass_statistics(cuda_device):
         assert all(v[0] == 0 for v in ext.values()) and all(v[0] == 0 for v in con.values())
     finally:
         ctx.close()
+
+
+def test_shading_arithmetic_bit_identical_to_the_host_build(cuda_device, tmp_path):
+    """include/rt_portable_math.h is shared by the oracle and the shading kernels: a frame comparison alone would not notice
+    the two compilers disagreeing on an input no test scene produces.  Here the device evaluates every pinned transcendental,
+    IEEE division / square root and an uncontracted multiply-add (rtc_probe_math: the shading translation unit's flags) over
+    dense and random inputs, and every result must carry the bits gcc's build of the same header produces.  (The header is
+    checked against float64 libm independently, tests/test_cpu_portable_math.py.)"""
+    from tweeker_raytracer_b200 import core
+    pm = H.portable_math_lib(tmp_path)
+    rng = np.random.default_rng(2024)
+    n = 1 << 20
+    wide = (rng.normal(size=n) * 10.0 ** rng.integers(-12, 12, size=n)).astype(np.float32)
+    wide2 = (rng.normal(size=n) * 10.0 ** rng.integers(-12, 12, size=n)).astype(np.float32)
+    unit = rng.uniform(-1.0, 1.0, size=n).astype(np.float32)
+    cases = {
+        "sin": [(np.linspace(-4 * np.pi, 4 * np.pi, n), None), (rng.uniform(-1e5, 1e5, size=n), None), (wide[np.abs(wide) < 1e8], None)],
+        "cos": [(np.linspace(-4 * np.pi, 4 * np.pi, n), None), (rng.uniform(-1e5, 1e5, size=n), None), (wide[np.abs(wide) < 1e8], None)],
+        "atan": [(np.linspace(-50, 50, n), None), (wide, None), (np.array([0.0, -0.0, 1.0, -1.0, 2.414213562373095, 0.4142135623730950]), None)],
+        "atan2": [(wide, wide2), (unit, rng.uniform(-1.0, 1.0, size=n)), (np.array([0.0, 1.0, -1.0, 0.0, 0.0]), np.array([0.0, 0.0, 0.0, -1.0, 1.0]))],
+        "acos": [(np.linspace(-1, 1, n), None), (unit, None), (np.array([1.0000001, -1.0000001, 1.0, -1.0, 0.5, -0.5, 0.0, 1e-5]), None)],
+        "exp": [(np.linspace(-85, 88.7, n), None), (rng.normal(size=n), None), (np.array([0.0, -0.0, 100.0, -200.0, 88.72283, -103.0]), None)],
+        "log": [(np.abs(wide) + 1e-30, None), (np.linspace(0.5, 2.0, n), None), (np.array([1.0, 0.0, -1.0, np.inf, 1e-40, 3.4e38]), None)],
+        "pow": [(rng.uniform(0, 4, size=n), np.full(n, 1.0 / 2.2)), (rng.uniform(0, 4, size=n), rng.uniform(0.1, 3.0, size=n)), (np.array([0.0, -1.0, 1.0]), np.array([2.0, 2.0, 2.2]))],
+        "div": [(wide, np.where(wide2 == 0, 1.0, wide2)), (unit, rng.uniform(0.5, 2.0, size=n))],
+        "sqrt": [(np.abs(wide), None), (np.linspace(0, 4, n), None)],
+        "muladd": [(wide, wide2), (unit, rng.uniform(-1.0, 1.0, size=n))],
+    }
+    assert sorted(cases) == sorted(core.MATH_FUNCTIONS)
+    ctx = core.Context(0)
+    try:
+        for name, inputs in cases.items():
+            for x, y in inputs:
+                x = np.ascontiguousarray(x, dtype=np.float32)
+                y = None if y is None else np.ascontiguousarray(y, dtype=np.float32)
+                got = ctx.probe_math(name, x, y)
+                want = H.portable_math_call(pm, name, x, y)
+                same = got.view(np.uint32) == want.view(np.uint32)
+                assert same.all(), (name, x[~same][:4], got[~same][:4], want[~same][:4])
+    finally:
+        ctx.close()

@@ -30,7 +30,10 @@ SYMBOLS = [
     "rtc_profile_enable", "rtc_profile_get", "rtc_trace_closest", "rtc_trace_any", "rtc_trace_count", "rtc_generate_primary",
     "rtc_composite", "rtc_tonemap", "rtc_stats_get", "rtc_stats_reset",
     "rtc_launch_pass_stats_get", "rtc_probe_gather", "rtc_probe_pipes", "rtc_scene_export", "rtc_gas_info", "rtc_gas_export",
+    "rtc_probe_math",
 ]
+
+MATH_FUNCTIONS = ["sin", "cos", "atan", "atan2", "acos", "exp", "log", "pow", "div", "sqrt", "muladd"]     # enum rtc_math_fn
 
 
 class Stats(C.Structure):
@@ -117,6 +120,7 @@ def lib():
         L.rtc_launch_pass_stats_get.argtypes = [C.c_void_p, C.POINTER(PassStats)]
         L.rtc_probe_gather.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_double)]
         L.rtc_probe_pipes.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        L.rtc_probe_math.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         _lib = L
     return _lib
 
@@ -301,6 +305,15 @@ class Context:
         v = C.c_double(0.0)
         _check(self.L.rtc_probe_pipes(self.h, mode, C.byref(v)))
         return v.value
+
+    def probe_math(self, name, x, y=None):
+        """name(x, y) element-wise on the device with the shading kernels' arithmetic (include/rt_portable_math.h, IEEE / and sqrt)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        y = np.ascontiguousarray(y if y is not None else np.zeros_like(x), dtype=np.float32)
+        out = np.zeros_like(x)
+        _check(self.L.rtc_probe_math(self.h, MATH_FUNCTIONS.index(name), x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p),
+                                     out.ctypes.data_as(C.c_void_p), x.size))
+        return out
 
     def launch_counts_reset(self):
         _check(self.L.rtc_launch_counts_reset(self.h))

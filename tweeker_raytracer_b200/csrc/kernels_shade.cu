@@ -1345,3 +1345,44 @@ int launch_tonemap(rtc_context* ctx, const rt_TonemapperParams& p, const float4*
   RTC_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Test hook (rtc_probe_math): the arithmetic the shading kernels are DEFINED by -- the pinned transcendentals of
+// include/rt_portable_math.h plus IEEE division and square root -- evaluated element-wise with exactly this translation
+// unit's compiler flags (-fmad=false -prec-div=true -prec-sqrt=true).  tests/test_gpu_edge_cases.py compares the bits with
+// the same header compiled by gcc, input by input, instead of only through rendered frames.
+namespace {
+__global__ void __launch_bounds__(kBlock)
+k_probe_math(int fn, const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out, uint32_t n)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float a = x[i], b = y[i];
+  float r;
+  switch (fn)
+  {
+    case RTC_MATH_SIN:   r = rt_sinf(a); break;
+    case RTC_MATH_COS:   r = rt_cosf(a); break;
+    case RTC_MATH_ATAN:  r = rt_atanf(a); break;
+    case RTC_MATH_ATAN2: r = rt_atan2f(a, b); break;
+    case RTC_MATH_ACOS:  r = rt_acosf(a); break;
+    case RTC_MATH_EXP:   r = rt_expf(a); break;
+    case RTC_MATH_LOG:   r = rt_logf(a); break;
+    case RTC_MATH_POW:   r = rt_powf(a, b); break;
+    case RTC_MATH_DIV:   r = a / b; break;
+    case RTC_MATH_SQRT:  r = sqrtf(a); break;
+    case RTC_MATH_MULADD: r = a * b + a; break;        // must stay two roundings (no contraction)
+    default:             r = 0.0f; break;
+  }
+  out[i] = r;
+}
+} // namespace
+
+int launch_probe_math(rtc_context* ctx, int fn, const float* x, const float* y, float* out, uint32_t n)
+{
+  if (n == 0) return 0;
+  k_probe_math<<<(n + kBlock - 1) / kBlock, kBlock, 0, ctx->stream>>>(fn, x, y, out, n);
+  ctx->kernelLaunches++;
+  RTC_CUDA(cudaGetLastError());
+  return 0;
+}

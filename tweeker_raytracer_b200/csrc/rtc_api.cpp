@@ -815,6 +815,24 @@ int rtc_tonemap(rtc_context* ctx, const rt_TonemapperParams* params, uint64_t rg
   return launch_tonemap(ctx, *params, (const float4*)(uintptr_t)rgba, (uint8_t*)(uintptr_t)rgb8, numPixels);
 }
 
+int rtc_probe_math(rtc_context* ctx, int fn, const float* x, const float* y, float* out, uint32_t n)
+{
+  if (!ctx || !x || !y || !out) RTC_FAIL("null argument");
+  if (fn < 0 || fn >= RTC_MATH_COUNT) RTC_FAIL("unknown function");
+  if (n == 0) return 0;
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  float* d = nullptr;
+  RTC_CUDA(cudaMalloc(&d, (size_t)n * 3 * sizeof(float)));
+  const bool ok = cudaMemcpyAsync(d, x, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
+                  cudaMemcpyAsync(d + n, y, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
+                  launch_probe_math(ctx, fn, d, d + n, d + 2 * (size_t)n, n) == 0 &&
+                  cudaMemcpyAsync(out, d + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+                  cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+  cudaFree(d);
+  if (!ok) RTC_FAIL("device error");
+  return 0;
+}
+
 int rtc_stats_get(rtc_context* ctx, rtc_stats* out)
 {
   if (!out) RTC_FAIL("out is null");

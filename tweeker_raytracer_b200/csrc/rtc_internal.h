@@ -198,6 +198,7 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
                      int accumFirst, bool countWork);
 int launch_composite(rtc_context* ctx, const rt_CompositorData& args);
 int launch_tonemap(rtc_context* ctx, const rt_TonemapperParams& p, const float4* rgba, uint8_t* rgb, uint64_t n);
+int launch_probe_math(rtc_context* ctx, int fn, const float* x, const float* y, float* out, uint32_t n);   // device pointers
 int ensure_wavefront(rtc_context* ctx, uint64_t capacity, bool* outOfMemory = nullptr);
 int ensure_pool_scratch(rtc_context* ctx, size_t warps, uint2** out);
 void release_cutout_graph(rtc_context* ctx);
