@@ -12,7 +12,7 @@ CXXFLAGS  := -O2 -std=c++17 -fPIC -ffp-contract=off $(INC) -I/usr/local/cuda/inc
 
 # e.g. make TRACE_DEFS='-DRTC_TRACE_MIN_BLOCKS=5 -DRTC_FETCH_THRESHOLD=16' to explore the traversal kernel's tuning knobs
 TRACE_DEFS ?=
-CORE_OBJS := $(LIB)/kernels_trace.o $(LIB)/kernels_shade.o $(LIB)/probes.o $(LIB)/bvh_build_gpu.o $(LIB)/rtc_api.o $(LIB)/bvh_build_host.o
+CORE_OBJS := $(LIB)/kernels_trace.o $(LIB)/kernels_shade.o $(LIB)/probes.o $(LIB)/bvh_build_gpu.o $(LIB)/rtc_api.o $(LIB)/bvh_build_host.o $(LIB)/accel_host.o
 
 all: core host oracle
 
@@ -21,7 +21,7 @@ core: $(LIB)/librtcore.so
 $(LIB)/kernels_trace.o: $(CSRC)/kernels_trace.cu $(CSRC)/trace.cuh $(CSRC)/trace_pool.cuh $(CSRC)/rtc_internal.h include/rtc_core.h include/rtigo3_abi.h
 	$(NVCC) $(NVFLAGS) $(TRACE_DEFS) -c $< -o $@
 # shading: FMA contraction off, IEEE division/sqrt -- bit-exact against the scalar oracle
-$(LIB)/kernels_shade.o: $(CSRC)/kernels_shade.cu $(CSRC)/shade.cuh $(CSRC)/trace.cuh $(CSRC)/trace_pool.cuh $(CSRC)/rtc_internal.h include/rtc_core.h include/rtigo3_abi.h include/rt_portable_math.h
+$(LIB)/kernels_shade.o: $(CSRC)/kernels_shade.cu $(CSRC)/shade.cuh $(CSRC)/trace.cuh $(CSRC)/trace_pool.cuh $(CSRC)/trace_packet.cuh $(CSRC)/rtc_internal.h include/rtc_core.h include/rtigo3_abi.h include/rt_portable_math.h
 	$(NVCC) $(NVFLAGS) $(TRACE_DEFS) -fmad=false -prec-div=true -prec-sqrt=true -c $< -o $@
 $(LIB)/probes.o: $(CSRC)/probes.cu $(CSRC)/rtc_internal.h include/rtc_core.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@
@@ -30,6 +30,8 @@ $(LIB)/bvh_build_gpu.o: $(CSRC)/bvh_build_gpu.cu $(CSRC)/rtc_internal.h
 $(LIB)/rtc_api.o: $(CSRC)/rtc_api.cpp $(CSRC)/rtc_internal.h include/rtc_core.h
 	g++ $(CXXFLAGS) -c $< -o $@
 $(LIB)/bvh_build_host.o: $(CSRC)/bvh_build_host.cpp $(CSRC)/rtc_internal.h
+	g++ $(CXXFLAGS) -c $< -o $@
+$(LIB)/accel_host.o: $(CSRC)/accel_host.cpp $(CSRC)/rtc_internal.h include/rtc_core.h
 	g++ $(CXXFLAGS) -c $< -o $@
 $(LIB)/librtcore.so: $(CORE_OBJS)
 	$(NVCC) -shared $(ARCH) -o $@ $(CORE_OBJS) -cudart shared

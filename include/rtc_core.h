@@ -174,6 +174,24 @@ int rtc_gas_export(rtc_context* ctx, uint32_t gas, void* nodes, float* tris);
 int rtc_instance_inverse(rtc_context* ctx, uint64_t topObject, uint32_t instance, float out[12]);
 
 /*
+ * Host-only twin of rtc_gas_build(RTC_BUILD_HOST_SAH) + rtc_ias_build: the same builder code (csrc/accel_host.cpp,
+ * csrc/bvh_build_host.cpp) fed from HOST arrays, returning the arrays the two functions would upload -- no CUDA call, no
+ * context.  For tools (tools/bvh_quality.py) and for the CPU tests of the builder: the test oracle traverses the result in the
+ * kernels' order of operations, so node / triangle / instance counts per ray of a B200 run are known before it happens.
+ *   geometry level: nodes = numNodes x 80 B, primOrder = numPrims triangle indices in leaf order, tris = numPrims x 12 floats
+ *   instance level: nodes, primOrder = the instance-level leaf slots (instance ids), worldToObject = numInstances x 12 floats
+ * transforms: 12 floats per instance (object -> world, rtc_instance_desc::transform); geometry[i]: the accel of instance i's mesh.
+ * Any pointer of rtc_host_accel_export may be null.
+ */
+typedef struct rtc_host_accel rtc_host_accel;
+int  rtc_host_gas_build(const void* attributes, uint32_t strideBytes, uint32_t numVerts, const uint32_t* indices, uint32_t numTris,
+                        rtc_host_accel** out);
+int  rtc_host_ias_build(const float* transforms, const rtc_host_accel* const* geometry, uint32_t numInstances, rtc_host_accel** out);
+int  rtc_host_accel_info(const rtc_host_accel* accel, uint64_t* numNodes, uint64_t* numPrims, float bounds[6]);
+int  rtc_host_accel_export(const rtc_host_accel* accel, void* nodes, uint32_t* primOrder, float* tris, float* worldToObject);
+void rtc_host_accel_destroy(rtc_host_accel* accel);
+
+/*
  * One optixLaunch-equivalent per iteration in [iterationFirst, iterationFirst + iterationCount):
  * sys is the HOST copy of SystemData (pointers inside are device pointers owned by the caller);
  * sys->iterationIndex is ignored in favour of the range.  raygen = RTC_RAYGEN_*, miss = RT_MISS_*.

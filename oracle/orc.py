@@ -309,9 +309,10 @@ class WideScene(C.Structure):
                 ("gasNodes", C.c_void_p), ("gasTris", C.c_void_p), ("numInstances", C.c_uint32)]
 
 
-def wide_trace(export, rays, any_hit=False, variant="pinned"):
+def wide_trace(export, rays, any_hit=False, variant="pinned", levels=False):
     """Scalar traversal of the PRODUCT's exported wide BVH (core.Context.scene_export) in the product's own order of operations
-    (oracle/wide_bvh.inc): returns (hits, (nodes, tris, instances)) -- the work counters the GPU's counting kernels must equal."""
+    (oracle/wide_bvh.inc): returns (hits, (nodes, tris, instances)) -- the work counters the GPU's counting kernels must equal.
+    levels=True appends a fourth counter: the nodes that belong to the instance level."""
     L = lib(variant)
     handles = sorted(export["gas"])
     slot = {g: k for k, g in enumerate(handles)}
@@ -324,11 +325,12 @@ def wide_trace(export, rays, any_hit=False, variant="pinned"):
                    len(export["instance_gas"]))
     rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
     hits = np.zeros(len(rays), dtype=HIT_DTYPE)
-    counts = (C.c_uint64 * 3)()
-    L.orc_wide_trace.argtypes = [C.POINTER(WideScene), C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.POINTER(C.c_uint64)]
-    L.orc_wide_trace.restype = None
-    L.orc_wide_trace(C.byref(ws), _ptr(rays), len(rays), 1 if any_hit else 0, _ptr(hits), counts)
-    return hits, (int(counts[0]), int(counts[1]), int(counts[2]))
+    counts = (C.c_uint64 * 4)()
+    fn = L.orc_wide_trace_levels if levels else L.orc_wide_trace
+    fn.argtypes = [C.POINTER(WideScene), C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.POINTER(C.c_uint64)]
+    fn.restype = None
+    fn(C.byref(ws), _ptr(rays), len(rays), 1 if any_hit else 0, _ptr(hits), counts)
+    return hits, tuple(int(counts[k]) for k in range(4 if levels else 3))
 
 
 def online_cores():

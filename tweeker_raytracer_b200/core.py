@@ -31,6 +31,7 @@ SYMBOLS = [
     "rtc_composite", "rtc_tonemap", "rtc_stats_get", "rtc_stats_reset",
     "rtc_launch_pass_stats_get", "rtc_probe_gather", "rtc_probe_pipes", "rtc_scene_export", "rtc_gas_info", "rtc_gas_export",
     "rtc_probe_math",
+    "rtc_host_gas_build", "rtc_host_ias_build", "rtc_host_accel_info", "rtc_host_accel_export", "rtc_host_accel_destroy",
 ]
 
 MATH_FUNCTIONS = ["sin", "cos", "atan", "atan2", "acos", "exp", "log", "pow", "div", "sqrt", "muladd"]     # enum rtc_math_fn
@@ -121,6 +122,12 @@ def lib():
         L.rtc_probe_gather.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_double)]
         L.rtc_probe_pipes.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
         L.rtc_probe_math.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.rtc_host_gas_build.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
+        L.rtc_host_ias_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
+        L.rtc_host_accel_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p]
+        L.rtc_host_accel_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rtc_host_accel_destroy.argtypes = [C.c_void_p]
+        L.rtc_host_accel_destroy.restype = None
         _lib = L
     return _lib
 
@@ -128,6 +135,48 @@ def lib():
 def _check(rc):
     if rc != 0:
         raise RtcError(lib().rtc_last_error().decode("utf-8", "replace"))
+
+
+def host_scene_export(geometries, instances):
+    """The acceleration structure rtc_gas_build(BUILD_HOST_SAH) + rtc_ias_build would upload for this scene, built WITHOUT a GPU
+    (rtc_host_gas_build / rtc_host_ias_build: the same builder code fed from host arrays), in the layout of Context.scene_export.
+    geometries: [(attributes structured array or [n, k] float32 with the position first, indices [m, 3] uint32)];
+    instances: [(transform 12 floats, geometry index)].  Also returns the build statistics per level."""
+    L = lib()
+    accels, gas, info = [], {}, {"gas_nodes": [], "gas_tris": []}
+    try:
+        for g, (attrs, idx) in enumerate(geometries):
+            attrs = np.ascontiguousarray(attrs)
+            idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1, 3)
+            h = C.c_void_p()
+            stride = attrs.dtype.itemsize * int(np.prod(attrs.shape[1:], dtype=np.int64))      # bytes per vertex record
+            _check(L.rtc_host_gas_build(attrs.ctypes.data_as(C.c_void_p), stride, len(attrs), idx.ctypes.data_as(C.c_void_p), len(idx), C.byref(h)))
+            accels.append(h)
+            nn, npr = C.c_uint64(0), C.c_uint64(0)
+            _check(L.rtc_host_accel_info(h, C.byref(nn), C.byref(npr), None))
+            nodes = np.zeros((nn.value, 80), dtype=np.uint8)
+            tris = np.zeros((max(npr.value, 1), 12), dtype=np.float32)
+            _check(L.rtc_host_accel_export(h, nodes.ctypes.data_as(C.c_void_p), None, tris.ctypes.data_as(C.c_void_p), None))
+            gas[g] = (nodes, tris[:npr.value])
+            info["gas_nodes"].append(int(nn.value)); info["gas_tris"].append(int(npr.value))
+        n = len(instances)
+        transforms = np.ascontiguousarray([np.asarray(t, dtype=np.float32).reshape(12) for t, _ in instances], dtype=np.float32).reshape(n, 12)
+        inst_gas = np.ascontiguousarray([g for _, g in instances], dtype=np.uint32)
+        handles = (C.c_void_p * max(n, 1))(*[accels[int(g)] for g in inst_gas])
+        top = C.c_void_p()
+        _check(L.rtc_host_ias_build(transforms.ctypes.data_as(C.c_void_p), C.cast(handles, C.c_void_p), n, C.byref(top)))
+        accels.append(top)
+        nn, npr = C.c_uint64(0), C.c_uint64(0)
+        _check(L.rtc_host_accel_info(top, C.byref(nn), C.byref(npr), None))
+        nodes = np.zeros((nn.value, 80), dtype=np.uint8)
+        leaves = np.zeros(max(npr.value, 1), dtype=np.uint32)
+        w2o = np.zeros((n, 12), dtype=np.float32)
+        _check(L.rtc_host_accel_export(top, nodes.ctypes.data_as(C.c_void_p), leaves.ctypes.data_as(C.c_void_p), None, w2o.ctypes.data_as(C.c_void_p)))
+        info["tlas_nodes"] = int(nn.value)
+    finally:
+        for h in accels:
+            L.rtc_host_accel_destroy(h)
+    return {"tlas_nodes": nodes, "tlas_leaves": leaves[:npr.value], "world_to_object": w2o, "instance_gas": inst_gas, "gas": gas}, info
 
 
 def device_count():

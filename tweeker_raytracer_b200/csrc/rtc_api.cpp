@@ -22,27 +22,6 @@ double now_ms()
   return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
-// World->object matrix of an instance.  DEFINED here (OptiX computed it inside optixAccelBuild,
-// Device.cpp:1478, read back by closesthit.cu:49-52): adjugate / determinant of the upper 3x3 in double,
-// rounded once to float; translation -(Minv * t) in double.  The oracle states the same definition.
-void invert_3x4(const float m[12], float out[12])
-{
-  const double a = m[0], b = m[1], c = m[2],  tx = m[3];
-  const double d = m[4], e = m[5], f = m[6],  ty = m[7];
-  const double g = m[8], h = m[9], i = m[10], tz = m[11];
-  const double c00 = e * i - f * h, c01 = c * h - b * i, c02 = b * f - c * e;
-  const double c10 = f * g - d * i, c11 = a * i - c * g, c12 = c * d - a * f;
-  const double c20 = d * h - e * g, c21 = b * g - a * h, c22 = a * e - b * d;
-  const double det = a * c00 + b * c10 + c * c20;
-  const double r = 1.0 / det;
-  const double i00 = c00 * r, i01 = c01 * r, i02 = c02 * r;
-  const double i10 = c10 * r, i11 = c11 * r, i12 = c12 * r;
-  const double i20 = c20 * r, i21 = c21 * r, i22 = c22 * r;
-  out[0] = (float)i00; out[1] = (float)i01; out[2]  = (float)i02; out[3]  = (float)(-(i00 * tx + i01 * ty + i02 * tz));
-  out[4] = (float)i10; out[5] = (float)i11; out[6]  = (float)i12; out[7]  = (float)(-(i10 * tx + i11 * ty + i12 * tz));
-  out[8] = (float)i20; out[9] = (float)i21; out[10] = (float)i22; out[11] = (float)(-(i20 * tx + i21 * ty + i22 * tz));
-}
-
 SceneRecord* find_scene(rtc_context* ctx, uint64_t topObject)
 {
   for (SceneRecord* s : ctx->scenes) if ((uint64_t)(uintptr_t)s->d_desc == topObject) return s;
@@ -350,38 +329,9 @@ int rtc_gas_build(rtc_context* ctx, uint64_t attributes, uint32_t strideBytes, u
     RTC_CUDA(cudaStreamSynchronize(ctx->stream));
     if (!verts.empty()) RTC_CUDA(cudaMemcpy(verts.data(), (const void*)(uintptr_t)attributes, verts.size(), cudaMemcpyDeviceToHost));
     if (!idx.empty()) RTC_CUDA(cudaMemcpy(idx.data(), (const void*)(uintptr_t)indices, idx.size() * 4u, cudaMemcpyDeviceToHost));
-    std::vector<PrimBox> boxes(numTris);
-    auto vertex = [&](uint32_t i) { return reinterpret_cast<const float*>(verts.data() + (size_t)i * strideBytes); };
-    for (uint32_t t = 0; t < numTris; ++t)
-    {
-      PrimBox& b = boxes[t];
-      for (int k = 0; k < 3; ++k) { b.lo[k] = std::numeric_limits<float>::infinity(); b.hi[k] = -b.lo[k]; }
-      for (int c = 0; c < 3; ++c)
-      {
-        const uint32_t vi = idx[3u * t + c];
-        if (vi >= numVerts) RTC_FAIL("triangle index out of range");
-        const float* p = vertex(vi);
-        for (int k = 0; k < 3; ++k) { b.lo[k] = std::fmin(b.lo[k], p[k]); b.hi[k] = std::fmax(b.hi[k], p[k]); }
-      }
-    }
     WideBvh bvh;
-    // triangles per leaf child of the host SAH build.  2: geometry scene 2526 -> 2545 Msamples/s, Cornell box 809 -> 820 against
-    // leaves of up to 3; 1 is better only for the instanced scene (355 -> 368) and loses 2 % elsewhere.  RTC_HOST_LEAF_MAX overrides.
-    uint32_t leafMax = 2;
-    if (const char* e = getenv("RTC_HOST_LEAF_MAX")) { const int v = atoi(e); if (1 <= v && v <= 3) leafMax = (uint32_t)v; }
-    build_wide_bvh_host(boxes.data(), numTris, bvh, leafMax);
-    std::vector<float4> tris((size_t)numTris * 3u);
-    for (uint32_t s = 0; s < numTris; ++s)
-    {
-      const uint32_t prim = bvh.primOrder[s];
-      for (int c = 0; c < 3; ++c)
-      {
-        const float* p = vertex(idx[3u * prim + c]);
-        float w = 0.0f;
-        if (c == 0) std::memcpy(&w, &prim, 4);
-        tris[3u * (size_t)s + c] = make_float4(p[0], p[1], p[2], w);
-      }
-    }
+    std::vector<float4> tris;
+    if (!gas_assemble_host(verts.data(), strideBytes, numVerts, idx.data(), numTris, bvh, tris)) RTC_FAIL("triangle index out of range");
     rec.numNodes = (uint32_t)bvh.nodes.size();
     for (int k = 0; k < 3; ++k) { rec.lo[k] = bvh.lo[k]; rec.hi[k] = bvh.hi[k]; }
     RTC_CUDA(cudaMalloc(&rec.d_nodes, bvh.nodes.size() * sizeof(Node8)));
@@ -443,51 +393,17 @@ int rtc_ias_build(rtc_context* ctx, const rtc_instance_desc* instances, uint32_t
     gi[i].attributes = g.attributes; gi[i].indices = g.indices; gi[i].materialIndex = d.materialIndex; gi[i].lightIndex = d.lightIndex;
 
   }
-  // World bounds per instance: exact bounds of the transformed vertices (device kernel), padded -- the object-space ray is a
-  // ROUNDED transform of the world ray, so a hit found in object space may lie a few ulps outside the exact world-space box.
-  // RTC_INSTANCE_BOUNDS=box falls back to the eight transformed corners of the GAS box (the round-1 bounds, looser for
-  // rotated instances).
-  const bool tight = !(getenv("RTC_INSTANCE_BOUNDS") && getenv("RTC_INSTANCE_BOUNDS")[0] == 'b');
+  // World bounds per instance: exact bounds of the transformed vertices (device kernel), padded by instance_box_finish
+  // (accel_host.cpp).  RTC_INSTANCE_BOUNDS=box falls back to the eight transformed corners of the GAS box.
+  const bool tight = instance_bounds_tight();
   if (tight) { if (int rc = instance_bounds_gpu(ctx, instances, numInstances, boxes.data())) { delete rec; return rc; } }
   for (uint32_t i = 0; i < numInstances; ++i)
   {
-    const rtc_instance_desc& d = instances[i];
-    const GasRecord& g = ctx->gas[d.gas];
-    PrimBox& b = boxes[i];
-    const double ext = std::fabs((double)g.hi[0] - g.lo[0]) + std::fabs((double)g.hi[1] - g.lo[1]) + std::fabs((double)g.hi[2] - g.lo[2]);
-    if (tight)
-    {
-      for (int r = 0; r < 3; ++r)
-      {
-        const float* m = &d.transform[4 * r];
-        const double scale = std::fabs((double)m[0]) + std::fabs((double)m[1]) + std::fabs((double)m[2]);
-        const double padLo = (std::fabs((double)b.lo[r]) + ext * scale) * 1.0e-5, padHi = (std::fabs((double)b.hi[r]) + ext * scale) * 1.0e-5;
-        b.lo[r] = std::nextafterf((float)((double)b.lo[r] - padLo), -std::numeric_limits<float>::infinity());
-        b.hi[r] = std::nextafterf((float)((double)b.hi[r] + padHi), std::numeric_limits<float>::infinity());
-      }
-    }
-    else
-    {
-      for (int k = 0; k < 3; ++k) { b.lo[k] = std::numeric_limits<float>::infinity(); b.hi[k] = -b.lo[k]; }
-      for (int corner = 0; corner < 8; ++corner)
-      {
-        const double x = (corner & 1) ? g.hi[0] : g.lo[0], y = (corner & 2) ? g.hi[1] : g.lo[1], z = (corner & 4) ? g.hi[2] : g.lo[2];
-        for (int r = 0; r < 3; ++r)
-        {
-          const float* m = &d.transform[4 * r];
-          const double wv = m[0] * x + m[1] * y + m[2] * z + m[3];
-          const double scale = std::fabs((double)m[0]) + std::fabs((double)m[1]) + std::fabs((double)m[2]);
-          const double pad = (std::fabs(wv) + ext * scale) * 1.0e-5;
-          const float lo = std::nextafterf((float)(wv - pad), -std::numeric_limits<float>::infinity());
-          const float hi = std::nextafterf((float)(wv + pad), std::numeric_limits<float>::infinity());
-          b.lo[r] = std::fmin(b.lo[r], lo); b.hi[r] = std::fmax(b.hi[r], hi);
-        }
-      }
-    }
-    if (g.numTris == 0) { for (int k = 0; k < 3; ++k) { b.lo[k] = 0.0f; b.hi[k] = 0.0f; } }
+    const GasRecord& g = ctx->gas[instances[i].gas];
+    instance_box_finish(instances[i].transform, g.lo, g.hi, tight, g.numTris == 0, boxes[i]);
   }
   WideBvh bvh;
-  build_wide_bvh_host(boxes.data(), numInstances, bvh, getenv("RTC_TLAS_LEAF") ? (uint32_t)atoi(getenv("RTC_TLAS_LEAF")) : 1u);
+  tlas_build_host(boxes.data(), numInstances, bvh);
 
   auto upload = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
     cudaError_t e = cudaMalloc(dst, bytes ? bytes : 16);

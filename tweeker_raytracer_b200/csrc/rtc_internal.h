@@ -72,6 +72,16 @@ struct PrimBox { float lo[3], hi[3]; };
 // (geometry scene: 1.30 -> 1.06 instance entries per ray, +7.5 % samples/s).
 void build_wide_bvh_host(const PrimBox* prims, uint32_t numPrims, WideBvh& out, uint32_t leafMax = 3);
 
+// accel_host.cpp: the host halves of rtc_gas_build (host SAH builder) and rtc_ias_build -- no CUDA call in any of them -- shared
+// with the host-only twin of the two builds (rtc_host_gas_build / rtc_host_ias_build, include/rtc_core.h).
+void invert_3x4(const float m[12], float out[12]);
+bool gas_assemble_host(const uint8_t* verts, uint32_t strideBytes, uint32_t numVerts, const uint32_t* idx, uint32_t numTris,
+                       WideBvh& bvh, std::vector<float4>& tris);
+void instance_bounds_host(const float transform[12], const uint8_t* verts, uint32_t strideBytes, uint32_t numVerts, PrimBox& out);
+void instance_box_finish(const float transform[12], const float gasLo[3], const float gasHi[3], bool tight, bool emptyGas, PrimBox& b);
+bool instance_bounds_tight();      // false with RTC_INSTANCE_BOUNDS=box
+void tlas_build_host(const PrimBox* boxes, uint32_t numInstances, WideBvh& bvh);
+
 struct GasRecord
 {
   void*    d_nodes = nullptr;              // Node8[numNodes]
