@@ -211,6 +211,20 @@ class Scene:
         self.L.orc_trace_any(self.h, _ptr(rays), len(rays), 1 if brute_force else 0, _ptr(occ), C.byref(stats) if stats is not None else None)
         return occ
 
+    def trace_closest_after(self, rays, keys):
+        """Closest candidate AFTER the key (t bits, instance, primitive) in the canonical order, per ray (orc_trace_closest_after:
+        the step of the ordered any-hit processing)."""
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        keys = np.ascontiguousarray(keys, dtype=np.uint32).reshape(len(rays), 3)
+        hits = np.zeros(len(rays), dtype=HIT_DTYPE)
+        self.L.orc_trace_closest_after.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_uint32, C.c_uint32, C.c_void_p]
+        self.L.orc_trace_closest_after.restype = None
+        t = keys[:, 0].copy().view(np.float32)
+        for i in range(len(rays)):
+            self.L.orc_trace_closest_after(self.h, C.c_void_p(rays.ctypes.data + i * RAY_DTYPE.itemsize), C.c_float(float(t[i])), int(keys[i, 1]), int(keys[i, 2]),
+                                           C.c_void_p(hits.ctypes.data + i * HIT_DTYPE.itemsize))
+        return hits
+
     def generate_primary(self, sys, launch_width, launch_height, iteration):
         rays = np.zeros(launch_width * launch_height, dtype=RAY_DTYPE)
         self.L.orc_generate_primary(self.h, C.byref(sys), launch_width, launch_height, iteration, _ptr(rays))

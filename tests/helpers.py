@@ -155,3 +155,58 @@ def portable_math_call(lib, name, x, y=None):
     o = np.zeros_like(x)
     getattr(lib, "p_" + name)(x.ctypes.data_as(ctypes.c_void_p), y.ctypes.data_as(ctypes.c_void_p), o.ctypes.data_as(ctypes.c_void_p), len(x))
     return o
+
+
+_trace_host = None
+
+
+def product_trace_lib():
+    """tests/native/trace_host.cpp: the PRODUCT's traversal source (csrc/trace.cuh) compiled for the host by g++; built once per
+    session into oracle/_build (git-ignored) next to the oracle."""
+    global _trace_host
+    if _trace_host is None:
+        import ctypes
+        import subprocess
+        src = os.path.join(ROOT, "tests", "native", "trace_host.cpp")
+        out_dir = os.path.join(ROOT, "oracle", "_build")
+        os.makedirs(out_dir, exist_ok=True)
+        so = os.path.join(out_dir, "libtrace_host.so")
+        deps = [src, os.path.join(ROOT, "tweeker_raytracer_b200", "csrc", "trace.cuh"), os.path.join(ROOT, "tweeker_raytracer_b200", "csrc", "rtc_internal.h")]
+        if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"),
+                                   "-I" + os.path.join(ROOT, "tweeker_raytracer_b200", "csrc"), "-I/usr/local/cuda/include", "-o", so, src])
+        _trace_host = ctypes.CDLL(so)
+    return _trace_host
+
+
+def product_trace(export, rays, any_hit=False, skip=None):
+    """Runs the host build of csrc/trace.cuh over an exported (or host-built) wide BVH: (hits, (nodes, tris, instances), stack
+    overflows).  skip: [n, 3] uint32 keys (t bits, instance, primitive) -> the closest candidate AFTER the key (SKIP variant)."""
+    import ctypes as C
+    L = product_trace_lib()
+    handles = sorted(export["gas"])
+    slot = {g: k for k, g in enumerate(handles)}
+    inst_gas = np.ascontiguousarray([slot[int(g)] for g in export["instance_gas"]], dtype=np.uint32)
+    keep_n = [np.ascontiguousarray(export["gas"][g][0]) for g in handles]
+    keep_t = [np.ascontiguousarray(export["gas"][g][1], dtype=np.float32) for g in handles]
+    node_ptrs = (C.c_void_p * max(len(handles), 1))(*[a.ctypes.data for a in keep_n])
+    tri_ptrs = (C.c_void_p * max(len(handles), 1))(*[a.ctypes.data for a in keep_t])
+    n_nodes = np.ascontiguousarray([len(a) for a in keep_n], dtype=np.uint32)
+    n_tris = np.ascontiguousarray([len(a) for a in keep_t], dtype=np.uint32)
+    tn, tl, w2o = (np.ascontiguousarray(export[k]) for k in ("tlas_nodes", "tlas_leaves", "world_to_object"))
+    ws = orc.WideScene(tn.ctypes.data, tl.ctypes.data, w2o.ctypes.data, inst_gas.ctypes.data, C.cast(node_ptrs, C.c_void_p), C.cast(tri_ptrs, C.c_void_p),
+                       len(export["instance_gas"]))
+    rays = np.ascontiguousarray(rays, dtype=orc.RAY_DTYPE)
+    hits = np.zeros(len(rays), dtype=orc.HIT_DTYPE)
+    counts = (C.c_uint64 * 3)()
+    overflows = C.c_uint64(0)
+    skip_ptr = None
+    if skip is not None:
+        skip = np.ascontiguousarray(skip, dtype=np.uint32).reshape(len(rays), 3)
+        skip_ptr = skip.ctypes.data_as(C.c_void_p)
+    L.th_trace.argtypes = [C.POINTER(orc.WideScene), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int,
+                           C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    rc = L.th_trace(C.byref(ws), len(tn), len(tl), len(handles), n_nodes.ctypes.data_as(C.c_void_p), n_tris.ctypes.data_as(C.c_void_p),
+                    rays.ctypes.data_as(C.c_void_p), len(rays), 1 if any_hit else 0, skip_ptr, hits.ctypes.data_as(C.c_void_p), counts, C.byref(overflows))
+    assert rc == 0
+    return hits, (int(counts[0]), int(counts[1]), int(counts[2])), int(overflows.value)

@@ -1,0 +1,124 @@
+// tests/native/trace_host.cpp -- TEST INFRASTRUCTURE: the PRODUCT's traversal source compiled for the host.
+//
+// csrc/trace.cuh (node test, watertight triangle test, instance entry, the stack machine of Traversal::step, the ordered
+// any-hit SKIP variant) is included here unchanged and compiled by g++: the CUDA intrinsics it uses are given their IEEE
+// meaning below, its three inline-PTX helpers carry a C++ twin behind `#if defined(__CUDACC__)` (the device build is
+// untouched: identical SASS).  One host thread plays one lane: begin(), step() until done, result().  What is NOT covered is
+// the warp-level driver (trace_stream: ballots, the ray cursor) -- it is never instantiated here -- and the approximate
+// reciprocal of the timed kernels (this build uses the IEEE one, like the GPU's counting kernels).
+//
+// tests/test_cpu_trace_source.py holds the result against the scalar oracle: hits bit for bit against the oracle's binary
+// BVH and brute force, node / triangle / instance counters against oracle/wide_bvh.inc (the restatement the GPU counters are
+// compared with), and the SKIP enumeration against orc_trace_closest_after.
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include <cuda_runtime.h>
+#include <device_launch_parameters.h>
+
+// ---- the intrinsics trace.cuh uses, with their defined (round-to-nearest) meaning; built with -ffp-contract=off ----------
+static inline float  __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+static inline float  __fadd_rn(float a, float b) { return a + b; }
+static inline float  __fsub_rn(float a, float b) { return a - b; }
+static inline float  __fmul_rn(float a, float b) { return a * b; }
+static inline float  __fdiv_rn(float a, float b) { return a / b; }
+static inline float  __frcp_rn(float a) { return 1.0f / a; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline float    __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned old = *p; *p += v; return old; }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long old = *p; *p += v; return old; }
+// warp intrinsics: named by trace_stream (a template that is parsed but never instantiated here)
+unsigned __ballot_sync(unsigned, int);
+unsigned __shfl_sync(unsigned, unsigned, int);
+unsigned long long __shfl_down_sync(unsigned, unsigned long long, int);
+
+#include "trace.cuh"
+
+extern "C" {
+
+// the layout of orc_wide_scene (oracle/wide_bvh.inc), i.e. of oracle/orc.py WideScene
+struct th_scene
+{
+  const void*     tlasNodes;
+  const uint32_t* tlasLeaves;
+  const float*    worldToObject;
+  const uint32_t* instGas;
+  const void* const*  gasNodes;
+  const float* const* gasTris;
+  uint32_t numInstances;
+};
+
+// rays: rtc_ray; hits: rtc_hit; counts: nodes, triangles, instances.  skip: optional, per ray {t bits, instance, primitive}
+// -- when given, the SKIP instantiation runs (closest candidate AFTER the key) with tmin raised exactly as the device's
+// ExtendPathsAfter::load does.  numTlasNodes / numGasNodes / numGasTris size the 16-byte aligned copies.
+int th_trace(const th_scene* ws, uint32_t numTlasNodes, uint32_t numTlasLeaves, uint32_t numGas, const uint32_t* numGasNodes,
+             const uint32_t* numGasTris, const rtc_ray* rays, uint64_t n, int any, const uint32_t* skip, rtc_hit* hits, uint64_t counts[3],
+             uint64_t* stackOverflows)
+{
+  // 16-byte aligned copies: the traversal reads nodes, triangles and instance records as uint4 / float4
+  auto aligned = [](size_t bytes) { void* p = nullptr; if (posix_memalign(&p, 16, bytes ? bytes : 16)) return (void*)nullptr; return p; };
+  std::vector<void*> owned;
+  auto copy = [&](const void* src, size_t bytes) { void* p = aligned(bytes); owned.push_back(p); if (bytes) std::memcpy(p, src, bytes); return p; };
+  std::vector<const uint4*> gasNodes(numGas);
+  std::vector<const float4*> gasTris(numGas);
+  for (uint32_t g = 0; g < numGas; ++g)
+  {
+    gasNodes[g] = (const uint4*)copy(ws->gasNodes[g], (size_t)numGasNodes[g] * 80u);
+    gasTris[g] = (const float4*)copy(ws->gasTris[g], (size_t)numGasTris[g] * 48u);
+  }
+  // instance records as rtc_ias_build writes them: world->object rows 0..2, {GAS nodes pointer, GAS triangles pointer}
+  float4* inst = (float4*)aligned((size_t)ws->numInstances * 64u); owned.push_back(inst);
+  for (uint32_t i = 0; i < ws->numInstances; ++i)
+  {
+    const float* m = ws->worldToObject + 12u * (size_t)i;
+    for (int r = 0; r < 3; ++r) inst[4u * i + r] = make_float4(m[4 * r], m[4 * r + 1], m[4 * r + 2], m[4 * r + 3]);
+    const uint64_t np = (uint64_t)(uintptr_t)gasNodes[ws->instGas[i]], tp = (uint64_t)(uintptr_t)gasTris[ws->instGas[i]];
+    const uint32_t w[4] = { (uint32_t)np, (uint32_t)(np >> 32), (uint32_t)tp, (uint32_t)(tp >> 32) };
+    std::memcpy(&inst[4u * i + 3], w, 16);
+  }
+  SceneDesc sc{};
+  sc.tlasNodes = (const uint4*)copy(ws->tlasNodes, (size_t)numTlasNodes * 80u);
+  sc.tlasLeaves = (const uint32_t*)copy(ws->tlasLeaves, (size_t)numTlasLeaves * 4u);
+  sc.instances = inst;
+  sc.numInstances = ws->numInstances; sc.numTlasNodes = numTlasNodes; sc.numTlasLeaves = numTlasLeaves;
+
+  counts[0] = counts[1] = counts[2] = 0;
+  const unsigned overflowsBefore = RTC_STACK_OVERFLOW_COUNTER;
+  uint2 smStack[RTC_SM_STACK]; float smRay[RTC_SM_RAY_WORDS]; uint2 lmStack[RTC_LM_STACK];
+  auto run = [&](auto& tr, const rtc_ray& r, float tmin) {
+    tr.smStack = smStack; tr.smRay = smRay; tr.lmStack = lmStack;
+    if (tr.begin(sc, make_float4(r.ox, r.oy, r.oz, tmin), make_float4(r.dx, r.dy, r.dz, r.tmax)))
+    {
+      while (tr.step(sc)) {}
+      counts[0] += tr.counts.nodes; counts[1] += tr.counts.tris; counts[2] += tr.counts.insts;
+    }
+    return tr.result();
+  };
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    TraceHit h;
+    if (skip)
+    {
+      Traversal<false, true, 1, true> tr;
+      tr.skipT = __uint_as_float(skip[3 * i]); tr.skipInst = skip[3 * i + 1]; tr.skipPrim = skip[3 * i + 2];
+      h = run(tr, rays[i], fmaxf(rays[i].tmin, __uint_as_float(skip[3 * i] - 1u)));
+    }
+    else if (any) { Traversal<true, true, 1, false> tr; h = run(tr, rays[i], rays[i].tmin); }
+    else          { Traversal<false, true, 1, false> tr; h = run(tr, rays[i], rays[i].tmin); }
+    if (hits) { hits[i].t = h.t; hits[i].u = h.u; hits[i].v = h.v; hits[i].inst = h.inst; hits[i].prim = h.prim; }
+  }
+  if (stackOverflows) *stackOverflows = RTC_STACK_OVERFLOW_COUNTER - overflowsBefore;
+  for (void* p : owned) free(p);
+  return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,145 @@
+"""The PRODUCT's traversal source on the CPU: csrc/trace.cuh -- node test, watertight triangle test, instance entry, the stack
+machine of Traversal::step, the SKIP variant of the ordered any-hit processing -- compiled unchanged by g++
+(tests/native/trace_host.cpp gives the CUDA intrinsics their IEEE meaning; one host thread plays one lane) and held against
+
+  * a B200: on the structure a B200 exported it finds the GPU's hits and counts the GPU's nodes / triangles / instance
+    entries (tests/golden/wide_bvh_small.npz), closest hit and any hit;
+  * the scalar oracle: hits bit for bit equal to the oracle's own binary BVH and to brute force over every triangle, counters
+    equal to oracle/wide_bvh.inc -- which makes that restatement a checked model of the kernels on a machine without a GPU;
+  * the ordered any-hit enumeration: repeated SKIP queries list a ray's candidates in the canonical order
+    (t, instance, primitive) exactly as orc_trace_closest_after does;
+  * today's builder: the same on structures built by the host-only twin of the builder for every leaf size and both collapses,
+    with no traversal-stack overflow.
+
+What this does not execute is the warp-level driver (trace_stream: ballots, the ray cursor) and rcp.approx (the host build
+uses the IEEE reciprocal, like the GPU's counting kernels)."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import orc
+from tweeker_raytracer_b200 import core, host
+
+GOLD = os.path.join(H.ROOT, "tests", "golden")
+
+
+def fixture_export():
+    z = np.load(os.path.join(GOLD, "wide_bvh_small.npz"))
+    gas = {}
+    for key in z.files:
+        if key.startswith("gas") and key.endswith("_nodes"):
+            g = int(key[3:-6])
+            gas[g] = (z[key], z["gas%d_tris" % g])
+    return z, {"tlas_nodes": z["tlas_nodes"], "tlas_leaves": z["tlas_leaves"], "world_to_object": z["world_to_object"],
+               "instance_gas": z["instance_gas"], "gas": gas}
+
+
+def small_scene(tmp_path):
+    app = host.App(H.write_system(tmp_path, "rtigo3_cornell_box", resolution="32 32", samplesSqrt=1),
+                   os.path.join(GOLD, "scene_small_wide_bvh.txt"), host_only=True)
+    geos = [app.geometry(g) for g in range(app.info.numGeometries)]
+    insts = [app.instance(i)[:2] for i in range(app.info.numInstances)]
+    return app, geos, insts
+
+
+def test_host_build_of_the_traversal_source_equals_the_b200(built):
+    z, export = fixture_export()
+    hits, counts, overflows = H.product_trace(export, z["rays"])
+    assert H.hits_equal(hits, z["gpu_hits"])
+    assert counts == tuple(int(v) for v in z["gpu_counts_closest"][:3])
+    occl, counts_any, _ = H.product_trace(export, z["rays"], any_hit=True)
+    assert np.array_equal(occl["inst"] != 0xffffffff, z["gpu_occluded"].astype(bool))
+    assert counts_any == tuple(int(v) for v in z["gpu_counts_any"][:3])
+    assert overflows == 0
+
+
+def test_traversal_source_equals_the_oracle_and_its_restatement(built, tmp_path):
+    z, export = fixture_export()
+    app, _, _ = small_scene(tmp_path)
+    ref = H.oracle_scene(app)
+    rays = np.concatenate([z["rays"], H.random_rays(3000, 11)])
+    hits, counts, _ = H.product_trace(export, rays)
+    assert H.hits_equal(hits, ref.trace_closest(rays))
+    assert H.hits_equal(hits[:400], ref.trace_closest(rays[:400], brute_force=True))
+    model_hits, model_counts = orc.wide_trace(export, rays)
+    assert H.hits_equal(hits, model_hits) and counts == model_counts
+    occl, counts_any, _ = H.product_trace(export, rays, any_hit=True)
+    model_occl, model_counts_any = orc.wide_trace(export, rays, any_hit=True)
+    assert counts_any == model_counts_any
+    assert np.array_equal(occl["inst"], model_occl["inst"]) and np.array_equal(occl["prim"], model_occl["prim"])
+    assert np.array_equal(occl["inst"] != 0xffffffff, ref.trace_any(rays).astype(bool))
+    app.close()
+
+
+def test_skip_variant_enumerates_candidates_in_canonical_order(built, tmp_path):
+    z, export = fixture_export()
+    app, _, _ = small_scene(tmp_path)
+    ref = H.oracle_scene(app)
+    rays = z["rays"][:600].copy()
+    prev = ref.trace_closest(rays)
+    assert H.hits_equal(H.product_trace(export, rays)[0], prev)
+    listed = 0
+    for _ in range(4):                       # candidate 2, 3, 4, 5 of every ray that still has one
+        live = prev["inst"] != 0xffffffff
+        if not live.any():
+            break
+        rays, prev = rays[live], prev[live]
+        keys = np.stack([prev["t"].view(np.uint32), prev["inst"], prev["prim"]], axis=1)
+        want = ref.trace_closest_after(rays, keys)
+        got, _, _ = H.product_trace(export, rays, skip=keys)
+        assert H.hits_equal(got, want)
+        found = got["inst"] != 0xffffffff
+        # strictly after the key in (t, instance, primitive)
+        later = (got["t"] > prev["t"]) | ((got["t"] == prev["t"]) & ((got["inst"] > prev["inst"]) | ((got["inst"] == prev["inst"]) & (got["prim"] > prev["prim"]))))
+        assert later[found].all()
+        listed += int(found.sum())
+        prev = got
+    assert listed > 200
+    app.close()
+
+
+@pytest.mark.parametrize("leaf_max", [1, 2, 3])
+@pytest.mark.parametrize("collapse", ["optimal", "greedy"])
+def test_traversal_source_on_todays_builder(built, tmp_path, monkeypatch, leaf_max, collapse):
+    monkeypatch.setenv("RTC_HOST_LEAF_MAX", str(leaf_max))
+    monkeypatch.setenv("RTC_HOST_COLLAPSE", collapse)
+    z, _ = fixture_export()
+    app, geos, insts = small_scene(tmp_path)
+    export, _ = core.host_scene_export(geos, insts)
+    ref = H.oracle_scene(app)
+    rays = z["rays"]
+    hits, counts, overflows = H.product_trace(export, rays)
+    assert overflows == 0
+    assert H.hits_equal(hits, ref.trace_closest(rays)) and H.hits_equal(hits, z["gpu_hits"])
+    assert counts == orc.wide_trace(export, rays)[1]
+    occl, counts_any, _ = H.product_trace(export, rays, any_hit=True)
+    assert np.array_equal(occl["inst"] != 0xffffffff, z["gpu_occluded"].astype(bool))
+    assert counts_any == orc.wide_trace(export, rays, any_hit=True)[1]
+    app.close()
+
+
+def test_traversal_source_on_the_cornell_box_and_an_instanced_lattice(built, tmp_path):
+    """Larger structures of today's builder: the Cornell box (32 K-triangle sphere) and 343 rotated instances of a torus."""
+    import sys
+    sys.path.insert(0, os.path.join(H.ROOT, "tools"))
+    import make_instances_scene
+    lattice = os.path.join(str(tmp_path), "scene_lattice.txt")
+    make_instances_scene.write_scene(lattice, count=343, tess=(24, 12))
+    for scene, name, box in ((H.scene_path("rtigo3_cornell_box"), "rtigo3_cornell_box", None), (lattice, "rtigo3_instances", 12.0)):
+        app = host.App(H.write_system(tmp_path, name, resolution="48 32", samplesSqrt=1), scene, host_only=True)
+        geos = [app.geometry(g) for g in range(app.info.numGeometries)]
+        insts = [app.instance(i)[:2] for i in range(app.info.numInstances)]
+        export, _ = core.host_scene_export(geos, insts)
+        ref = H.oracle_scene(app)
+        w, h = app.resolution
+        primary = ref.generate_primary(H.oracle_sys(app), w, h, 0)
+        rand = H.random_rays(2500, 5) if box is None else H.random_rays(2500, 5, lo=(-box, 0.0, -box), hi=(box, box, box))
+        rays = np.concatenate([primary[primary["tmax"] > 0], rand])
+        hits, counts, overflows = H.product_trace(export, rays)
+        assert overflows == 0
+        assert H.hits_equal(hits, ref.trace_closest(rays))
+        assert counts == orc.wide_trace(export, rays)[1]
+        assert 0.05 < float((hits["inst"] != 0xffffffff).mean())
+        app.close()

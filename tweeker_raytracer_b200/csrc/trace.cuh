@@ -46,10 +46,14 @@ struct ObjRay
 // component k of (x, y, z) as two selects (a nested ternary compiles to divergent branches here)
 __device__ __forceinline__ float sel3(float x, float y, float z, int k)
 {
+#if defined(__CUDACC__)
   float r;
   asm("{\n\t.reg .pred p1, p2;\n\tsetp.eq.s32 p1, %4, 1;\n\tsetp.eq.s32 p2, %4, 2;\n\tselp.f32 %0, %2, %1, p1;\n\tselp.f32 %0, %3, %0, p2;\n\t}"
       : "=&f"(r) : "f"(x), "f"(y), "f"(z), "r"(k));
   return r;
+#else      // host build of this header (tests/native/trace_host.cpp): the same selection in C++
+  return (k == 2) ? z : ((k == 1) ? y : x);
+#endif
 }
 
 __device__ __forceinline__ void shear_setup(ObjRay& r)
@@ -126,9 +130,13 @@ __device__ __forceinline__ float fast_rcp(float d)
 {
   if (fabsf(d) < 0x1p-80f) d = copysignf(0x1p-80f, d);
   if (EXACT) return __frcp_rn(d);
+#if defined(__CUDACC__)
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
   return r;
+#else      // host build: rcp.approx has no portable definition; the host harness only instantiates EXACT = true
+  return 1.0f / d;
+#endif
 }
 
 template <bool EXACT = false>
@@ -149,9 +157,13 @@ __device__ __forceinline__ void box_setup(BoxRay& b, float ox, float oy, float o
 template <uint32_t I>
 __device__ __forceinline__ float quant_f(uint32_t w, uint32_t bias)
 {
+#if defined(__CUDACC__)
   uint32_t r;
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(bias), "n"(0x7404u | (I << 4)));
   return __uint_as_float(r);
+#else      // host build: selector 0x74I4 = {bias byte 3, bias byte 0, w byte I, bias byte 0} from the top byte down
+  return __uint_as_float((bias & 0xff000000u) | ((bias & 0xffu) << 16) | (((w >> (8u * I)) & 0xffu) << 8) | (bias & 0xffu));
+#endif
 }
 
 // q as a float through the conversion unit: one I2F.U8 with a byte selector.  It runs on the XU pipe, which the traversal
