@@ -143,3 +143,63 @@ def test_traversal_source_on_the_cornell_box_and_an_instanced_lattice(built, tmp
         assert counts == orc.wide_trace(export, rays)[1]
         assert 0.05 < float((hits["inst"] != 0xffffffff).mean())
         app.close()
+
+
+@pytest.mark.parametrize("seed", list(range(16)))
+def test_random_scenes_of_the_gpu_fuzz_test(built, tmp_path, seed):
+    """The scenes of tests/test_gpu_fuzz.py (same generator, same seeds: random instance transforms with non-uniform scale and
+    rotation, every model kind) through the host-only builder and the host build of the traversal source: closest hits and
+    occlusion of the same 30 000 random rays equal the oracle's, and the counters equal the restatement's."""
+    from test_gpu_fuzz import random_scene
+    rng = np.random.default_rng(1000 + seed)
+    scene = os.path.join(str(tmp_path), "scene_fuzz.txt")
+    random_scene(scene, rng)
+    app = host.App(H.write_system(tmp_path, "rtigo3_geometry", resolution="32 32", samplesSqrt=1), scene, host_only=True)
+    geos = [app.geometry(g) for g in range(app.info.numGeometries)]
+    insts = [app.instance(i)[:2] for i in range(app.info.numInstances)]
+    export, _ = core.host_scene_export(geos, insts)
+    ref = H.oracle_scene(app)
+    rays = H.random_rays(30000, seed=seed, lo=(-5, 0.05, -5), hi=(5, 4, 5))
+    hits, counts, overflows = H.product_trace(export, rays)
+    assert overflows == 0
+    assert H.hits_equal(hits, ref.trace_closest(rays))
+    assert counts == orc.wide_trace(export, rays)[1]
+    occl, _, _ = H.product_trace(export, rays, any_hit=True)
+    assert np.array_equal(occl["inst"] != 0xffffffff, ref.trace_any(rays).astype(bool))
+    app.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_random_triangle_soups_with_degenerate_input(built, seed):
+    """Unstructured soups straight through the C ABI of the host-only builder: triangles of wildly different sizes, exact
+    duplicates, zero-area triangles (repeated vertex, collinear), coordinates far from the origin; two instances (one mirrored
+    and non-uniformly scaled).  The reference for the hits is brute force over every triangle."""
+    rng = np.random.default_rng(seed)
+    n = 1500
+    centre = rng.uniform(-3, 3, size=(n, 1, 3)) + (1000.0 if seed == 4 else 0.0)
+    size = np.exp(rng.uniform(np.log(1e-3), np.log(2.0), size=(n, 1, 1)))
+    tris = (centre + size * rng.normal(size=(n, 3, 3))).astype(np.float32)
+    tris[10:20] = tris[0:10]                       # exact duplicates: ties -> smaller primitive id
+    tris[20:30, 1] = tris[20:30, 0]                # repeated vertex
+    tris[30:40, 2] = (tris[30:40, 0] + tris[30:40, 1]) * np.float32(0.5)      # collinear
+    verts = tris.reshape(-1, 3)
+    idx = np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+    ident = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], dtype=np.float32)
+    warped = np.array([-0.7, 0.2, 0, 1.5, 0.1, 1.3, 0.3, -0.5, 0, -0.4, 0.6, 2.0], dtype=np.float32)
+    export, info = core.host_scene_export([(verts, idx)], [(ident, 0), (warped, 0)])
+    attrs = np.zeros(len(verts), dtype=orc.ATTR_DTYPE)
+    attrs["vertex"] = verts
+    ref = orc.Scene()
+    ref.add_geometry(attrs, idx)
+    ref.add_instance(ident, 0, 0)
+    ref.add_instance(warped, 0, 0)
+    ref.commit()
+    off = 1000.0 if seed == 4 else 0.0
+    rays = H.random_rays(4000, seed=seed, lo=(-4 + off, -4 + off, -4 + off), hi=(4 + off, 4 + off, 4 + off))
+    hits, counts, overflows = H.product_trace(export, rays)
+    assert overflows == 0
+    assert H.hits_equal(hits, ref.trace_closest(rays, brute_force=True))
+    assert H.hits_equal(hits, ref.trace_closest(rays))
+    assert counts == orc.wide_trace(export, rays)[1]
+    assert float((hits["inst"] != 0xffffffff).mean()) > 0.2
+    ref.close()
