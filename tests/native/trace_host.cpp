@@ -121,4 +121,86 @@ int th_trace(const th_scene* ws, uint32_t numTlasNodes, uint32_t numTlasLeaves, 
   return 0;
 }
 
+// Lock-step emulation of ONE persistent warp of trace_stream (csrc/trace.cuh) over a ray list, for tools/simd_cost.py: 32
+// lanes, each owning one ray; when at least `fetchThreshold` lanes are idle (or all are) the idle lanes take the next rays in
+// list order; every iteration every active lane runs Traversal::step.  What a warp pays per iteration is the MAXIMUM over its
+// lanes, not the sum: out[] accumulates, over all iterations,
+//   [0] iterations  [1] iterations in which some lane visited a node  [2] sum over iterations of the largest number of
+//   triangles one lane tested  [3] iterations in which some lane entered an instance  [4] lane-steps (active lanes summed)
+//   [5] node visits summed over lanes  [6] triangle tests summed over lanes  [7] instance entries summed over lanes
+//   [8] refills  [9] rays
+// so that warpCost = cN*[1] + cT*[2] + cI*[3] + c0*[0] can be compared between acceleration structures built in different
+// ways -- a SIMD-aware version of the per-ray counters, still a model (no memory system, no issue scheduling).
+int th_simd_cost(const th_scene* ws, uint32_t numTlasNodes, uint32_t numTlasLeaves, uint32_t numGas, const uint32_t* numGasNodes,
+                 const uint32_t* numGasTris, const rtc_ray* rays, uint64_t n, int any, uint32_t fetchThreshold, uint64_t out[10])
+{
+  auto aligned = [](size_t bytes) { void* p = nullptr; if (posix_memalign(&p, 16, bytes ? bytes : 16)) return (void*)nullptr; return p; };
+  std::vector<void*> owned;
+  auto copy = [&](const void* src, size_t bytes) { void* p = aligned(bytes); owned.push_back(p); if (bytes) std::memcpy(p, src, bytes); return p; };
+  std::vector<const uint4*> gasNodes(numGas);
+  std::vector<const float4*> gasTris(numGas);
+  for (uint32_t g = 0; g < numGas; ++g)
+  {
+    gasNodes[g] = (const uint4*)copy(ws->gasNodes[g], (size_t)numGasNodes[g] * 80u);
+    gasTris[g] = (const float4*)copy(ws->gasTris[g], (size_t)numGasTris[g] * 48u);
+  }
+  float4* inst = (float4*)aligned((size_t)ws->numInstances * 64u); owned.push_back(inst);
+  for (uint32_t i = 0; i < ws->numInstances; ++i)
+  {
+    const float* m = ws->worldToObject + 12u * (size_t)i;
+    for (int r = 0; r < 3; ++r) inst[4u * i + r] = make_float4(m[4 * r], m[4 * r + 1], m[4 * r + 2], m[4 * r + 3]);
+    const uint64_t np = (uint64_t)(uintptr_t)gasNodes[ws->instGas[i]], tp = (uint64_t)(uintptr_t)gasTris[ws->instGas[i]];
+    const uint32_t w[4] = { (uint32_t)np, (uint32_t)(np >> 32), (uint32_t)tp, (uint32_t)(tp >> 32) };
+    std::memcpy(&inst[4u * i + 3], w, 16);
+  }
+  SceneDesc sc{};
+  sc.tlasNodes = (const uint4*)copy(ws->tlasNodes, (size_t)numTlasNodes * 80u);
+  sc.tlasLeaves = (const uint32_t*)copy(ws->tlasLeaves, (size_t)numTlasLeaves * 4u);
+  sc.instances = inst;
+  sc.numInstances = ws->numInstances; sc.numTlasNodes = numTlasNodes; sc.numTlasLeaves = numTlasLeaves;
+
+  for (int k = 0; k < 10; ++k) out[k] = 0;
+  struct Lane { uint2 smStack[RTC_SM_STACK]; float smRay[RTC_SM_RAY_WORDS]; uint2 lmStack[RTC_LM_STACK]; bool active = false; };
+  std::vector<Lane> lanes(32);
+  auto simulate = [&](auto proto) {
+    using Tr = decltype(proto);
+    std::vector<Tr> tr(32);
+    for (int l = 0; l < 32; ++l) { tr[l].smStack = lanes[l].smStack; tr[l].smRay = lanes[l].smRay; tr[l].lmStack = lanes[l].lmStack; lanes[l].active = false; }
+    uint64_t next = 0;
+    for (;;)
+    {
+      int idle = 0; for (int l = 0; l < 32; ++l) idle += lanes[l].active ? 0 : 1;
+      if (idle && next < n && (idle == 32 || (uint32_t)idle >= fetchThreshold))
+      {
+        out[8]++;
+        for (int l = 0; l < 32 && next < n; ++l)
+        {
+          if (lanes[l].active) continue;
+          const rtc_ray& r = rays[next++];
+          out[9]++;
+          if (tr[l].begin(sc, make_float4(r.ox, r.oy, r.oz, r.tmin), make_float4(r.dx, r.dy, r.dz, r.tmax))) lanes[l].active = true;
+        }
+      }
+      else if (idle == 32) break;
+      bool anyNode = false, anyInst = false; uint32_t maxTris = 0; int live = 0;
+      for (int l = 0; l < 32; ++l)
+      {
+        if (!lanes[l].active) continue;
+        ++live;
+        const uint32_t n0 = tr[l].counts.nodes, t0 = tr[l].counts.tris, i0 = tr[l].counts.insts;
+        const bool more = tr[l].step(sc);
+        const uint32_t dn = tr[l].counts.nodes - n0, dt = tr[l].counts.tris - t0, di = tr[l].counts.insts - i0;
+        anyNode |= dn != 0; anyInst |= di != 0; if (dt > maxTris) maxTris = dt;
+        out[5] += dn; out[6] += dt; out[7] += di;
+        if (!more) lanes[l].active = false;
+      }
+      if (live) { out[0]++; out[1] += anyNode ? 1 : 0; out[2] += maxTris; out[3] += anyInst ? 1 : 0; out[4] += (uint64_t)live; }
+    }
+  };
+  if (any) simulate(Traversal<true, true, 1, false>());
+  else     simulate(Traversal<false, true, 1, false>());
+  for (void* p : owned) free(p);
+  return 0;
+}
+
 } // extern "C"

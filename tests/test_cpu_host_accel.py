@@ -2,11 +2,11 @@
 csrc/accel_host.cpp): the same code rtc_gas_build(RTC_BUILD_HOST_SAH) and rtc_ias_build run before their uploads, fed from
 host arrays -- no CUDA call, no context.
 
-  * pinned against a B200: with the builder settings of the committed fixture's vintage (leaves of <= 3 triangles, the greedy
-    collapse) the host-only build reproduces BYTE FOR BYTE the structure a B200 exported (tests/golden/wide_bvh_small.npz,
+  * pinned against a B200: with the leaf size of the committed fixture's vintage (<= 3 triangles; today <= 2) the host-only
+    build reproduces BYTE FOR BYTE the structure a B200 exported (tests/golden/wide_bvh_small.npz,
     tests/golden/make_golden_wide_bvh.py) -- nodes, leaf-ordered triangles, instance-level leaves, world->object matrices,
     including the instance bounds the device kernel k_instance_bounds computed;
-  * the builder of today (leaves of <= 2, SAH-optimal collapse): every structural invariant of the node format the kernels
+  * every leaf size x both collapses (the greedy default and the opt-in SAH-optimal one): every structural invariant of the node format the kernels
     rely on, and closest hits / occlusion identical to the oracle's own binary BVH and to brute force over every triangle;
   * the optimal collapse never costs more summed node area than the greedy one, and needs fewer nodes;
   * edge cases: empty geometry, one triangle, an instance of an empty mesh, coincident primitives, index out of range.
@@ -119,8 +119,7 @@ def tri_boxes(tris):
 
 
 def test_host_only_build_reproduces_the_structure_a_b200_exported(built, tmp_path, monkeypatch):
-    monkeypatch.setenv("RTC_HOST_LEAF_MAX", "3")          # the builder settings the fixture was exported with
-    monkeypatch.setenv("RTC_HOST_COLLAPSE", "greedy")
+    monkeypatch.setenv("RTC_HOST_LEAF_MAX", "3")          # the leaf size the fixture was exported with (today: 2)
     z = np.load(os.path.join(GOLD, "wide_bvh_small.npz"))
     app, geos, insts = scene_arrays(tmp_path, os.path.join(GOLD, "scene_small_wide_bvh.txt"))
     export, info = core.host_scene_export(geos, insts)
@@ -142,6 +141,7 @@ def test_host_only_build_reproduces_the_structure_a_b200_exported(built, tmp_pat
 def test_builder_invariants_and_hits(built, tmp_path, monkeypatch, leaf_max, collapse):
     monkeypatch.setenv("RTC_HOST_LEAF_MAX", str(leaf_max))
     monkeypatch.setenv("RTC_HOST_COLLAPSE", collapse)
+    monkeypatch.setenv("RTC_TLAS_COLLAPSE", collapse)
     z = np.load(os.path.join(GOLD, "wide_bvh_small.npz"))
     app, geos, insts = scene_arrays(tmp_path, os.path.join(GOLD, "scene_small_wide_bvh.txt"))
     export, info = core.host_scene_export(geos, insts)
@@ -183,6 +183,7 @@ def test_optimal_collapse_beats_the_greedy_one(built, tmp_path, monkeypatch):
     result = {}
     for collapse in ("greedy", "optimal"):
         monkeypatch.setenv("RTC_HOST_COLLAPSE", collapse)
+        monkeypatch.setenv("RTC_TLAS_COLLAPSE", collapse)
         export, info = core.host_scene_export(geos, insts)
         g = max(export["gas"], key=lambda k: len(export["gas"][k][0]))        # the tessellated sphere
         result[collapse] = (len(export["gas"][g][0]), node_area_sum(export["gas"][g][0]))

@@ -105,6 +105,7 @@ def test_skip_variant_enumerates_candidates_in_canonical_order(built, tmp_path):
 def test_traversal_source_on_todays_builder(built, tmp_path, monkeypatch, leaf_max, collapse):
     monkeypatch.setenv("RTC_HOST_LEAF_MAX", str(leaf_max))
     monkeypatch.setenv("RTC_HOST_COLLAPSE", collapse)
+    monkeypatch.setenv("RTC_TLAS_COLLAPSE", collapse)
     z, _ = fixture_export()
     app, geos, insts = small_scene(tmp_path)
     export, _ = core.host_scene_export(geos, insts)

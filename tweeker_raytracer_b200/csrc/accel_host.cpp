@@ -138,7 +138,7 @@ bool instance_bounds_tight()
 
 void tlas_build_host(const PrimBox* boxes, uint32_t numInstances, WideBvh& bvh)
 {
-  build_wide_bvh_host(boxes, numInstances, bvh, getenv("RTC_TLAS_LEAF") ? (uint32_t)atoi(getenv("RTC_TLAS_LEAF")) : 1u);
+  build_wide_bvh_host(boxes, numInstances, bvh, getenv("RTC_TLAS_LEAF") ? (uint32_t)atoi(getenv("RTC_TLAS_LEAF")) : 1u, true);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -130,8 +130,8 @@ inline float pow2f(int e) { uint32_t u = (uint32_t)(e + 127) << 23; float f; std
 //   inner n: t[n][1] = area(n) + D(n, 8)                       one wide node whose <= 8 children cover the subtree
 //            t[n][i] = min(D(n, i), t[n][i - 1])               2 <= i <= 7
 //            D(n, j) = min over 0 < k < j of t[left][k] + t[right][j - k]
-// The greedy rule this replaces (open the child with the largest area until there are eight) fills the upper levels well but
-// leaves the bottom of the tree with two- and three-child nodes: 3.6 children per node on the instanced stress scene.
+// The greedy rule (open the child with the largest area until there are eight) fills the upper levels well but leaves the
+// bottom of the tree with two- and three-child nodes: 3.6 children per node on the instanced stress scene.
 struct Collapse
 {
   struct Entry
@@ -143,11 +143,12 @@ struct Collapse
   const std::vector<BinNode>& bn;
   std::vector<Entry> e;
 
-  explicit Collapse(const std::vector<BinNode>& nodes) : bn(nodes), e(nodes.size()) {}
+  explicit Collapse(const std::vector<BinNode>& nodes) : bn(nodes) {}
 
   // children are created after their parent (Builder::build), so a reverse sweep is bottom-up
   void run()
   {
+    e.resize(bn.size());
     for (size_t n = bn.size(); n-- > 0;)
     {
       Entry& x = e[n];
@@ -204,7 +205,7 @@ struct Emitter
   const std::vector<BinNode>& bn;
   const std::vector<uint32_t>& order;
   WideBvh& out;
-  const Collapse* collapse;     // null: the greedy collapse (RTC_HOST_COLLAPSE=greedy)
+  const Collapse* collapse;     // null: the greedy collapse (the default)
 
   // writes wide node `dst` for the binary subtree `src`
   void emit(uint32_t dst, int src)
@@ -314,7 +315,7 @@ struct Emitter
 
 } // namespace
 
-void build_wide_bvh_host(const PrimBox* prims, uint32_t numPrims, WideBvh& out, uint32_t leafMax)
+void build_wide_bvh_host(const PrimBox* prims, uint32_t numPrims, WideBvh& out, uint32_t leafMax, bool instanceLevel)
 {
   out.nodes.clear(); out.primOrder.clear();
   for (int k = 0; k < 3; ++k) { out.lo[k] = 0.0f; out.hi[k] = 0.0f; }
@@ -337,9 +338,15 @@ void build_wide_bvh_host(const PrimBox* prims, uint32_t numPrims, WideBvh& out, 
   out.nodes.reserve(numPrims / 2 + 8);
   out.primOrder.reserve(numPrims);
   out.nodes.emplace_back();
-  // RTC_HOST_COLLAPSE=greedy selects the round-1 collapse (largest child first) for A/B runs
-  const char* mode = getenv("RTC_HOST_COLLAPSE");
-  const bool greedy = mode && mode[0] == 'g';
+  // Collapse: greedy (open the largest child first) unless RTC_HOST_COLLAPSE=optimal (geometry level) / RTC_TLAS_COLLAPSE=optimal
+  // (instance level) selects the SAH-optimal dynamic programme.  The optimal collapse needs 30-48 % fewer nodes and visits 3-7 %
+  // fewer of them per ray, but a warp pays per iteration for the lane with the MOST triangles, and full bottom nodes hand one
+  // lane more triangles at a time; instance-level leaves of one node are entered without a new box test, so a fuller
+  // instance-level node culls less.  The lock-step warp model of tools/simd_cost.py (which reproduces the sign and size of
+  // six A/Bs round 2 measured on a B200) puts it at -3 % on the geometry scene, -2 % on the Cornell box, +2 % on the instanced
+  // stress scene (profiles/bvh_quality_r2.md); no GPU measurement of it exists, so the measured collapse stays the default.
+  const char* mode = getenv(instanceLevel ? "RTC_TLAS_COLLAPSE" : "RTC_HOST_COLLAPSE");
+  const bool greedy = !(mode && mode[0] == 'o');
   Collapse collapse(b.nodes);
   if (!greedy) collapse.run();
   Emitter em{ b.nodes, b.order, out, greedy ? nullptr : &collapse };

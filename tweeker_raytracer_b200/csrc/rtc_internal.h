@@ -70,7 +70,7 @@ struct PrimBox { float lo[3], hi[3]; };
 // leafMax: primitives per leaf child (1..3).  Triangles: 2 (rtc_gas_build).  Instances: 1 -- entering an instance costs about three node
 // visits (transform, shear constants, the GAS root), so a leaf box shared by two or three instances is never worth it
 // (geometry scene: 1.30 -> 1.06 instance entries per ray, +7.5 % samples/s).
-void build_wide_bvh_host(const PrimBox* prims, uint32_t numPrims, WideBvh& out, uint32_t leafMax = 3);
+void build_wide_bvh_host(const PrimBox* prims, uint32_t numPrims, WideBvh& out, uint32_t leafMax = 3, bool instanceLevel = false);
 
 // accel_host.cpp: the host halves of rtc_gas_build (host SAH builder) and rtc_ias_build -- no CUDA call in any of them -- shared
 // with the host-only twin of the two builds (rtc_host_gas_build / rtc_host_ias_build, include/rtc_core.h).
