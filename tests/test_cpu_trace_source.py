@@ -204,3 +204,22 @@ def test_random_triangle_soups_with_degenerate_input(built, seed):
     assert counts == orc.wide_trace(export, rays)[1]
     assert float((hits["inst"] != 0xffffffff).mean()) > 0.2
     ref.close()
+
+
+def test_lock_step_warp_model_is_consistent_with_the_per_ray_counters(built):
+    """tools/simd_cost.py's instrument (th_simd_cost): one persistent warp in lock step.  Its summed lane work must be the work
+    the per-ray run counts, whatever the refill threshold; its per-iteration maxima are bounded by both."""
+    z, export = fixture_export()
+    rays = z["rays"]
+    _, counts, _ = H.product_trace(export, rays)
+    for threshold in (1, 12, 32):
+        c = H.product_simd_cost(export, rays, fetch_threshold=threshold)
+        assert (c["nodes"], c["tris"], c["instances"]) == counts and c["rays"] == len(rays)
+        assert c["node_passes"] <= c["iterations"] and c["inst_passes"] <= c["iterations"]
+        assert c["nodes"] <= 32 * c["node_passes"] and c["node_passes"] <= c["nodes"]
+        assert c["tris"] <= 32 * c["tri_passes_max"] and c["tri_passes_max"] <= c["tris"]
+        assert c["lane_steps"] <= 32 * c["iterations"]
+    eager, lazy = H.product_simd_cost(export, rays, fetch_threshold=1), H.product_simd_cost(export, rays, fetch_threshold=32)
+    assert eager["iterations"] < lazy["iterations"]          # refilling early keeps the lanes busy: fewer warp iterations
+    occl = H.product_simd_cost(export, rays, any_hit=True)
+    assert (occl["nodes"], occl["tris"], occl["instances"]) == H.product_trace(export, rays, any_hit=True)[1]
