@@ -8,9 +8,9 @@ the product's traversal source compiled for the host (tests/native/trace_host.cp
 builder makes, and prints, per ray set (primary rays in 8x4 pixel tiles; bounce rays from the primary hit points grouped by
 direction octant inside runs of 256 like block_append2_sorted does; the same rays as shadow rays):
   iterations, node passes, triangle passes (sum of per-iteration maxima), instance passes, mean live lanes per iteration,
-  and cost = cN * node passes + cT * triangle passes + cI * instance passes + c0 * iterations, per ray.
+  and cost = cN * node passes + cT * triangle passes + cI * instance passes + c0 * iterations + cF * refills, per ray.
 The constants are static instruction counts of the kernel's phases relative to a node visit (profiles/sass_mix_r1.txt:
-node visit ~ 230 instructions, one triangle test ~ 100, instance entry ~ 170, loop + pop ~ 40).  It is a MODEL -- no memory
+node visit ~ 230 instructions, one triangle test ~ 100, instance entry ~ 170, loop + pop ~ 40, ray fetch + begin + store ~ 140).  It is a MODEL -- no memory
 system, no scheduler -- meant for A/B comparisons between builder settings (RTC_HOST_LEAF_MAX, RTC_TLAS_LEAF,
 RTC_HOST_COLLAPSE, RTC_INSTANCE_BOUNDS ...); profiles/bvh_quality_r2.md compares it with the A/Bs round 2 measured on a B200.
 
@@ -34,7 +34,7 @@ from oracle import orc                             # noqa: E402
 from tweeker_raytracer_b200 import core            # noqa: E402
 import bvh_quality                                 # noqa: E402
 
-C_NODE, C_TRI, C_INST, C_ITER = 1.0, 0.45, 0.75, 0.17
+C_NODE, C_TRI, C_INST, C_ITER, C_FETCH = 1.0, 0.45, 0.75, 0.17, 0.6
 
 
 def tile_order(w, h):
@@ -55,10 +55,10 @@ def octant_runs(rays, run=256):
 
 def summarise(c):
     rays = max(c["rays"], 1)
-    cost = C_NODE * c["node_passes"] + C_TRI * c["tri_passes_max"] + C_INST * c["inst_passes"] + C_ITER * c["iterations"]
+    cost = C_NODE * c["node_passes"] + C_TRI * c["tri_passes_max"] + C_INST * c["inst_passes"] + C_ITER * c["iterations"] + C_FETCH * c["refills"]
     return {"rays": c["rays"], "iterations_per_ray": round(c["iterations"] / rays, 4), "live_lanes": round(c["lane_steps"] / max(c["iterations"], 1), 2),
             "node_passes_per_ray": round(c["node_passes"] / rays, 4), "tri_passes_per_ray": round(c["tri_passes_max"] / rays, 4),
-            "inst_passes_per_ray": round(c["inst_passes"] / rays, 4), "nodes": round(c["nodes"] / rays, 3), "tris": round(c["tris"] / rays, 3),
+            "inst_passes_per_ray": round(c["inst_passes"] / rays, 4), "refills_per_ray": round(c["refills"] / rays, 4), "nodes": round(c["nodes"] / rays, 3), "tris": round(c["tris"] / rays, 3),
             "instances": round(c["instances"] / rays, 3), "warp_cost_per_ray": round(cost / rays, 4)}
 
 
