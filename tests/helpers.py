@@ -157,33 +157,36 @@ def portable_math_call(lib, name, x, y=None):
     return o
 
 
-_trace_host = None
+_trace_host = {}
 
 
-def product_trace_lib():
+def product_trace_lib(defs=()):
     """tests/native/trace_host.cpp: the PRODUCT's traversal source (csrc/trace.cuh) compiled for the host by g++; built once per
-    session into oracle/_build (git-ignored) next to the oracle."""
-    global _trace_host
-    if _trace_host is None:
+    session into oracle/_build (git-ignored) next to the oracle.  defs: extra -D switches of trace.cuh (e.g.
+    "RTC_ONE_TRI_PER_STEP=1"), each combination its own library."""
+    key = tuple(defs)
+    if key not in _trace_host:
         import ctypes
         import subprocess
         src = os.path.join(ROOT, "tests", "native", "trace_host.cpp")
         out_dir = os.path.join(ROOT, "oracle", "_build")
         os.makedirs(out_dir, exist_ok=True)
-        so = os.path.join(out_dir, "libtrace_host.so")
+        tag = "".join("_" + "".join(ch if ch.isalnum() else "-" for ch in d) for d in key)
+        so = os.path.join(out_dir, "libtrace_host%s.so" % tag)
         deps = [src, os.path.join(ROOT, "tweeker_raytracer_b200", "csrc", "trace.cuh"), os.path.join(ROOT, "tweeker_raytracer_b200", "csrc", "rtc_internal.h")]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"),
-                                   "-I" + os.path.join(ROOT, "tweeker_raytracer_b200", "csrc"), "-I/usr/local/cuda/include", "-o", so, src])
-        _trace_host = ctypes.CDLL(so)
-    return _trace_host
+                                   "-I" + os.path.join(ROOT, "tweeker_raytracer_b200", "csrc"), "-I/usr/local/cuda/include"]
+                                  + ["-D" + d for d in key] + ["-o", so, src])
+        _trace_host[key] = ctypes.CDLL(so)
+    return _trace_host[key]
 
 
-def product_trace(export, rays, any_hit=False, skip=None):
+def product_trace(export, rays, any_hit=False, skip=None, defs=()):
     """Runs the host build of csrc/trace.cuh over an exported (or host-built) wide BVH: (hits, (nodes, tris, instances), stack
     overflows).  skip: [n, 3] uint32 keys (t bits, instance, primitive) -> the closest candidate AFTER the key (SKIP variant)."""
     import ctypes as C
-    L = product_trace_lib()
+    L = product_trace_lib(defs)
     handles = sorted(export["gas"])
     slot = {g: k for k, g in enumerate(handles)}
     inst_gas = np.ascontiguousarray([slot[int(g)] for g in export["instance_gas"]], dtype=np.uint32)
@@ -215,11 +218,11 @@ def product_trace(export, rays, any_hit=False, skip=None):
 SIMD_COST_FIELDS = ["iterations", "node_passes", "tri_passes_max", "inst_passes", "lane_steps", "nodes", "tris", "instances", "refills", "rays"]
 
 
-def product_simd_cost(export, rays, any_hit=False, fetch_threshold=12):
+def product_simd_cost(export, rays, any_hit=False, fetch_threshold=12, defs=(), leaf_threshold=0):
     """Lock-step emulation of one persistent warp of trace_stream over `rays` in list order (tests/native/trace_host.cpp
     th_simd_cost): dict of SIMD_COST_FIELDS.  A model of what a warp pays (the maximum over its lanes per iteration)."""
     import ctypes as C
-    L = product_trace_lib()
+    L = product_trace_lib(defs)
     handles = sorted(export["gas"])
     slot = {g: k for k, g in enumerate(handles)}
     inst_gas = np.ascontiguousarray([slot[int(g)] for g in export["instance_gas"]], dtype=np.uint32)
@@ -235,8 +238,8 @@ def product_simd_cost(export, rays, any_hit=False, fetch_threshold=12):
     rays = np.ascontiguousarray(rays, dtype=orc.RAY_DTYPE)
     out = (C.c_uint64 * 10)()
     L.th_simd_cost.argtypes = [C.POINTER(orc.WideScene), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int,
-                               C.c_uint32, C.POINTER(C.c_uint64)]
+                               C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
     rc = L.th_simd_cost(C.byref(ws), len(tn), len(tl), len(handles), n_nodes.ctypes.data_as(C.c_void_p), n_tris.ctypes.data_as(C.c_void_p),
-                        rays.ctypes.data_as(C.c_void_p), len(rays), 1 if any_hit else 0, fetch_threshold, out)
+                        rays.ctypes.data_as(C.c_void_p), len(rays), 1 if any_hit else 0, fetch_threshold, leaf_threshold, out)
     assert rc == 0
     return {k: int(out[i]) for i, k in enumerate(SIMD_COST_FIELDS)}

@@ -123,7 +123,8 @@ int th_trace(const th_scene* ws, uint32_t numTlasNodes, uint32_t numTlasLeaves, 
 
 // Lock-step emulation of ONE persistent warp of trace_stream (csrc/trace.cuh) over a ray list, for tools/simd_cost.py: 32
 // lanes, each owning one ray; when at least `fetchThreshold` lanes are idle (or all are) the idle lanes take the next rays in
-// list order; every iteration every active lane runs Traversal::step.  What a warp pays per iteration is the MAXIMUM over its
+// list order; every iteration every active lane runs Traversal::step (leafThreshold > 0: the gated leaf phase of trace_stream's
+// RTC_LEAF_THRESHOLD path instead).  What a warp pays per iteration is the MAXIMUM over its
 // lanes, not the sum: out[] accumulates, over all iterations,
 //   [0] iterations  [1] iterations in which some lane visited a node  [2] sum over iterations of the largest number of
 //   triangles one lane tested  [3] iterations in which some lane entered an instance  [4] lane-steps (active lanes summed)
@@ -132,7 +133,8 @@ int th_trace(const th_scene* ws, uint32_t numTlasNodes, uint32_t numTlasLeaves, 
 // so that warpCost = cN*[1] + cT*[2] + cI*[3] + c0*[0] can be compared between acceleration structures built in different
 // ways -- a SIMD-aware version of the per-ray counters, still a model (no memory system, no issue scheduling).
 int th_simd_cost(const th_scene* ws, uint32_t numTlasNodes, uint32_t numTlasLeaves, uint32_t numGas, const uint32_t* numGasNodes,
-                 const uint32_t* numGasTris, const rtc_ray* rays, uint64_t n, int any, uint32_t fetchThreshold, uint64_t out[10])
+                 const uint32_t* numGasTris, const rtc_ray* rays, uint64_t n, int any, uint32_t fetchThreshold, uint32_t leafThreshold,
+                 uint64_t out[10])
 {
   auto aligned = [](size_t bytes) { void* p = nullptr; if (posix_memalign(&p, 16, bytes ? bytes : 16)) return (void*)nullptr; return p; };
   std::vector<void*> owned;
@@ -188,11 +190,38 @@ int th_simd_cost(const th_scene* ws, uint32_t numTlasNodes, uint32_t numTlasLeav
         if (!lanes[l].active) continue;
         ++live;
         const uint32_t n0 = tr[l].counts.nodes, t0 = tr[l].counts.tris, i0 = tr[l].counts.insts;
+        if (leafThreshold > 0)
+        {
+          // trace_stream's RTC_LEAF_THRESHOLD path, first half: node visits of the lanes without a pending leaf group
+          if (!tr[l].has_leaves()) tr[l].node_phase();
+          const uint32_t dnA = tr[l].counts.nodes - n0;
+          anyNode |= dnA != 0; out[5] += dnA;
+          continue;
+        }
         const bool more = tr[l].step(sc);
         const uint32_t dn = tr[l].counts.nodes - n0, dt = tr[l].counts.tris - t0, di = tr[l].counts.insts - i0;
         anyNode |= dn != 0; anyInst |= di != 0; if (dt > maxTris) maxTris = dt;
         out[5] += dn; out[6] += dt; out[7] += di;
         if (!more) lanes[l].active = false;
+      }
+      if (leafThreshold > 0)
+      {
+        // second half: the held lanes run their leaf phase together once enough of them hold one
+        int nHeld = 0;
+        for (int l = 0; l < 32; ++l) if (lanes[l].active && tr[l].has_leaves()) ++nHeld;
+        const bool runLeaves = nHeld && ((uint32_t)nHeld >= leafThreshold || nHeld * 4 >= live);
+        for (int l = 0; l < 32; ++l)
+        {
+          if (!lanes[l].active) continue;
+          bool running = true;
+          const uint32_t t0 = tr[l].counts.tris, i0 = tr[l].counts.insts;
+          if (runLeaves && tr[l].has_leaves()) running = tr[l].leaf_phase(sc);
+          const uint32_t dt = tr[l].counts.tris - t0, di = tr[l].counts.insts - i0;
+          anyInst |= di != 0; if (dt > maxTris) maxTris = dt;
+          out[6] += dt; out[7] += di;
+          if (running && !tr[l].has_leaves()) running = tr[l].advance(sc);
+          if (!running) lanes[l].active = false;
+        }
       }
       if (live) { out[0]++; out[1] += anyNode ? 1 : 0; out[2] += maxTris; out[3] += anyInst ? 1 : 0; out[4] += (uint64_t)live; }
     }

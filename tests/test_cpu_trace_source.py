@@ -223,3 +223,23 @@ def test_lock_step_warp_model_is_consistent_with_the_per_ray_counters(built):
     assert eager["iterations"] < lazy["iterations"]          # refilling early keeps the lanes busy: fewer warp iterations
     occl = H.product_simd_cost(export, rays, any_hit=True)
     assert (occl["nodes"], occl["tris"], occl["instances"]) == H.product_trace(export, rays, any_hit=True)[1]
+
+
+def test_one_triangle_per_step_variant_changes_no_hit_and_no_counter(built, tmp_path):
+    """RTC_ONE_TRI_PER_STEP=1 (an unmeasured experiment kept behind a compile-time switch, csrc/trace.cuh Traversal::step): the same
+    tests in the same order per ray -- identical hits, identical work counters, closest hit, any hit and the SKIP enumeration --
+    spread over more iterations with at most one triangle each."""
+    defs = ("RTC_ONE_TRI_PER_STEP=1",)
+    z, export = fixture_export()
+    rays = np.concatenate([z["rays"], H.random_rays(3000, 3)])
+    for any_hit in (False, True):
+        a_hits, a_counts, _ = H.product_trace(export, rays, any_hit=any_hit)
+        b_hits, b_counts, overflows = H.product_trace(export, rays, any_hit=any_hit, defs=defs)
+        assert H.hits_equal(a_hits, b_hits) and a_counts == b_counts and overflows == 0
+    first = H.product_trace(export, rays[:500])[0]
+    live = first["inst"] != 0xffffffff
+    keys = np.stack([first["t"].view(np.uint32), first["inst"], first["prim"]], axis=1)[live]
+    assert H.hits_equal(H.product_trace(export, rays[:500][live], skip=keys)[0], H.product_trace(export, rays[:500][live], skip=keys, defs=defs)[0])
+    base, variant = H.product_simd_cost(export, rays), H.product_simd_cost(export, rays, defs=defs)
+    assert (variant["nodes"], variant["tris"], variant["instances"]) == (base["nodes"], base["tris"], base["instances"])
+    assert variant["tri_passes_max"] < 0.6 * base["tri_passes_max"] and variant["iterations"] > base["iterations"]

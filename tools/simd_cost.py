@@ -15,6 +15,7 @@ system, no scheduler -- meant for A/B comparisons between builder settings (RTC_
 RTC_HOST_COLLAPSE, RTC_INSTANCE_BOUNDS ...); profiles/bvh_quality_r2.md compares it with the A/Bs round 2 measured on a B200.
 
   python tools/simd_cost.py [--config c1|c2|c4|textures] [--width 240 --height 136] [--instances 10000]
+                            [--threshold 12] [--leaf-threshold 0] [--define RTC_ONE_TRI_PER_STEP=1]
 """
 import argparse
 import json
@@ -68,7 +69,9 @@ def main():
     ap.add_argument("--width", type=int, default=240)
     ap.add_argument("--height", type=int, default=136)
     ap.add_argument("--instances", type=int, default=10000)
-    ap.add_argument("--threshold", type=int, default=12)
+    ap.add_argument("--threshold", type=int, default=12, help="idle lanes that trigger a refill (RTC_FETCH_THRESHOLD)")
+    ap.add_argument("--leaf-threshold", type=int, default=0, help="> 0: the gated leaf phase of trace_stream (RTC_LEAF_THRESHOLD)")
+    ap.add_argument("--define", action="append", default=[], help="compile-time switch of csrc/trace.cuh for the host build, e.g. RTC_ONE_TRI_PER_STEP=1")
     args = ap.parse_args()
     assert args.width % 8 == 0 and args.height % 4 == 0
     with tempfile.TemporaryDirectory() as tmp:
@@ -85,9 +88,10 @@ def main():
         finally:
             app.close()
     result = {"config": args.config, "resolution": [args.width, args.height], "nodes_total": sum(info["gas_nodes"]) + info["tlas_nodes"]}
-    result["primary"] = summarise(H.product_simd_cost(export, primary, False, args.threshold))
-    result["bounce"] = summarise(H.product_simd_cost(export, bounce, False, args.threshold))
-    result["shadow"] = summarise(H.product_simd_cost(export, bounce, True, args.threshold))
+    defs = tuple(args.define)
+    result["primary"] = summarise(H.product_simd_cost(export, primary, False, args.threshold, defs, args.leaf_threshold))
+    result["bounce"] = summarise(H.product_simd_cost(export, bounce, False, args.threshold, defs, args.leaf_threshold))
+    result["shadow"] = summarise(H.product_simd_cost(export, bounce, True, args.threshold, defs, args.leaf_threshold))
     print(json.dumps(result))
 
 

@@ -24,6 +24,9 @@
 #ifndef RTC_LEAF_THRESHOLD
 #define RTC_LEAF_THRESHOLD 0      // > 0: hold lanes with a pending leaf group back until this many lanes of the warp have one (trace_stream)
 #endif
+#ifndef RTC_ONE_TRI_PER_STEP
+#define RTC_ONE_TRI_PER_STEP 0    // 1: a step tests at most ONE triangle; a lane with more pending skips its node visit until they are done (see Traversal::step)
+#endif
 #ifndef RTC_FETCH_THRESHOLD
 #define RTC_FETCH_THRESHOLD 12    // refill a warp when at least this many lanes have finished their ray (8: -1.3 %, 16: same; re-swept in round 2)
 #endif
@@ -436,6 +439,9 @@ struct Traversal
             }
           }
         }
+#if RTC_ONE_TRI_PER_STEP
+        break;
+#endif
       }
     }
     return true;
@@ -466,9 +472,24 @@ struct Traversal
   // returns true while the ray needs more steps
   __device__ __forceinline__ bool step(const SceneDesc& sc)
   {
+#if RTC_ONE_TRI_PER_STEP
+    // EXPERIMENT, never measured on a GPU (built after the last GPU session of round 2; profiles/bvh_quality_r2.md).  A warp
+    // pays the triangle loop of an iteration for as long as its unluckiest lane: 3.2 tests on bounce rays of the geometry
+    // scene although a lane tests 0.4 per node visit on average.  Here a step tests at most one triangle and a lane with more
+    // pending skips its node visit, so every iteration costs one node pass plus one triangle pass: the same tests in the same
+    // order per ray (hits and work counters are unchanged, tests/test_cpu_trace_source.py), 26 % more iterations, 60 % fewer
+    // triangle passes.  The lock-step model of tools/simd_cost.py predicts -11 % traversal cost on the geometry scene and -20 %
+    // on the instanced one -- but the same model predicts a gain for the gated leaf phase (RTC_LEAF_THRESHOLD), which a B200
+    // measured 5 % SLOWER, so this is a lead to measure (make TRACE_DEFS=-DRTC_ONE_TRI_PER_STEP=1), not a result.
+    if (!(blasBase >= 0 && has_leaves())) node_phase();
+    if (!leaf_phase(sc)) return false;
+    if (blasBase >= 0 && has_leaves()) return true;
+    return advance(sc);
+#else
     node_phase();
     if (!leaf_phase(sc)) return false;
     return advance(sc);
+#endif
   }
 };
 
