@@ -22,6 +22,9 @@ Path-tracing configs (c1, c2, c4, c5).  A "step" renders `--spp-per-step` iterat
   cpu_baseline  oracle/_ref (the reference's shader sources host-compiled, kind "reference"; traversal served by the oracle's
             intersector) on a bounded sample of the same workload, one process per host core, plus one single-threaded run.
 
+  trace_schedule  which schedule of the triangle tests the timed steps ran with and the three warm-up batch times the library chose
+            it from (include/rtc_core.h rtc_trace_schedule_get; needs >= 3 warm-up steps to be settled before the timed ones).
+
 Ray configs (c3-*).  A step traces one set of rays against a synthetic triangle soup; value = Mrays/s.
 """
 import argparse
@@ -363,8 +366,9 @@ def ncu_child(args):
     app.close()
 
 
-def ncu_measure(args):
-    """{'extend': {...}, 'connect': {...}} per-launch averages of one step from an ncu child run, or (None, reason)."""
+def ncu_measure(args, schedule="group"):
+    """{'extend': {...}, 'connect': {...}} per-launch averages of one step from an ncu child run, or (None, reason).
+    schedule: the traversal schedule the timed steps ran with; the child is pinned to it (RTC_TRACE_SCHEDULE)."""
     import shutil
     ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
     if not os.path.exists(ncu):
@@ -375,7 +379,8 @@ def ncu_measure(args):
            sys.executable, os.path.abspath(__file__), "--ncu-child", "--config", args.config, "--scene", args.scene, "--resolution", args.resolution,
            "--spp-per-step", str(args.spp_per_step), "--instances", str(args.instances)]
     try:
-        out = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0")))
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0"),
+                                      RTC_TRACE_SCHEDULE="onetri" if schedule == "one_tri" else "group"))
     except Exception as e:
         return None, "ncu child failed: %r" % (e,)
     if out.returncode != 0 or not os.path.exists(log):
@@ -527,6 +532,12 @@ def main():
     prof = ctx.profile()
     ctx.profile_enable(False)
     stats = ctx.stats()
+    # which schedule of the triangle tests the timed steps ran with (the library times one warm-up batch with each and keeps the
+    # faster: include/rtc_core.h rtc_trace_schedule_get); with fewer than 3 warm-up steps the measurement reaches into the timed steps
+    try:
+        schedule = ctx.trace_schedule()
+    except Exception as e:          # reporting only
+        schedule = {"schedule": "group", "error": repr(e)}
     total_ms = steps_ms + reduce_ms
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     rays = torch.tensor([float(stats.radianceRays + stats.shadowRays)], dtype=torch.float64, device="cuda")
@@ -572,7 +583,7 @@ def main():
     traffic, traffic_src, ncu_res = None, "not measured (--no-ncu or N > 1)", None
     physical = {}
     if rank == 0 and n == 1 and not args.no_ncu:
-        ncu_res, traffic_src = ncu_measure(args)
+        ncu_res, traffic_src = ncu_measure(args, schedule.get("schedule", "group"))
         if ncu_res and "extend" in ncu_res and ext_ms > 0:
             e = ncu_res["extend"]
             traffic = e["dram_bytes_per_launch"]
@@ -658,7 +669,7 @@ def main():
                         "calling_pattern": args.calling_pattern,
                         "path": ("Application::render(count)" if not per_iteration else "%d x unsigned int Raytracer::render() (coalesced)" % S)
                                 + " + getOutputBufferHost per step" + (" (collective: ncclReduce mean to rank 0, then read back)" if n > 1 else "")},
-                "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline}
+                "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "trace_schedule": schedule}
         if parity is not None:
             line["parity_check"] = parity["result"]
             line["parity_detail"] = parity

@@ -226,9 +226,10 @@ def test_lock_step_warp_model_is_consistent_with_the_per_ray_counters(built):
 
 
 def test_one_triangle_per_step_variant_changes_no_hit_and_no_counter(built, tmp_path):
-    """RTC_ONE_TRI_PER_STEP=1 (an unmeasured experiment kept behind a compile-time switch, csrc/trace.cuh Traversal::step): the same
-    tests in the same order per ray -- identical hits, identical work counters, closest hit, any hit and the SKIP enumeration --
-    spread over more iterations with at most one triangle each."""
+    """The second schedule of the triangle tests (Traversal<..., ONETRI = true>, RTC_SCHEDULE_ONE_TRI; the host build selects it
+    with -DRTC_ONE_TRI_PER_STEP=1, the default of the template flag): the same tests in the same order per ray -- identical hits,
+    identical work counters, closest hit, any hit and the SKIP enumeration -- spread over more iterations with at most one
+    triangle each.  The GPU twin of this test is tests/test_gpu_trace_schedule.py."""
     defs = ("RTC_ONE_TRI_PER_STEP=1",)
     z, export = fixture_export()
     rays = np.concatenate([z["rays"], H.random_rays(3000, 3)])

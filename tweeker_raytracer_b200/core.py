@@ -32,6 +32,7 @@ SYMBOLS = [
     "rtc_launch_pass_stats_get", "rtc_probe_gather", "rtc_probe_pipes", "rtc_scene_export", "rtc_gas_info", "rtc_gas_export",
     "rtc_probe_math",
     "rtc_host_gas_build", "rtc_host_ias_build", "rtc_host_accel_info", "rtc_host_accel_export", "rtc_host_accel_destroy",
+    "rtc_trace_schedule_get", "rtc_trace_schedule_set",
 ]
 
 MATH_FUNCTIONS = ["sin", "cos", "atan", "atan2", "acos", "exp", "log", "pow", "div", "sqrt", "muladd"]     # enum rtc_math_fn
@@ -49,6 +50,15 @@ class SceneInfo(C.Structure):
 
 class TraceCounts(C.Structure):
     _fields_ = [("nodes", C.c_uint64), ("tris", C.c_uint64), ("instances", C.c_uint64), ("rays", C.c_uint64)]
+
+
+SCHEDULE_GROUP, SCHEDULE_ONE_TRI = 0, 1
+SCHEDULE_NAMES = ["group", "one_tri"]
+
+
+class TraceSchedule(C.Structure):
+    _fields_ = [("schedule", C.c_int), ("decided", C.c_int), ("measured", C.c_int), ("pathsPerBatch", C.c_uint64),
+                ("groupMs", C.c_float * 2), ("oneTriMs", C.c_float)]
 
 
 class PassStats(C.Structure):
@@ -122,6 +132,8 @@ def lib():
         L.rtc_probe_gather.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_double)]
         L.rtc_probe_pipes.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
         L.rtc_probe_math.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.rtc_trace_schedule_get.argtypes = [C.c_void_p, C.POINTER(TraceSchedule)]
+        L.rtc_trace_schedule_set.argtypes = [C.c_void_p, C.c_int]
         L.rtc_host_gas_build.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
         L.rtc_host_ias_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
         L.rtc_host_accel_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p]
@@ -335,6 +347,18 @@ class Context:
             gas[g] = (gn, gt[:nt.value])
         return {"tlas_nodes": nodes, "tlas_leaves": leaves[:info.numTlasLeaves], "world_to_object": w2o,
                 "instance_gas": inst_gas[:info.numInstances], "gas": gas}
+
+    def trace_schedule(self):
+        """Which schedule of the triangle tests the next launch uses and how it was chosen (rtc_trace_schedule_get): dict with
+        schedule ("group" | "one_tri"), decided, measured, paths_per_batch, group_ms [first, second], one_tri_ms."""
+        t = TraceSchedule()
+        _check(self.L.rtc_trace_schedule_get(self.h, C.byref(t)))
+        return {"schedule": SCHEDULE_NAMES[t.schedule], "decided": bool(t.decided), "measured": bool(t.measured), "paths_per_batch": int(t.pathsPerBatch),
+                "group_ms": [float(t.groupMs[0]), float(t.groupMs[1])], "one_tri_ms": float(t.oneTriMs)}
+
+    def set_trace_schedule(self, schedule):
+        """schedule: "group", "one_tri", or "auto" (measure again)."""
+        _check(self.L.rtc_trace_schedule_set(self.h, {"group": 0, "one_tri": 1, "auto": -1}[schedule]))
 
     def launch_pass_stats(self):
         """(extend, connect): {phase: (passes, slots processed, mean lanes per pass)} of the ray pool during count_work launches."""

@@ -257,12 +257,12 @@ k_extend_primary_packet(const SceneDesc sc, const ExtendPrimary policy, uint32_t
   trace_packets(sc, n, cursor, policy, stacks + (threadIdx.x >> 5) * RTC_PACKET_STACK);
 }
 
-template <bool COUNT>
+template <bool COUNT, bool ONETRI = false>
 __global__ void __launch_bounds__(kPrimaryBlock, RTC_TRACE_MIN_BLOCKS)
 k_extend_primary(const SceneDesc sc, const ExtendPrimary policy, uint32_t n, uint32_t* __restrict__ cursor, unsigned long long* __restrict__ counts)
 {
   __shared__ uint2 smem[RTC_SM_STACK * kPrimaryBlock + (RTC_SM_RAY_WORDS * kPrimaryBlock + 1) / 2];
-  trace_stream<false, COUNT, kPrimaryBlock, false>(sc, n, cursor, policy, smem, counts);
+  trace_stream<false, COUNT, kPrimaryBlock, false, ONETRI>(sc, n, cursor, policy, smem, counts);
 }
 
 __device__ __forceinline__ float3 xf_vector(const float4 r0, const float4 r1, const float4 r2, float3 v)
@@ -1198,6 +1198,83 @@ void release_cutout_graph(rtc_context* ctx)
   ctx->cutoutGraph = nullptr;
 }
 
+// ---- schedule tuner (rtc_internal.h ScheduleTuner) ---------------------------------------------------------------------------
+// Nothing in here may fail a launch: on any CUDA error the tuner retires with the schedule rounds 1 and 2 measured.
+namespace {
+
+constexpr uint64_t kTuneMinPaths = 1ull << 20;     // smaller batches are launch- and tail-bound: nothing to learn from timing them
+constexpr float    kTuneMargin = 0.97f;            // schedule 1 must beat the faster schedule-0 batch by 3 %
+
+void tuner_give_up(rtc_context* ctx)
+{
+  cudaGetLastError();
+  ctx->tuner.state = ScheduleTuner::DONE;
+  ctx->traceSchedule = RTC_SCHEDULE_GROUP;
+}
+
+// Called before the launches of a batch.  Returns the timed slot the batch fills (0 group, 1 one triangle, 2 group again) or -1,
+// and sets ctx->traceSchedule for the batch.
+int tuner_begin(rtc_context* ctx, uint64_t paths, bool eligible)
+{
+  ScheduleTuner& t = ctx->tuner;
+  if (t.state == ScheduleTuner::DONE) return -1;
+  if (t.state == ScheduleTuner::PENDING) { tuner_finish(ctx); return -1; }
+  ctx->traceSchedule = RTC_SCHEDULE_GROUP;
+  if (!eligible || paths < kTuneMinPaths) return -1;
+  if (t.state == ScheduleTuner::WARMUP)
+  {
+    // the first batch pays for allocations, lazily loaded kernels and the clock ramp: not timed
+    for (int k = 0; k < 6; ++k) if (!t.ev[k] && cudaEventCreate(&t.ev[k]) != cudaSuccess) { tuner_give_up(ctx); return -1; }
+    cudaFuncAttributes attr;
+    cudaFuncGetAttributes(&attr, k_extend_primary<false, true>);
+    preload_one_tri_trace_kernels();
+    cudaGetLastError();
+    t.state = ScheduleTuner::TIME_GROUP_A;
+    return -1;
+  }
+  if (t.state != ScheduleTuner::TIME_GROUP_A && paths != t.paths)
+  {
+    if (++t.restarts > 8) { t.state = ScheduleTuner::DONE; return -1; }
+    t.state = ScheduleTuner::TIME_GROUP_A;
+  }
+  const int slot = t.state - ScheduleTuner::TIME_GROUP_A;      // 0, 1, 2
+  if (slot == 0) t.paths = paths;
+  ctx->traceSchedule = (slot == 1) ? RTC_SCHEDULE_ONE_TRI : RTC_SCHEDULE_GROUP;
+  if (cudaEventRecord(t.ev[2 * slot], ctx->stream) != cudaSuccess) { tuner_give_up(ctx); return -1; }
+  return slot;
+}
+
+// Called behind the launches of a batch tuner_begin gave a slot.
+void tuner_end(rtc_context* ctx, int slot)
+{
+  if (slot < 0) return;
+  ScheduleTuner& t = ctx->tuner;
+  ctx->traceSchedule = RTC_SCHEDULE_GROUP;
+  if (t.state == ScheduleTuner::DONE) return;
+  if (cudaEventRecord(t.ev[2 * slot + 1], ctx->stream) != cudaSuccess) { tuner_give_up(ctx); return; }
+  t.state = ScheduleTuner::TIME_GROUP_A + slot + 1;            // ... TIME_GROUP_B -> PENDING
+}
+
+} // namespace
+
+// Decides once the three timed batches have finished (waits for the last one).
+void tuner_finish(rtc_context* ctx)
+{
+  ScheduleTuner& t = ctx->tuner;
+  if (t.state != ScheduleTuner::PENDING) return;
+  bool ok = cudaEventSynchronize(t.ev[5]) == cudaSuccess;
+  for (int slot = 0; ok && slot < 3; ++slot) ok = cudaEventElapsedTime(&t.ms[slot], t.ev[2 * slot], t.ev[2 * slot + 1]) == cudaSuccess;
+  if (!ok) { tuner_give_up(ctx); return; }
+  const float group = t.ms[0] < t.ms[2] ? t.ms[0] : t.ms[2];
+  ctx->traceSchedule = (t.ms[1] > 0.0f && t.ms[1] < kTuneMargin * group) ? RTC_SCHEDULE_ONE_TRI : RTC_SCHEDULE_GROUP;
+  t.state = ScheduleTuner::DONE;
+}
+
+void tuner_release(rtc_context* ctx)
+{
+  for (int k = 0; k < 6; ++k) if (ctx->tuner.ev[k]) { cudaEventDestroy(ctx->tuner.ev[k]); ctx->tuner.ev[k] = nullptr; }
+}
+
 int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uint32_t h, int raygen, int miss, int iterFirst, int iterCount,
                      int accumFirst, bool countWork)
 {
@@ -1238,6 +1315,8 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
     WfArgs a;
     a.wf = ctx->wf; a.sys = sys; a.launchWidth = w; a.launchHeight = h; a.raygen = raygen; a.miss = miss;
     a.iterFirst = iterFirst + done; a.iterCount = batch; a.accumFirst = accumFirst + done; a.numPaths = (uint32_t)(pixels * (uint64_t)batch);
+    // schedule tuner: the lane-owned driver on scenes without cutout materials, timed launches only
+    const int tuneSlot = tuner_begin(ctx, a.numPaths, !countWork && !cutout && ctx->traceDriver == RTC_DRIVER_LANE && !ctx->primaryPackets);
     uint32_t* cnt = ctx->wf.counters;
     RTC_CUDA(cudaMemsetAsync(cnt, 0, 4 * kNumCounters, ctx->stream));
     // Fused primary path (scenes without material textures): no generate pass.  The depth-0 extend computes its rays from the
@@ -1277,6 +1356,7 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
         {
           const int gridTrace = ctx->numSMs * RTC_TRACE_MIN_BLOCKS;
           if (countWork) k_extend_primary<true><<<gridTrace, kPrimaryBlock, 0, ctx->stream>>>(scene->desc, policy, a.numPaths, cnt + 128, ctx->d_launchCounts);
+          else if (ctx->traceSchedule == RTC_SCHEDULE_ONE_TRI) k_extend_primary<false, true><<<gridTrace, kPrimaryBlock, 0, ctx->stream>>>(scene->desc, policy, a.numPaths, cnt + 128, nullptr);
           else           k_extend_primary<false><<<gridTrace, kPrimaryBlock, 0, ctx->stream>>>(scene->desc, policy, a.numPaths, cnt + 128, nullptr);
         }
         ctx->kernelLaunches++;
@@ -1304,6 +1384,7 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
     k_stats<<<1, 32, 0, ctx->stream>>>(cnt, maxDepth, a.numPaths, ctx->d_stats);
     ctx->kernelLaunches += 2;
     RTC_CUDA(cudaGetLastError());
+    tuner_end(ctx, tuneSlot);
   }
   return 0;
 }

@@ -100,6 +100,12 @@ static int context_init(rtc_context* ctx, int deviceOrdinal)
   ctx->traceDriver = RTC_DRIVER_LANE;
   if (const char* e = getenv("RTC_PRIMARY_PACKETS")) ctx->primaryPackets = atoi(e) != 0;
   if (const char* e = getenv("RTC_TRACE_DRIVER")) ctx->traceDriver = (e[0] == 'p' || e[0] == '1') ? RTC_DRIVER_POOL : RTC_DRIVER_LANE;
+  // schedule of the lane-owned driver's triangle tests: measured per context (auto) unless RTC_TRACE_SCHEDULE=group|onetri fixes it
+  if (const char* e = getenv("RTC_TRACE_SCHEDULE"))
+  {
+    if (e[0] == 'g' || e[0] == '0') { ctx->traceSchedule = RTC_SCHEDULE_GROUP; ctx->tuner.state = ScheduleTuner::DONE; ctx->tuner.fixedByEnv = true; }
+    else if (e[0] == 'o' || e[0] == '1') { ctx->traceSchedule = RTC_SCHEDULE_ONE_TRI; ctx->tuner.state = ScheduleTuner::DONE; ctx->tuner.fixedByEnv = true; }
+  }
   RTC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   {
     // keep freed build scratch in the device's default memory pool instead of returning it to the OS at every synchronise
@@ -150,6 +156,7 @@ int rtc_context_destroy(rtc_context* ctx)
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   release_cutout_graph(ctx);
+  tuner_release(ctx);
   for (SceneRecord* s : ctx->scenes) free_scene(s);
   for (GasRecord& g : ctx->gas) { cudaFree(g.d_nodes); cudaFree(g.d_tris); }
   if (ctx->wf.base) cudaFree(ctx->wf.base);
@@ -583,6 +590,37 @@ int rtc_launch_ex(rtc_context* ctx, const rt_SystemData* sys, uint32_t launchWid
   if (accumulationFirst < 0) RTC_FAIL("accumulationFirst < 0");
   RTC_CUDA(cudaSetDevice(ctx->device));
   return launch_wavefront(ctx, *sys, launchWidth, launchHeight, raygen, miss, iterationFirst, iterationCount, accumulationFirst, countWork != 0);
+}
+
+int rtc_trace_schedule_get(rtc_context* ctx, rtc_trace_schedule* out)
+{
+  if (!out) RTC_FAIL("out is null");
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  tuner_finish(ctx);        // a pending decision is taken now (waits for the last timed batch)
+  const ScheduleTuner& t = ctx->tuner;
+  out->schedule = ctx->traceSchedule;
+  out->decided = t.state == ScheduleTuner::DONE ? 1 : 0;
+  out->measured = (t.state == ScheduleTuner::DONE && t.ms[1] > 0.0f) ? 1 : 0;
+  out->pathsPerBatch = t.paths;
+  out->groupMs[0] = t.ms[0]; out->oneTriMs = t.ms[1]; out->groupMs[1] = t.ms[2];
+  return 0;
+}
+
+int rtc_trace_schedule_set(rtc_context* ctx, int schedule)
+{
+  RTC_CUDA(cudaSetDevice(ctx->device));
+  if (schedule == RTC_SCHEDULE_GROUP || schedule == RTC_SCHEDULE_ONE_TRI)
+  {
+    ctx->traceSchedule = schedule;
+    ctx->tuner.state = ScheduleTuner::DONE;
+    return 0;
+  }
+  if (schedule != -1) RTC_FAIL("schedule must be RTC_SCHEDULE_GROUP, RTC_SCHEDULE_ONE_TRI or -1 (measure again)");
+  ctx->traceSchedule = RTC_SCHEDULE_GROUP;
+  ctx->tuner.state = ScheduleTuner::WARMUP;
+  ctx->tuner.restarts = 0; ctx->tuner.paths = 0;
+  ctx->tuner.ms[0] = ctx->tuner.ms[1] = ctx->tuner.ms[2] = 0.0f;
+  return 0;
 }
 
 int rtc_launch_counts_get(rtc_context* ctx, rtc_trace_counts out[2])

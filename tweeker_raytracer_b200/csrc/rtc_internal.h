@@ -134,6 +134,24 @@ struct WavefrontBuffers
   void* cutBase = nullptr;
 };
 
+// RTC_SCHEDULE_GROUP / RTC_SCHEDULE_ONE_TRI (rtc_core.h): how the lane-owned traversal driver times its triangle tests
+// (trace.cuh Traversal::step); hits and work counters do not depend on it.
+// Run-time choice between the two schedules.  The second one was written when no GPU was left to measure it on, so the library
+// measures it itself: of the first batches of a context that are large enough to time (>= 1 Mi paths), one is a warm-up and the
+// next three run schedule 0, schedule 1 and schedule 0 again, each between two events; schedule 1 serves every later launch only
+// if it beats the FASTER of the two schedule-0 batches by 3 %.  Results are bit-identical under both, so the choice never shows
+// in a frame.  RTC_TRACE_SCHEDULE=group|onetri fixes it (auto is the default); rtc_trace_schedule_get reports what happened.
+struct ScheduleTuner
+{
+  enum State { WARMUP = 0, TIME_GROUP_A = 1, TIME_ONE_TRI = 2, TIME_GROUP_B = 3, PENDING = 4, DONE = 5 };
+  int         state = WARMUP;
+  cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   // begin / end of the three timed batches
+  uint64_t    paths = 0;            // size of the timed batches (all three must be the same)
+  int         restarts = 0;         // a batch of another size restarts the measurement; bounded
+  float       ms[3] = { 0.0f, 0.0f, 0.0f };   // group, one triangle, group again
+  bool        fixedByEnv = false;
+};
+
 struct rtc_context
 {
   int device = 0;
@@ -163,6 +181,8 @@ struct rtc_context
   uint32_t* d_cursor = nullptr;                   // ray cursor of the query kernels (rtc_trace_*)
   bool   primaryPackets = false;                  // primary rays by packet traversal (trace_packet.cuh): measured slower, RTC_PRIMARY_PACKETS=1 turns it on
   int    traceDriver = 0;                         // RTC_DRIVER_LANE or RTC_DRIVER_POOL: which traversal driver the launches use
+  int    traceSchedule = 0;                       // RTC_SCHEDULE_*: how the lane-owned driver times its triangle tests (what the NEXT launch uses)
+  ScheduleTuner tuner;                            // picks traceSchedule by timing one batch with each (kernels_shade.cu, "schedule tuner")
   void*  cutoutGraph = nullptr;                   // CutoutGraph (kernels_shade.cu): the device-side loop of the ordered any-hit rounds
   void*  d_poolScratch = nullptr;                 // global part of the ray pool's traversal stacks (trace_pool.cuh), grown on demand
   size_t poolScratchBytes = 0;
@@ -213,4 +233,8 @@ int ensure_wavefront(rtc_context* ctx, uint64_t capacity, bool* outOfMemory = nu
 int ensure_pool_scratch(rtc_context* ctx, size_t warps, uint2** out);
 void release_cutout_graph(rtc_context* ctx);
 int read_stack_overflows(rtc_context* ctx, uint64_t* out);
+// schedule tuner (kernels_shade.cu); tuner_finish blocks for the last timed batch when a decision is pending
+void tuner_finish(rtc_context* ctx);
+void tuner_release(rtc_context* ctx);
+void preload_one_tri_trace_kernels();      // kernels_trace.cu: loads the schedule-1 kernels before they are timed (lazy module loading)
 int read_stack_overflows_primary(rtc_context* ctx, uint64_t* out);   // the counter of the primary-ray extend kernel (kernels_shade.cu)
