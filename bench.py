@@ -22,8 +22,8 @@ Path-tracing configs (c1, c2, c4, c5).  A "step" renders `--spp-per-step` iterat
   cpu_baseline  oracle/_ref (the reference's shader sources host-compiled, kind "reference"; traversal served by the oracle's
             intersector) on a bounded sample of the same workload, one process per host core, plus one single-threaded run.
 
-  trace_schedule  which schedule of the triangle tests the timed steps ran with and the three warm-up batch times the library chose
-            it from (include/rtc_core.h rtc_trace_schedule_get; needs >= 3 warm-up steps to be settled before the timed ones).
+  trace_schedule  which schedule of the triangle tests the timed steps ran with and the four warm-up batch times the library chose
+            it from (include/rtc_core.h rtc_trace_schedule_get; needs >= 4 warm-up steps to be settled before the timed ones).
 
 Ray configs (c3-*).  A step traces one set of rays against a synthetic triangle soup; value = Mrays/s.
 """
@@ -63,7 +63,7 @@ def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=5)      # >= 4: the schedule tuner of the traversal kernels settles during the warm-up steps
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c2")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
@@ -380,7 +380,7 @@ def ncu_measure(args, schedule="group"):
            "--spp-per-step", str(args.spp_per_step), "--instances", str(args.instances)]
     try:
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0"),
-                                      RTC_TRACE_SCHEDULE="onetri" if schedule == "one_tri" else "group"))
+                                      RTC_TRACE_SCHEDULE={"one_tri": "onetri", "two_tri": "twotri"}.get(schedule, "group")))
     except Exception as e:
         return None, "ncu child failed: %r" % (e,)
     if out.returncode != 0 or not os.path.exists(log):
@@ -533,7 +533,7 @@ def main():
     ctx.profile_enable(False)
     stats = ctx.stats()
     # which schedule of the triangle tests the timed steps ran with (the library times one warm-up batch with each and keeps the
-    # faster: include/rtc_core.h rtc_trace_schedule_get); with fewer than 3 warm-up steps the measurement reaches into the timed steps
+    # faster: include/rtc_core.h rtc_trace_schedule_get); with fewer than 4 warm-up steps the measurement reaches into the timed steps
     try:
         schedule = ctx.trace_schedule()
     except Exception as e:          # reporting only

@@ -209,24 +209,27 @@ int rtc_launch(rtc_context* ctx, const rt_SystemData* sys, uint32_t launchWidth,
 int rtc_launch_ex(rtc_context* ctx, const rt_SystemData* sys, uint32_t launchWidth, uint32_t launchHeight,
                   int raygen, int miss, int iterationFirst, int iterationCount, int accumulationFirst, int countWork);
 /*
- * Schedule of the triangle tests in the traversal kernels (csrc/trace.cuh Traversal::step).  Two are compiled; hits, frames and
- * work counters are bit-identical under both, only the timing inside a warp differs:
+ * Schedule of the triangle tests in the traversal kernels (csrc/trace.cuh Traversal::step).  Three are compiled; hits, frames and
+ * work counters are bit-identical under all of them, only the timing inside a warp differs:
  *   RTC_SCHEDULE_GROUP    a step tests every triangle of the leaves its node visit found (what rounds 1 and 2 measured);
- *   RTC_SCHEDULE_ONE_TRI  a step tests at most one triangle, and a lane with more pending skips its node visit.
- * By default every context MEASURES: of its first rtc_launch batches of >= 1 Mi paths one is a warm-up and the next three run
- * group / one triangle / group between events; one-triangle serves the later launches only if it beats the faster group
- * batch by 3 %.  The environment variable RTC_TRACE_SCHEDULE=group|onetri, or rtc_trace_schedule_set, fixes the schedule;
- * rtc_trace_schedule_set(ctx, -1) measures again.  rtc_trace_schedule_get reports the schedule in use and the three batch
- * times (it takes a pending decision first, which waits for the last timed batch).
+ *   RTC_SCHEDULE_ONE_TRI  a step tests at most one triangle, and a lane with more pending skips its node visit;
+ *   RTC_SCHEDULE_TWO_TRI  the same with at most two (one leaf of the host builder).
+ * By default every context MEASURES: of its first rtc_launch batches of >= 1 Mi paths one is a warm-up and the next four run
+ * group / one triangle / two triangles / group between events; a capped schedule serves the later launches only if it beats
+ * the faster group batch by 3 % (the faster capped one if both do).  The environment variable
+ * RTC_TRACE_SCHEDULE=group|onetri|twotri, or rtc_trace_schedule_set, fixes the schedule; rtc_trace_schedule_set(ctx, -1) measures
+ * again.  rtc_trace_schedule_get reports the schedule in use and the four batch times (it takes a pending decision first,
+ * which waits for the last timed batch).
  */
-enum { RTC_SCHEDULE_GROUP = 0, RTC_SCHEDULE_ONE_TRI = 1 };
+enum { RTC_SCHEDULE_GROUP = 0, RTC_SCHEDULE_ONE_TRI = 1, RTC_SCHEDULE_TWO_TRI = 2 };
 typedef struct {
   int      schedule;         /* RTC_SCHEDULE_* the next launch uses */
   int      decided;          /* 0 while the measurement is still running */
-  int      measured;         /* 1 when the decision came from the three timed batches (not from the environment / _set) */
+  int      measured;         /* 1 when the decision came from the timed batches (not from the environment / _set) */
   uint64_t pathsPerBatch;    /* size of the timed batches */
   float    groupMs[2];       /* device time of the first and the second RTC_SCHEDULE_GROUP batch */
   float    oneTriMs;         /* device time of the RTC_SCHEDULE_ONE_TRI batch */
+  float    twoTriMs;         /* device time of the RTC_SCHEDULE_TWO_TRI batch */
 } rtc_trace_schedule;
 int rtc_trace_schedule_get(rtc_context* ctx, rtc_trace_schedule* out);
 int rtc_trace_schedule_set(rtc_context* ctx, int schedule);

@@ -52,13 +52,13 @@ class TraceCounts(C.Structure):
     _fields_ = [("nodes", C.c_uint64), ("tris", C.c_uint64), ("instances", C.c_uint64), ("rays", C.c_uint64)]
 
 
-SCHEDULE_GROUP, SCHEDULE_ONE_TRI = 0, 1
-SCHEDULE_NAMES = ["group", "one_tri"]
+SCHEDULE_GROUP, SCHEDULE_ONE_TRI, SCHEDULE_TWO_TRI = 0, 1, 2
+SCHEDULE_NAMES = ["group", "one_tri", "two_tri"]
 
 
 class TraceSchedule(C.Structure):
     _fields_ = [("schedule", C.c_int), ("decided", C.c_int), ("measured", C.c_int), ("pathsPerBatch", C.c_uint64),
-                ("groupMs", C.c_float * 2), ("oneTriMs", C.c_float)]
+                ("groupMs", C.c_float * 2), ("oneTriMs", C.c_float), ("twoTriMs", C.c_float)]
 
 
 class PassStats(C.Structure):
@@ -350,15 +350,15 @@ class Context:
 
     def trace_schedule(self):
         """Which schedule of the triangle tests the next launch uses and how it was chosen (rtc_trace_schedule_get): dict with
-        schedule ("group" | "one_tri"), decided, measured, paths_per_batch, group_ms [first, second], one_tri_ms."""
+        schedule ("group" | "one_tri" | "two_tri"), decided, measured, paths_per_batch, group_ms [first, second], one_tri_ms, two_tri_ms."""
         t = TraceSchedule()
         _check(self.L.rtc_trace_schedule_get(self.h, C.byref(t)))
         return {"schedule": SCHEDULE_NAMES[t.schedule], "decided": bool(t.decided), "measured": bool(t.measured), "paths_per_batch": int(t.pathsPerBatch),
-                "group_ms": [float(t.groupMs[0]), float(t.groupMs[1])], "one_tri_ms": float(t.oneTriMs)}
+                "group_ms": [float(t.groupMs[0]), float(t.groupMs[1])], "one_tri_ms": float(t.oneTriMs), "two_tri_ms": float(t.twoTriMs)}
 
     def set_trace_schedule(self, schedule):
-        """schedule: "group", "one_tri", or "auto" (measure again)."""
-        _check(self.L.rtc_trace_schedule_set(self.h, {"group": 0, "one_tri": 1, "auto": -1}[schedule]))
+        """schedule: "group", "one_tri", "two_tri", or "auto" (measure again)."""
+        _check(self.L.rtc_trace_schedule_set(self.h, {"group": 0, "one_tri": 1, "two_tri": 2, "auto": -1}[schedule]))
 
     def launch_pass_stats(self):
         """(extend, connect): {phase: (passes, slots processed, mean lanes per pass)} of the ray pool during count_work launches."""

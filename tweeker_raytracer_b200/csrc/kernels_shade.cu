@@ -257,12 +257,12 @@ k_extend_primary_packet(const SceneDesc sc, const ExtendPrimary policy, uint32_t
   trace_packets(sc, n, cursor, policy, stacks + (threadIdx.x >> 5) * RTC_PACKET_STACK);
 }
 
-template <bool COUNT, bool ONETRI = false>
+template <bool COUNT, int TRICAP = 0>
 __global__ void __launch_bounds__(kPrimaryBlock, RTC_TRACE_MIN_BLOCKS)
 k_extend_primary(const SceneDesc sc, const ExtendPrimary policy, uint32_t n, uint32_t* __restrict__ cursor, unsigned long long* __restrict__ counts)
 {
   __shared__ uint2 smem[RTC_SM_STACK * kPrimaryBlock + (RTC_SM_RAY_WORDS * kPrimaryBlock + 1) / 2];
-  trace_stream<false, COUNT, kPrimaryBlock, false, ONETRI>(sc, n, cursor, policy, smem, counts);
+  trace_stream<false, COUNT, kPrimaryBlock, false, TRICAP>(sc, n, cursor, policy, smem, counts);
 }
 
 __device__ __forceinline__ float3 xf_vector(const float4 r0, const float4 r1, const float4 r2, float3 v)
@@ -1203,7 +1203,9 @@ void release_cutout_graph(rtc_context* ctx)
 namespace {
 
 constexpr uint64_t kTuneMinPaths = 1ull << 20;     // smaller batches are launch- and tail-bound: nothing to learn from timing them
-constexpr float    kTuneMargin = 0.97f;            // schedule 1 must beat the faster schedule-0 batch by 3 %
+constexpr float    kTuneMargin = 0.97f;            // a capped schedule must beat the faster group batch by 3 %
+// the schedule each timed batch runs: group first and last, so that a drift of the clocks cannot favour a capped schedule
+constexpr int      kTuneSchedule[ScheduleTuner::kSlots] = { RTC_SCHEDULE_GROUP, RTC_SCHEDULE_ONE_TRI, RTC_SCHEDULE_TWO_TRI, RTC_SCHEDULE_GROUP };
 
 void tuner_give_up(rtc_context* ctx)
 {
@@ -1212,8 +1214,8 @@ void tuner_give_up(rtc_context* ctx)
   ctx->traceSchedule = RTC_SCHEDULE_GROUP;
 }
 
-// Called before the launches of a batch.  Returns the timed slot the batch fills (0 group, 1 one triangle, 2 group again) or -1,
-// and sets ctx->traceSchedule for the batch.
+// Called before the launches of a batch.  Returns the timed slot the batch fills (0 .. kSlots - 1) or -1, and sets
+// ctx->traceSchedule for the batch.
 int tuner_begin(rtc_context* ctx, uint64_t paths, bool eligible)
 {
   ScheduleTuner& t = ctx->tuner;
@@ -1224,24 +1226,25 @@ int tuner_begin(rtc_context* ctx, uint64_t paths, bool eligible)
   if (t.state == ScheduleTuner::WARMUP)
   {
     // the first batch pays for allocations, lazily loaded kernels and the clock ramp: not timed
-    for (int k = 0; k < 6; ++k) if (!t.ev[k] && cudaEventCreate(&t.ev[k]) != cudaSuccess) { tuner_give_up(ctx); return -1; }
+    for (int k = 0; k < 2 * ScheduleTuner::kSlots; ++k) if (!t.ev[k] && cudaEventCreate(&t.ev[k]) != cudaSuccess) { tuner_give_up(ctx); return -1; }
     cudaFuncAttributes attr;
-    cudaFuncGetAttributes(&attr, k_extend_primary<false, true>);
-    preload_one_tri_trace_kernels();
+    cudaFuncGetAttributes(&attr, k_extend_primary<false, 1>);
+    cudaFuncGetAttributes(&attr, k_extend_primary<false, 2>);
+    preload_capped_trace_kernels();
     cudaGetLastError();
-    t.state = ScheduleTuner::TIME_GROUP_A;
+    t.state = ScheduleTuner::TIMING;
+    t.slot = 0;
     return -1;
   }
-  if (t.state != ScheduleTuner::TIME_GROUP_A && paths != t.paths)
+  if (t.slot > 0 && paths != t.paths)
   {
     if (++t.restarts > 8) { t.state = ScheduleTuner::DONE; return -1; }
-    t.state = ScheduleTuner::TIME_GROUP_A;
+    t.slot = 0;
   }
-  const int slot = t.state - ScheduleTuner::TIME_GROUP_A;      // 0, 1, 2
-  if (slot == 0) t.paths = paths;
-  ctx->traceSchedule = (slot == 1) ? RTC_SCHEDULE_ONE_TRI : RTC_SCHEDULE_GROUP;
-  if (cudaEventRecord(t.ev[2 * slot], ctx->stream) != cudaSuccess) { tuner_give_up(ctx); return -1; }
-  return slot;
+  if (t.slot == 0) t.paths = paths;
+  ctx->traceSchedule = kTuneSchedule[t.slot];
+  if (cudaEventRecord(t.ev[2 * t.slot], ctx->stream) != cudaSuccess) { tuner_give_up(ctx); return -1; }
+  return t.slot;
 }
 
 // Called behind the launches of a batch tuner_begin gave a slot.
@@ -1250,29 +1253,32 @@ void tuner_end(rtc_context* ctx, int slot)
   if (slot < 0) return;
   ScheduleTuner& t = ctx->tuner;
   ctx->traceSchedule = RTC_SCHEDULE_GROUP;
-  if (t.state == ScheduleTuner::DONE) return;
+  if (t.state != ScheduleTuner::TIMING) return;
   if (cudaEventRecord(t.ev[2 * slot + 1], ctx->stream) != cudaSuccess) { tuner_give_up(ctx); return; }
-  t.state = ScheduleTuner::TIME_GROUP_A + slot + 1;            // ... TIME_GROUP_B -> PENDING
+  t.slot = slot + 1;
+  if (t.slot == ScheduleTuner::kSlots) t.state = ScheduleTuner::PENDING;
 }
 
 } // namespace
 
-// Decides once the three timed batches have finished (waits for the last one).
+// Decides once the timed batches have finished (waits for the last one).
 void tuner_finish(rtc_context* ctx)
 {
   ScheduleTuner& t = ctx->tuner;
   if (t.state != ScheduleTuner::PENDING) return;
-  bool ok = cudaEventSynchronize(t.ev[5]) == cudaSuccess;
-  for (int slot = 0; ok && slot < 3; ++slot) ok = cudaEventElapsedTime(&t.ms[slot], t.ev[2 * slot], t.ev[2 * slot + 1]) == cudaSuccess;
+  bool ok = cudaEventSynchronize(t.ev[2 * ScheduleTuner::kSlots - 1]) == cudaSuccess;
+  for (int slot = 0; ok && slot < ScheduleTuner::kSlots; ++slot) ok = cudaEventElapsedTime(&t.ms[slot], t.ev[2 * slot], t.ev[2 * slot + 1]) == cudaSuccess;
   if (!ok) { tuner_give_up(ctx); return; }
-  const float group = t.ms[0] < t.ms[2] ? t.ms[0] : t.ms[2];
-  ctx->traceSchedule = (t.ms[1] > 0.0f && t.ms[1] < kTuneMargin * group) ? RTC_SCHEDULE_ONE_TRI : RTC_SCHEDULE_GROUP;
+  const float group = t.ms[0] < t.ms[3] ? t.ms[0] : t.ms[3];
+  int best = RTC_SCHEDULE_GROUP; float bestMs = kTuneMargin * group;
+  for (int slot = 1; slot <= 2; ++slot) if (t.ms[slot] > 0.0f && t.ms[slot] < bestMs) { bestMs = t.ms[slot]; best = kTuneSchedule[slot]; }
+  ctx->traceSchedule = best;
   t.state = ScheduleTuner::DONE;
 }
 
 void tuner_release(rtc_context* ctx)
 {
-  for (int k = 0; k < 6; ++k) if (ctx->tuner.ev[k]) { cudaEventDestroy(ctx->tuner.ev[k]); ctx->tuner.ev[k] = nullptr; }
+  for (int k = 0; k < 2 * ScheduleTuner::kSlots; ++k) if (ctx->tuner.ev[k]) { cudaEventDestroy(ctx->tuner.ev[k]); ctx->tuner.ev[k] = nullptr; }
 }
 
 int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uint32_t h, int raygen, int miss, int iterFirst, int iterCount,
@@ -1356,7 +1362,8 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
         {
           const int gridTrace = ctx->numSMs * RTC_TRACE_MIN_BLOCKS;
           if (countWork) k_extend_primary<true><<<gridTrace, kPrimaryBlock, 0, ctx->stream>>>(scene->desc, policy, a.numPaths, cnt + 128, ctx->d_launchCounts);
-          else if (ctx->traceSchedule == RTC_SCHEDULE_ONE_TRI) k_extend_primary<false, true><<<gridTrace, kPrimaryBlock, 0, ctx->stream>>>(scene->desc, policy, a.numPaths, cnt + 128, nullptr);
+          else if (ctx->traceSchedule == RTC_SCHEDULE_ONE_TRI) k_extend_primary<false, 1><<<gridTrace, kPrimaryBlock, 0, ctx->stream>>>(scene->desc, policy, a.numPaths, cnt + 128, nullptr);
+          else if (ctx->traceSchedule == RTC_SCHEDULE_TWO_TRI) k_extend_primary<false, 2><<<gridTrace, kPrimaryBlock, 0, ctx->stream>>>(scene->desc, policy, a.numPaths, cnt + 128, nullptr);
           else           k_extend_primary<false><<<gridTrace, kPrimaryBlock, 0, ctx->stream>>>(scene->desc, policy, a.numPaths, cnt + 128, nullptr);
         }
         ctx->kernelLaunches++;

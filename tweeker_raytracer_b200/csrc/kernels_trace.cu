@@ -147,15 +147,15 @@ k_trace_pool(const SceneDesc sc, const Policy policy, uint32_t n, const uint32_t
   rtpool::trace_pool<ANY, COUNT, SKIP>(sc, count, cursor, policy, poolWords + warp * rtpool::warp_words(ANY, SKIP), overflow + warpGlobal * rtpool::kOverflowPerWarp, counts);
 }
 
-// ONETRI: the "one triangle per step" schedule of the traversal (trace.cuh Traversal::step); instantiated for the timed kernels only.
-template <bool ANY, bool COUNT, class Policy, bool SKIP = false, bool ONETRI = false>
+// TRICAP: the capped schedules of the triangle tests (trace.cuh Traversal::step); 1 and 2 are instantiated for the timed kernels only.
+template <bool ANY, bool COUNT, class Policy, bool SKIP = false, int TRICAP = 0>
 __global__ void __launch_bounds__(kTraceBlock, SKIP ? 4 : RTC_TRACE_MIN_BLOCKS)
 k_trace(const SceneDesc sc, const Policy policy, uint32_t n, const uint32_t* __restrict__ nPtr, uint32_t* __restrict__ cursor,
         unsigned long long* __restrict__ counts)
 {
   __shared__ uint2 smem[RTC_SM_STACK * kTraceBlock + (RTC_SM_RAY_WORDS * kTraceBlock + 1) / 2];     // stack columns, then the float columns (trace.cuh smRay)
   const uint32_t count = nPtr ? *nPtr : n;
-  trace_stream<ANY, COUNT, kTraceBlock, SKIP, ONETRI>(sc, count, cursor, policy, smem, counts);
+  trace_stream<ANY, COUNT, kTraceBlock, SKIP, TRICAP>(sc, count, cursor, policy, smem, counts);
 }
 
 template <bool ANY, bool COUNT, class Policy, bool SKIP>
@@ -174,7 +174,11 @@ int launch_k_trace(rtc_context* ctx, const SceneDesc* scene, const Policy& p, ui
   else if (!COUNT && !SKIP && ctx->traceSchedule == RTC_SCHEDULE_ONE_TRI)
   {
     // the counting kernels and the ordered any-hit re-traces keep the one schedule: their per-ray results do not depend on it
-    k_trace<ANY, false, Policy, false, true><<<ctx->numSMs * RTC_TRACE_MIN_BLOCKS, kTraceBlock, 0, ctx->stream>>>(*scene, p, n, nPtr, cursor, counts);
+    k_trace<ANY, false, Policy, false, 1><<<ctx->numSMs * RTC_TRACE_MIN_BLOCKS, kTraceBlock, 0, ctx->stream>>>(*scene, p, n, nPtr, cursor, counts);
+  }
+  else if (!COUNT && !SKIP && ctx->traceSchedule == RTC_SCHEDULE_TWO_TRI)
+  {
+    k_trace<ANY, false, Policy, false, 2><<<ctx->numSMs * RTC_TRACE_MIN_BLOCKS, kTraceBlock, 0, ctx->stream>>>(*scene, p, n, nPtr, cursor, counts);
   }
   else
   {
@@ -202,11 +206,13 @@ int ensure_pool_scratch(rtc_context* ctx, size_t warps, uint2** out)
 }
 
 // With lazy module loading a kernel is loaded at its first launch; the schedule tuner must not time that.
-void preload_one_tri_trace_kernels()
+void preload_capped_trace_kernels()
 {
   cudaFuncAttributes attr;
-  cudaFuncGetAttributes(&attr, k_trace<false, false, ExtendPaths, false, true>);
-  cudaFuncGetAttributes(&attr, k_trace<true, false, ConnectPaths, false, true>);
+  cudaFuncGetAttributes(&attr, k_trace<false, false, ExtendPaths, false, 1>);
+  cudaFuncGetAttributes(&attr, k_trace<true, false, ConnectPaths, false, 1>);
+  cudaFuncGetAttributes(&attr, k_trace<false, false, ExtendPaths, false, 2>);
+  cudaFuncGetAttributes(&attr, k_trace<true, false, ConnectPaths, false, 2>);
   cudaGetLastError();
 }
 

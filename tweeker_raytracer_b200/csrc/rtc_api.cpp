@@ -100,11 +100,12 @@ static int context_init(rtc_context* ctx, int deviceOrdinal)
   ctx->traceDriver = RTC_DRIVER_LANE;
   if (const char* e = getenv("RTC_PRIMARY_PACKETS")) ctx->primaryPackets = atoi(e) != 0;
   if (const char* e = getenv("RTC_TRACE_DRIVER")) ctx->traceDriver = (e[0] == 'p' || e[0] == '1') ? RTC_DRIVER_POOL : RTC_DRIVER_LANE;
-  // schedule of the lane-owned driver's triangle tests: measured per context (auto) unless RTC_TRACE_SCHEDULE=group|onetri fixes it
+  // schedule of the lane-owned driver's triangle tests: measured per context (auto) unless RTC_TRACE_SCHEDULE=group|onetri|twotri fixes it
   if (const char* e = getenv("RTC_TRACE_SCHEDULE"))
   {
     if (e[0] == 'g' || e[0] == '0') { ctx->traceSchedule = RTC_SCHEDULE_GROUP; ctx->tuner.state = ScheduleTuner::DONE; ctx->tuner.fixedByEnv = true; }
     else if (e[0] == 'o' || e[0] == '1') { ctx->traceSchedule = RTC_SCHEDULE_ONE_TRI; ctx->tuner.state = ScheduleTuner::DONE; ctx->tuner.fixedByEnv = true; }
+    else if (e[0] == 't' || e[0] == '2') { ctx->traceSchedule = RTC_SCHEDULE_TWO_TRI; ctx->tuner.state = ScheduleTuner::DONE; ctx->tuner.fixedByEnv = true; }
   }
   RTC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   {
@@ -602,24 +603,24 @@ int rtc_trace_schedule_get(rtc_context* ctx, rtc_trace_schedule* out)
   out->decided = t.state == ScheduleTuner::DONE ? 1 : 0;
   out->measured = (t.state == ScheduleTuner::DONE && t.ms[1] > 0.0f) ? 1 : 0;
   out->pathsPerBatch = t.paths;
-  out->groupMs[0] = t.ms[0]; out->oneTriMs = t.ms[1]; out->groupMs[1] = t.ms[2];
+  out->groupMs[0] = t.ms[0]; out->oneTriMs = t.ms[1]; out->twoTriMs = t.ms[2]; out->groupMs[1] = t.ms[3];
   return 0;
 }
 
 int rtc_trace_schedule_set(rtc_context* ctx, int schedule)
 {
   RTC_CUDA(cudaSetDevice(ctx->device));
-  if (schedule == RTC_SCHEDULE_GROUP || schedule == RTC_SCHEDULE_ONE_TRI)
+  if (schedule == RTC_SCHEDULE_GROUP || schedule == RTC_SCHEDULE_ONE_TRI || schedule == RTC_SCHEDULE_TWO_TRI)
   {
     ctx->traceSchedule = schedule;
     ctx->tuner.state = ScheduleTuner::DONE;
     return 0;
   }
-  if (schedule != -1) RTC_FAIL("schedule must be RTC_SCHEDULE_GROUP, RTC_SCHEDULE_ONE_TRI or -1 (measure again)");
+  if (schedule != -1) RTC_FAIL("schedule must be one of RTC_SCHEDULE_* or -1 (measure again)");
   ctx->traceSchedule = RTC_SCHEDULE_GROUP;
   ctx->tuner.state = ScheduleTuner::WARMUP;
-  ctx->tuner.restarts = 0; ctx->tuner.paths = 0;
-  ctx->tuner.ms[0] = ctx->tuner.ms[1] = ctx->tuner.ms[2] = 0.0f;
+  ctx->tuner.slot = 0; ctx->tuner.restarts = 0; ctx->tuner.paths = 0;
+  for (float& ms : ctx->tuner.ms) ms = 0.0f;
   return 0;
 }
 

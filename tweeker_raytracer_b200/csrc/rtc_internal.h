@@ -134,21 +134,24 @@ struct WavefrontBuffers
   void* cutBase = nullptr;
 };
 
-// RTC_SCHEDULE_GROUP / RTC_SCHEDULE_ONE_TRI (rtc_core.h): how the lane-owned traversal driver times its triangle tests
+// RTC_SCHEDULE_GROUP / RTC_SCHEDULE_ONE_TRI / RTC_SCHEDULE_TWO_TRI (rtc_core.h): how the lane-owned traversal driver times its triangle tests
 // (trace.cuh Traversal::step); hits and work counters do not depend on it.
-// Run-time choice between the two schedules.  The second one was written when no GPU was left to measure it on, so the library
-// measures it itself: of the first batches of a context that are large enough to time (>= 1 Mi paths), one is a warm-up and the
-// next three run schedule 0, schedule 1 and schedule 0 again, each between two events; schedule 1 serves every later launch only
-// if it beats the FASTER of the two schedule-0 batches by 3 %.  Results are bit-identical under both, so the choice never shows
-// in a frame.  RTC_TRACE_SCHEDULE=group|onetri fixes it (auto is the default); rtc_trace_schedule_get reports what happened.
+// Run-time choice between the schedules.  The capped ones were written when no GPU was left to measure them on, so the library
+// measures them itself: of the first batches of a context that are large enough to time (>= 1 Mi paths), one is a warm-up and
+// the next four run group / one triangle / two triangles / group, each between two events; a capped schedule serves every later
+// launch only if it beats the FASTER of the two group batches by 3 % (the faster capped one if both do).  Results are
+// bit-identical under all of them, so the choice never shows in a frame.  RTC_TRACE_SCHEDULE=group|onetri|twotri fixes it (auto
+// is the default); rtc_trace_schedule_get reports what happened.
 struct ScheduleTuner
 {
-  enum State { WARMUP = 0, TIME_GROUP_A = 1, TIME_ONE_TRI = 2, TIME_GROUP_B = 3, PENDING = 4, DONE = 5 };
+  enum State { WARMUP = 0, TIMING = 1, PENDING = 2, DONE = 3 };
+  static constexpr int kSlots = 4;  // timed batches: group, one triangle, two triangles, group again
   int         state = WARMUP;
-  cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   // begin / end of the three timed batches
-  uint64_t    paths = 0;            // size of the timed batches (all three must be the same)
+  int         slot = 0;             // TIMING: the next timed batch
+  cudaEvent_t ev[2 * kSlots] = {};  // begin / end of each timed batch
+  uint64_t    paths = 0;            // size of the timed batches (all must be the same)
   int         restarts = 0;         // a batch of another size restarts the measurement; bounded
-  float       ms[3] = { 0.0f, 0.0f, 0.0f };   // group, one triangle, group again
+  float       ms[kSlots] = { 0.0f, 0.0f, 0.0f, 0.0f };
   bool        fixedByEnv = false;
 };
 
@@ -236,5 +239,5 @@ int read_stack_overflows(rtc_context* ctx, uint64_t* out);
 // schedule tuner (kernels_shade.cu); tuner_finish blocks for the last timed batch when a decision is pending
 void tuner_finish(rtc_context* ctx);
 void tuner_release(rtc_context* ctx);
-void preload_one_tri_trace_kernels();      // kernels_trace.cu: loads the schedule-1 kernels before they are timed (lazy module loading)
+void preload_capped_trace_kernels();       // kernels_trace.cu: loads the capped-schedule kernels before they are timed (lazy module loading)
 int read_stack_overflows_primary(rtc_context* ctx, uint64_t* out);   // the counter of the primary-ray extend kernel (kernels_shade.cu)

@@ -25,7 +25,7 @@
 #define RTC_LEAF_THRESHOLD 0      // > 0: hold lanes with a pending leaf group back until this many lanes of the warp have one (trace_stream)
 #endif
 #ifndef RTC_ONE_TRI_PER_STEP
-#define RTC_ONE_TRI_PER_STEP 0    // default of the ONETRI template flag of Traversal / trace_stream (the kernels instantiate both and pick per launch)
+#define RTC_ONE_TRI_PER_STEP 0    // default of the TRICAP template parameter of Traversal / trace_stream (the kernels instantiate 0, 1 and 2 and pick per launch)
 #endif
 #ifndef RTC_FETCH_THRESHOLD
 #define RTC_FETCH_THRESHOLD 12    // refill a warp when at least this many lanes have finished their ray (8: -1.3 %, 16: same; re-swept in round 2)
@@ -268,9 +268,9 @@ __device__ unsigned int RTC_STACK_OVERFLOW_COUNTER = 0;
 // SKIP = true (ordered any-hit processing of cutout materials, anyhit.cu:46-132): only candidates that come AFTER the key
 // (skipT, skipInst, skipPrim) in the canonical order (t, instance, primitive) count, so repeated closest-hit queries
 // enumerate the candidates of a ray in that order.
-// ONETRI = true ("one triangle per step", rtc_context::traceSchedule 1): a step tests at most ONE triangle and a lane with more
-// pending skips its node visit until they are done; see step().
-template <bool ANY, bool COUNT, int BLOCK, bool SKIP = false, bool ONETRI = (RTC_ONE_TRI_PER_STEP != 0)>
+// TRICAP > 0 (rtc_context::traceSchedule, RTC_SCHEDULE_ONE_TRI / RTC_SCHEDULE_TWO_TRI): a step tests at most TRICAP triangles and a
+// lane with more pending skips its node visit until they are done; see step().  0: every triangle of the leaves a node visit found.
+template <bool ANY, bool COUNT, int BLOCK, bool SKIP = false, int TRICAP = RTC_ONE_TRI_PER_STEP>
 struct Traversal
 {
   float skipT; uint32_t skipInst, skipPrim;       // SKIP only
@@ -383,6 +383,7 @@ struct Traversal
   // returns false when the ray is finished (ANY: first hit)
   __device__ __forceinline__ bool leaf_phase(const SceneDesc& sc)
   {
+    int tested = 0;      // TRICAP > 1 only
     while (triGroup.y)
     {
       const uint32_t idx = (uint32_t)__ffs((int)triGroup.y) - 1u;
@@ -441,7 +442,7 @@ struct Traversal
             }
           }
         }
-        if (ONETRI) break;
+        if (TRICAP == 1 || (TRICAP > 1 && ++tested >= TRICAP)) break;
       }
     }
     return true;
@@ -472,15 +473,16 @@ struct Traversal
   // returns true while the ray needs more steps
   __device__ __forceinline__ bool step(const SceneDesc& sc)
   {
-    if (ONETRI)
+    if (TRICAP > 0)
     {
       // A warp pays the triangle loop of an iteration for as long as its unluckiest lane: 3.2 tests per iteration on bounce
       // rays of the geometry scene, although a lane tests 0.4 triangles per node visit on average.  Here a step tests at most
-      // one triangle, and a lane with more of them pending skips its node visit, so an iteration costs one node pass plus one
-      // triangle pass.  Per ray nothing changes -- the same tests in the same order, identical hits and work counters
-      // (tests/test_cpu_trace_source.py) -- only their timing within the warp: 26 % more iterations, 60 % fewer triangle passes
-      // (tools/simd_cost.py).  Built after the last GPU session of round 2 and therefore never enabled blindly: the library
-      // times one batch with each schedule and keeps this one only where it is faster (kernels_shade.cu, "schedule tuner").
+      // TRICAP triangles (one, or two = one leaf of the host builder), and a lane with more of them pending skips its node
+      // visit, so an iteration costs one node pass plus TRICAP triangle passes.  Per ray nothing changes -- the same tests in
+      // the same order, identical hits and work counters (tests/test_cpu_trace_source.py) -- only their timing within the
+      // warp: with a cap of one 26 % more iterations and 60 % fewer triangle passes, with two 6 % and 40 % (tools/simd_cost.py).
+      // Built after the last GPU session of round 2 and therefore never enabled blindly: the library times one batch with each
+      // schedule and keeps a capped one only where it is faster (kernels_shade.cu, "schedule tuner").
       if (!(blasBase >= 0 && has_leaves())) node_phase();
       if (!leaf_phase(sc)) return false;
       if (blasBase >= 0 && has_leaves()) return true;
@@ -496,11 +498,11 @@ struct Traversal
 // global cursor (one atomicAdd per warp and refill), so short rays do not leave their lanes idle while the longest ray of
 // the warp finishes.  Policy (stateless, shared with trace_pool.cuh) supplies load(i, org, dir, tag) -> bool (false: skip this
 // index; tag = the policy's per-ray word, e.g. the path id), store(tag, hit) and, for SKIP kernels, skip_key(tag, t, inst, prim).
-template <bool ANY, bool COUNT, int BLOCK, bool SKIP, bool ONETRI = (RTC_ONE_TRI_PER_STEP != 0), class Policy>
+template <bool ANY, bool COUNT, int BLOCK, bool SKIP, int TRICAP = RTC_ONE_TRI_PER_STEP, class Policy>
 __device__ __forceinline__ void trace_stream(const SceneDesc& sc, uint32_t n, uint32_t* __restrict__ cursor, Policy& policy, uint2* smem,
                                              unsigned long long* __restrict__ countsOut)
 {
-  Traversal<ANY, COUNT, BLOCK, SKIP, ONETRI> tr;
+  Traversal<ANY, COUNT, BLOCK, SKIP, TRICAP> tr;
   uint2 overflow[RTC_LM_STACK];
   tr.smStack = smem + threadIdx.x;
   tr.smRay = reinterpret_cast<float*>(smem + RTC_SM_STACK * BLOCK) + threadIdx.x;
