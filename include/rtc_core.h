@@ -176,7 +176,7 @@ int rtc_instance_inverse(rtc_context* ctx, uint64_t topObject, uint32_t instance
 /*
  * Host-only twin of rtc_gas_build(RTC_BUILD_HOST_SAH) + rtc_ias_build: the same builder code (csrc/accel_host.cpp,
  * csrc/bvh_build_host.cpp) fed from HOST arrays, returning the arrays the two functions would upload -- no CUDA call, no
- * context.  For tools (tools/bvh_quality.py) and for the CPU tests of the builder: the test oracle traverses the result in the
+ * context.  For tools (tests/tools/bvh_quality.py) and for the CPU tests of the builder: the test oracle traverses the result in the
  * kernels' order of operations, so node / triangle / instance counts per ray of a B200 run are known before it happens.
  *   geometry level: nodes = numNodes x 80 B, primOrder = numPrims triangle indices in leaf order, tris = numPrims x 12 floats
  *   instance level: nodes, primOrder = the instance-level leaf slots (instance ids), worldToObject = numInstances x 12 floats

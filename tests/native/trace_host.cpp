@@ -121,7 +121,7 @@ int th_trace(const th_scene* ws, uint32_t numTlasNodes, uint32_t numTlasLeaves, 
   return 0;
 }
 
-// Lock-step emulation of ONE persistent warp of trace_stream (csrc/trace.cuh) over a ray list, for tools/simd_cost.py: 32
+// Lock-step emulation of ONE persistent warp of trace_stream (csrc/trace.cuh) over a ray list, for tests/tools/simd_cost.py: 32
 // lanes, each owning one ray; when at least `fetchThreshold` lanes are idle (or all are) the idle lanes take the next rays in
 // list order; every iteration every active lane runs Traversal::step (leafThreshold > 0: the gated leaf phase of trace_stream's
 // RTC_LEAF_THRESHOLD path instead).  What a warp pays per iteration is the MAXIMUM over its

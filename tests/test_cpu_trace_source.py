@@ -207,7 +207,7 @@ def test_random_triangle_soups_with_degenerate_input(built, seed):
 
 
 def test_lock_step_warp_model_is_consistent_with_the_per_ray_counters(built):
-    """tools/simd_cost.py's instrument (th_simd_cost): one persistent warp in lock step.  Its summed lane work must be the work
+    """tests/tools/simd_cost.py's instrument (th_simd_cost): one persistent warp in lock step.  Its summed lane work must be the work
     the per-ray run counts, whatever the refill threshold; its per-iteration maxima are bounded by both."""
     z, export = fixture_export()
     rays = z["rays"]

@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Acceleration-structure quality WITHOUT a GPU: builds the scene's wide BVH through the host-only twin of the builder
+"""TEST INFRASTRUCTURE (it drives the test oracle; nothing in the product imports it).
+
+Acceleration-structure quality WITHOUT a GPU: builds the scene's wide BVH through the host-only twin of the builder
 (rtc_host_gas_build / rtc_host_ias_build -- byte for byte the arrays a B200 is handed, tests/test_cpu_host_accel.py) and lets
 the test oracle traverse it in the kernels' order of operations (oracle/wide_bvh.inc), which reproduces the work counters of
 the GPU's counting kernels ray by ray (tests/test_gpu_wide_bvh.py).  Prints wide nodes visited, triangles tested and instances
@@ -9,7 +11,7 @@ entered per ray for
 and the combined cost in node visits (a triangle test costs a warp about 2.7 node visits and an instance entry about 3 in the
 lane-owned traversal driver, profiles/sweeps_r2.md).  Every hit is checked against the oracle's own binary BVH.
 
-  python tools/bvh_quality.py [--config c1|c2|c4|textures] [--width 240 --height 135] [--instances 10000] [--any]
+  python tests/tools/bvh_quality.py [--config c1|c2|c4|textures] [--width 240 --height 135] [--instances 10000] [--any]
 Environment knobs of the builder (RTC_HOST_LEAF_MAX, RTC_TLAS_LEAF, RTC_INSTANCE_BOUNDS, RTC_HOST_* ...) apply.
 """
 import argparse
@@ -21,10 +23,11 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "tools"))
 
 import helpers as H                                # noqa: E402
 from oracle import orc                             # noqa: E402

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
-"""SIMD-aware traversal cost of a scene's acceleration structure WITHOUT a GPU.
+"""TEST INFRASTRUCTURE (it drives the test oracle and the host build of the traversal source; nothing in the product imports it).
 
-tools/bvh_quality.py counts work per RAY.  A warp pays per ITERATION: the node visit once if any lane visits a node, the
+SIMD-aware traversal cost of a scene's acceleration structure WITHOUT a GPU.
+
+tests/tools/bvh_quality.py counts work per RAY.  A warp pays per ITERATION: the node visit once if any lane visits a node, the
 triangle loop for as long as the lane with the most triangles, the instance entry once if any lane enters one.  This tool runs
 the product's traversal source compiled for the host (tests/native/trace_host.cpp) as one persistent warp in lock step --
 32 lanes, refill when 12 are idle, rays in the order the GPU's queues hold them -- over the structure the host-only twin of the
@@ -14,7 +16,7 @@ node visit ~ 230 instructions, one triangle test ~ 100, instance entry ~ 170, lo
 system, no scheduler -- meant for A/B comparisons between builder settings (RTC_HOST_LEAF_MAX, RTC_TLAS_LEAF,
 RTC_HOST_COLLAPSE, RTC_INSTANCE_BOUNDS ...); profiles/bvh_quality_r2.md compares it with the A/Bs round 2 measured on a B200.
 
-  python tools/simd_cost.py [--config c1|c2|c4|textures] [--width 240 --height 136] [--instances 10000]
+  python tests/tools/simd_cost.py [--config c1|c2|c4|textures] [--width 240 --height 136] [--instances 10000]
                             [--threshold 12] [--leaf-threshold 0] [--define RTC_ONE_TRI_PER_STEP=1]
 """
 import argparse
@@ -25,10 +27,11 @@ import tempfile
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "tools"))
 
 import helpers as H                                # noqa: E402
 from oracle import orc                             # noqa: E402

@@ -342,7 +342,7 @@ void build_wide_bvh_host(const PrimBox* prims, uint32_t numPrims, WideBvh& out, 
   // (instance level) selects the SAH-optimal dynamic programme.  The optimal collapse needs 30-48 % fewer nodes and visits 3-7 %
   // fewer of them per ray, but a warp pays per iteration for the lane with the MOST triangles, and full bottom nodes hand one
   // lane more triangles at a time; instance-level leaves of one node are entered without a new box test, so a fuller
-  // instance-level node culls less.  The lock-step warp model of tools/simd_cost.py (which reproduces the sign and size of
+  // instance-level node culls less.  The lock-step warp model of tests/tools/simd_cost.py (which reproduces the sign and size of
   // six A/Bs round 2 measured on a B200) puts it at -3 % on the geometry scene, -2 % on the Cornell box, +2 % on the instanced
   // stress scene (profiles/bvh_quality_r2.md); no GPU measurement of it exists, so the measured collapse stays the default.
   const char* mode = getenv(instanceLevel ? "RTC_TLAS_COLLAPSE" : "RTC_HOST_COLLAPSE");

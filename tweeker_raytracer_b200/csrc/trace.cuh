@@ -480,7 +480,7 @@ struct Traversal
       // TRICAP triangles (one, or two = one leaf of the host builder), and a lane with more of them pending skips its node
       // visit, so an iteration costs one node pass plus TRICAP triangle passes.  Per ray nothing changes -- the same tests in
       // the same order, identical hits and work counters (tests/test_cpu_trace_source.py) -- only their timing within the
-      // warp: with a cap of one 26 % more iterations and 60 % fewer triangle passes, with two 6 % and 40 % (tools/simd_cost.py).
+      // warp: with a cap of one 26 % more iterations and 60 % fewer triangle passes, with two 6 % and 40 % (tests/tools/simd_cost.py).
       // Built after the last GPU session of round 2 and therefore never enabled blindly: the library times one batch with each
       // schedule and keeps a capped one only where it is faster (kernels_shade.cu, "schedule tuner").
       if (!(blasBase >= 0 && has_leaves())) node_phase();
