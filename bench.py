@@ -826,6 +826,31 @@ def run_rays(args, rank, local_rank, world):
     K, W = args.steps, args.warmup
     for _ in range(W):
         trace()
+    # Schedule of the triangle tests (include/rtc_core.h rtc_trace_schedule_set).  The library measures it by itself only inside
+    # rtc_launch; for the query interface the caller does what the library does there: one step with each schedule (group first
+    # and last) after the warm-up, a capped schedule only if it beats the faster group step by 3 %.  Results are bit-identical.
+    schedule = {"schedule": "group", "measured": False}
+    if (os.environ.get("RTC_TRACE_SCHEDULE") or "auto")[0] not in "go01t2":
+        try:
+            times = []
+            for name in ("group", "one_tri", "two_tri", "group"):
+                ctx.set_trace_schedule(name)
+                ctx.timer_start()
+                trace()
+                times.append(ctx.timer_stop())
+            group = min(times[0], times[3])
+            best = "group"
+            if min(times[1], times[2]) < 0.97 * group:
+                best = "one_tri" if times[1] <= times[2] else "two_tri"
+            if dist is not None:        # one choice for the job: rank 0's
+                pick = [best]
+                dist.broadcast_object_list(pick, src=0)
+                best = pick[0]
+            ctx.set_trace_schedule(best)
+            schedule = {"schedule": best, "measured": True, "group_ms": [times[0], times[3]], "one_tri_ms": times[1], "two_tri_ms": times[2]}
+        except Exception as e:          # reporting only: fall back to the measured schedule
+            ctx.set_trace_schedule("group")
+            schedule = {"schedule": "group", "measured": False, "error": repr(e)}
     sampler = ClockSampler(local_rank, getattr(torch.cuda.get_device_properties(local_rank), "uuid", None))
     ctx.stats_reset()
     barrier()
@@ -888,7 +913,7 @@ def run_rays(args, rank, local_rank, world):
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "scene_info": scene_info,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": ne * 32, "d2h_bytes_per_step": ne * (20 if mode == "closest" else 4),
                         "path": "rtc_upload (pinned host rays) + rtc_trace_%s + rtc_download (hits) of %d rays per step" % (mode, ne)},
-                "gpu_launches": launches, "clocks": sampler.summary(),
+                "gpu_launches": launches, "clocks": sampler.summary(), "trace_schedule": schedule,
                 "roofline": {"bound": "hbm" if bvh_mb > 126.0 else "l2", "kernel": "k_trace<ANY=%d, Query%s>" % (mode == "any", "Closest" if mode == "closest" else "Any"),
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                              "fractions": fractions, "peaks": peaks,
