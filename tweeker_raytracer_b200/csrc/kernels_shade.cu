@@ -15,6 +15,7 @@
 #define RTC_STACK_OVERFLOW_COUNTER g_rtcStackOverflowsPrimary
 #include "trace_pool.cuh"
 #include "trace_packet.cuh"
+#include "schedule_tuner.h"
 
 #include <cstdlib>
 #include <cstring>
@@ -1198,88 +1199,23 @@ void release_cutout_graph(rtc_context* ctx)
   ctx->cutoutGraph = nullptr;
 }
 
-// ---- schedule tuner (rtc_internal.h ScheduleTuner) ---------------------------------------------------------------------------
-// Nothing in here may fail a launch: on any CUDA error the tuner retires with the schedule rounds 1 and 2 measured.
+// ---- schedule tuner (rtc_internal.h ScheduleTuner; the state machine lives in schedule_tuner.h so that a CPU test can run it) ----
 namespace {
 
-constexpr uint64_t kTuneMinPaths = 1ull << 20;     // smaller batches are launch- and tail-bound: nothing to learn from timing them
-constexpr float    kTuneMargin = 0.97f;            // a capped schedule must beat the faster group batch by 3 %
-// the schedule each timed batch runs: group first and last, so that a drift of the clocks cannot favour a capped schedule
-constexpr int      kTuneSchedule[ScheduleTuner::kSlots] = { RTC_SCHEDULE_GROUP, RTC_SCHEDULE_ONE_TRI, RTC_SCHEDULE_TWO_TRI, RTC_SCHEDULE_GROUP };
-
-void tuner_give_up(rtc_context* ctx)
+// With lazy module loading a kernel is loaded at its first launch; the tuner must not time that.
+void preload_capped_kernels()
 {
+  cudaFuncAttributes attr;
+  cudaFuncGetAttributes(&attr, k_extend_primary<false, 1>);
+  cudaFuncGetAttributes(&attr, k_extend_primary<false, 2>);
+  preload_capped_trace_kernels();
   cudaGetLastError();
-  ctx->tuner.state = ScheduleTuner::DONE;
-  ctx->traceSchedule = RTC_SCHEDULE_GROUP;
-}
-
-// Called before the launches of a batch.  Returns the timed slot the batch fills (0 .. kSlots - 1) or -1, and sets
-// ctx->traceSchedule for the batch.
-int tuner_begin(rtc_context* ctx, uint64_t paths, bool eligible)
-{
-  ScheduleTuner& t = ctx->tuner;
-  if (t.state == ScheduleTuner::DONE) return -1;
-  if (t.state == ScheduleTuner::PENDING) { tuner_finish(ctx); return -1; }
-  ctx->traceSchedule = RTC_SCHEDULE_GROUP;
-  if (!eligible || paths < kTuneMinPaths) return -1;
-  if (t.state == ScheduleTuner::WARMUP)
-  {
-    // the first batch pays for allocations, lazily loaded kernels and the clock ramp: not timed
-    for (int k = 0; k < 2 * ScheduleTuner::kSlots; ++k) if (!t.ev[k] && cudaEventCreate(&t.ev[k]) != cudaSuccess) { tuner_give_up(ctx); return -1; }
-    cudaFuncAttributes attr;
-    cudaFuncGetAttributes(&attr, k_extend_primary<false, 1>);
-    cudaFuncGetAttributes(&attr, k_extend_primary<false, 2>);
-    preload_capped_trace_kernels();
-    cudaGetLastError();
-    t.state = ScheduleTuner::TIMING;
-    t.slot = 0;
-    return -1;
-  }
-  if (t.slot > 0 && paths != t.paths)
-  {
-    if (++t.restarts > 8) { t.state = ScheduleTuner::DONE; return -1; }
-    t.slot = 0;
-  }
-  if (t.slot == 0) t.paths = paths;
-  ctx->traceSchedule = kTuneSchedule[t.slot];
-  if (cudaEventRecord(t.ev[2 * t.slot], ctx->stream) != cudaSuccess) { tuner_give_up(ctx); return -1; }
-  return t.slot;
-}
-
-// Called behind the launches of a batch tuner_begin gave a slot.
-void tuner_end(rtc_context* ctx, int slot)
-{
-  if (slot < 0) return;
-  ScheduleTuner& t = ctx->tuner;
-  ctx->traceSchedule = RTC_SCHEDULE_GROUP;
-  if (t.state != ScheduleTuner::TIMING) return;
-  if (cudaEventRecord(t.ev[2 * slot + 1], ctx->stream) != cudaSuccess) { tuner_give_up(ctx); return; }
-  t.slot = slot + 1;
-  if (t.slot == ScheduleTuner::kSlots) t.state = ScheduleTuner::PENDING;
 }
 
 } // namespace
 
-// Decides once the timed batches have finished (waits for the last one).
-void tuner_finish(rtc_context* ctx)
-{
-  ScheduleTuner& t = ctx->tuner;
-  if (t.state != ScheduleTuner::PENDING) return;
-  bool ok = cudaEventSynchronize(t.ev[2 * ScheduleTuner::kSlots - 1]) == cudaSuccess;
-  for (int slot = 0; ok && slot < ScheduleTuner::kSlots; ++slot) ok = cudaEventElapsedTime(&t.ms[slot], t.ev[2 * slot], t.ev[2 * slot + 1]) == cudaSuccess;
-  if (!ok) { tuner_give_up(ctx); return; }
-  const float group = t.ms[0] < t.ms[3] ? t.ms[0] : t.ms[3];
-  int best = RTC_SCHEDULE_GROUP; float bestMs = kTuneMargin * group;
-  for (int slot = 1; slot <= 2; ++slot) if (t.ms[slot] > 0.0f && t.ms[slot] < bestMs) { bestMs = t.ms[slot]; best = kTuneSchedule[slot]; }
-  ctx->traceSchedule = best;
-  t.state = ScheduleTuner::DONE;
-}
-
-void tuner_release(rtc_context* ctx)
-{
-  for (int k = 0; k < 2 * ScheduleTuner::kSlots; ++k) if (ctx->tuner.ev[k]) { cudaEventDestroy(ctx->tuner.ev[k]); ctx->tuner.ev[k] = nullptr; }
-}
+void tuner_finish(rtc_context* ctx) { rtc_tuner::finish(ctx); }
+void tuner_release(rtc_context* ctx) { rtc_tuner::release(ctx); }
 
 int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uint32_t h, int raygen, int miss, int iterFirst, int iterCount,
                      int accumFirst, bool countWork)
@@ -1322,7 +1258,7 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
     a.wf = ctx->wf; a.sys = sys; a.launchWidth = w; a.launchHeight = h; a.raygen = raygen; a.miss = miss;
     a.iterFirst = iterFirst + done; a.iterCount = batch; a.accumFirst = accumFirst + done; a.numPaths = (uint32_t)(pixels * (uint64_t)batch);
     // schedule tuner: the lane-owned driver on scenes without cutout materials, timed launches only
-    const int tuneSlot = tuner_begin(ctx, a.numPaths, !countWork && !cutout && ctx->traceDriver == RTC_DRIVER_LANE && !ctx->primaryPackets);
+    const int tuneSlot = rtc_tuner::begin(ctx, a.numPaths, !countWork && !cutout && ctx->traceDriver == RTC_DRIVER_LANE && !ctx->primaryPackets, preload_capped_kernels);
     uint32_t* cnt = ctx->wf.counters;
     RTC_CUDA(cudaMemsetAsync(cnt, 0, 4 * kNumCounters, ctx->stream));
     // Fused primary path (scenes without material textures): no generate pass.  The depth-0 extend computes its rays from the
@@ -1391,7 +1327,7 @@ int launch_wavefront(rtc_context* ctx, const rt_SystemData& sys, uint32_t w, uin
     k_stats<<<1, 32, 0, ctx->stream>>>(cnt, maxDepth, a.numPaths, ctx->d_stats);
     ctx->kernelLaunches += 2;
     RTC_CUDA(cudaGetLastError());
-    tuner_end(ctx, tuneSlot);
+    rtc_tuner::end(ctx, tuneSlot);
   }
   return 0;
 }
