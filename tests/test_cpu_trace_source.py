@@ -245,3 +245,28 @@ def test_capped_schedules_change_no_hit_and_no_counter(built, tmp_path, cap):
     base, variant = H.product_simd_cost(export, rays), H.product_simd_cost(export, rays, defs=defs)
     assert (variant["nodes"], variant["tris"], variant["instances"]) == (base["nodes"], base["tris"], base["instances"])
     assert variant["tri_passes_max"] < (0.6, 0.8)[cap - 1] * base["tri_passes_max"] and variant["iterations"] > base["iterations"]
+
+
+@pytest.mark.parametrize("seed", [0, 5, 11])
+@pytest.mark.parametrize("cap", [1, 2])
+def test_capped_schedules_on_random_scenes(built, tmp_path, seed, cap):
+    """The capped schedules on scenes of the GPU fuzz test (rotated, non-uniformly scaled instances of every model kind): hits,
+    occlusion and work counters equal those of the uncapped schedule and of the oracle."""
+    from test_gpu_fuzz import random_scene
+    defs = ("RTC_ONE_TRI_PER_STEP=%d" % cap,)
+    rng = np.random.default_rng(1000 + seed)
+    scene = os.path.join(str(tmp_path), "scene_fuzz.txt")
+    random_scene(scene, rng)
+    app = host.App(H.write_system(tmp_path, "rtigo3_geometry", resolution="32 32", samplesSqrt=1), scene, host_only=True)
+    geos = [app.geometry(g) for g in range(app.info.numGeometries)]
+    insts = [app.instance(i)[:2] for i in range(app.info.numInstances)]
+    export, _ = core.host_scene_export(geos, insts)
+    ref = H.oracle_scene(app)
+    rays = H.random_rays(20000, seed=seed, lo=(-5, 0.05, -5), hi=(5, 4, 5))
+    hits, counts, overflows = H.product_trace(export, rays, defs=defs)
+    assert overflows == 0 and H.hits_equal(hits, ref.trace_closest(rays))
+    assert counts == H.product_trace(export, rays)[1] == orc.wide_trace(export, rays)[1]
+    occl, counts_any, _ = H.product_trace(export, rays, any_hit=True, defs=defs)
+    assert np.array_equal(occl["inst"] != 0xffffffff, ref.trace_any(rays).astype(bool))
+    assert counts_any == orc.wide_trace(export, rays, any_hit=True)[1]
+    app.close()
