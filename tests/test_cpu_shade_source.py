@@ -1,0 +1,132 @@
+"""The PRODUCT's ray-generation source on the CPU: csrc/shade.cuh compiled unchanged by g++ (tests/native/shade_host.cpp, the
+flags of the device build of the shading translation unit: no FMA contraction, IEEE division and square root) and held against
+
+  * the reference: its TEA and LCG generators reproduce the golden vectors made by the reference's own sources
+    (tests/golden/reference_rng.json);
+  * the oracle (which is pinned against the reference bit for bit): start_path() -- distribute(), seeding, jitter, the pinhole /
+    fisheye / sphere lens shaders -- gives the oracle's primary rays bit for bit, for a single device and for every device of a
+    tiled multi-GPU launch, where launch indices outside the image must be skipped identically;
+  * the texture fetch this repository defines (bilinear, wrap / wrap): equal to the oracle's, bit for bit, inside and far
+    outside the unit square.
+
+This is the CPU twin of tests/test_gpu_trace_parity.py's primary-ray test; the BSDF, light and integrator code is only reachable
+through whole frames and stays a GPU test (tests/test_gpu_render_parity.py)."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import orc
+from tweeker_raytracer_b200 import host
+
+GOLDEN = os.path.join(H.ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def shade():
+    src = os.path.join(H.ROOT, "tests", "native", "shade_host.cpp")
+    out_dir = os.path.join(H.ROOT, "oracle", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libshade_host.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I" + os.path.join(H.ROOT, "include"),
+                           "-I" + os.path.join(H.ROOT, "tweeker_raytracer_b200", "csrc"), "-I/usr/local/cuda/include", "-o", so, src])
+    L = C.CDLL(so)
+    L.sh_tea4.argtypes = [C.c_uint32, C.c_uint32]
+    L.sh_tea4.restype = C.c_uint32
+    L.sh_rng_sequence.argtypes = [C.c_uint32, C.c_int, C.c_void_p, C.POINTER(C.c_uint32)]
+    L.sh_generate_primary.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+    L.sh_tex2d.argtypes = [C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+    return L
+
+
+def test_generators_reproduce_the_reference_golden_vectors(built, shade):
+    with open(os.path.join(GOLDEN, "reference_rng.json")) as f:
+        g = json.load(f)
+    for a, b, want in g["tea4"]:
+        assert shade.sh_tea4(a, b) == want
+    for row in g["lcg"]:
+        n = len(row["samples_hex"])
+        seq = np.zeros(n, dtype=np.float32)
+        state = C.c_uint32(0)
+        shade.sh_rng_sequence(row["seed"], n, seq.ctypes.data, C.byref(state))
+        assert state.value == row["state"]
+        assert [float(x).hex() for x in seq] == row["samples_hex"]
+    rng = np.random.default_rng(3)
+    for a, b in rng.integers(0, 2 ** 32, size=(200, 2), dtype=np.uint64):
+        assert shade.sh_tea4(int(a), int(b)) == orc.tea4(int(a), int(b))
+
+
+def primary_rays(shade, app, device_index, launch_width, launch_height, iteration):
+    sysd = app.system_data(device_index)
+    camera = np.ascontiguousarray(app.camera())
+    sysd.cameraDefinitions = camera.ctypes.data          # host_only: the host copy stands in for the device array
+    rays = np.zeros(launch_width * launch_height, dtype=orc.RAY_DTYPE)
+    shade.sh_generate_primary(C.byref(sysd), launch_width, launch_height, iteration, rays.ctypes.data)
+    return rays
+
+
+def rays_identical(a, b):
+    return all(np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)) for k in a.dtype.names)
+
+
+@pytest.mark.parametrize("lens", [0, 1, 2])
+def test_primary_rays_equal_the_oracle_for_every_lens_shader(built, shade, tmp_path, lens):
+    app = host.App(H.write_system(tmp_path, "rtigo3_cornell_box", resolution="96 64", samplesSqrt=2, lensShader=lens),
+                   H.scene_path("rtigo3_cornell_box"), host_only=True)
+    ref = H.oracle_scene(app)
+    for iteration in (0, 3):
+        got = primary_rays(shade, app, 0, 96, 64, iteration)
+        want = ref.generate_primary(H.oracle_sys(app), 96, 64, iteration)
+        assert rays_identical(got, want)
+        assert (got["tmax"] > 0).all()
+    app.close()
+
+
+def test_primary_rays_of_a_tiled_multi_device_launch(built, shade, tmp_path):
+    """distribute(): device d of 3 renders the tiles (x + y) % 3 == d of a 100 x 40 image (a width that is not a multiple of the
+    tile grid, so some launch indices fall outside the image and are skipped)."""
+    app = host.App(H.write_system(tmp_path, "rtigo3_geometry", resolution="100 40", samplesSqrt=1), H.scene_path("rtigo3_geometry"), host_only=True)
+    ref = H.oracle_scene(app)
+    base = app.system_data(0)
+    skipped = 0
+    for device in range(3):
+        camera = np.ascontiguousarray(app.camera())
+        sysd = host.SystemData.from_buffer_copy(bytes(base))
+        sysd.cameraDefinitions = camera.ctypes.data
+        sysd.deviceCount, sysd.deviceIndex, sysd.distribution = 3, device, 1
+        launch_width = ((100 + 8 * 3 - 1) // (8 * 3)) * 8          # tiles of 8 columns dealt to 3 devices
+        rays = np.zeros(launch_width * 40, dtype=orc.RAY_DTYPE)
+        shade.sh_generate_primary(C.byref(sysd), launch_width, 40, 0, rays.ctypes.data)
+        osys = H.oracle_sys(app)
+        osys.deviceCount, osys.deviceIndex, osys.distribution = 3, device, 1
+        want = ref.generate_primary(osys, launch_width, 40, 0)
+        assert rays_identical(rays, want)
+        skipped += int((rays["tmax"] < 0).sum())
+    assert skipped > 0
+    app.close()
+
+
+def test_texture_fetch_equals_the_oracle(built, shade):
+    rng = np.random.default_rng(5)
+    w, h = 13, 7
+    block = np.zeros(4 + 4 * w * h, dtype=np.float32)
+    block[:4].view(np.uint32)[:] = [w, h, 0, 0]
+    block[4:] = rng.uniform(0.0, 1.0, size=4 * w * h).astype(np.float32)
+    handle = block.ctypes.data
+    uv = np.concatenate([rng.uniform(0, 1, size=(500, 2)), rng.uniform(-7, 9, size=(500, 2)),
+                         [[0.0, 0.0], [1.0, 1.0], [0.5 / w, 0.5 / h], [1.0 - 1e-7, 1e-7]]]).astype(np.float32)
+    got = np.zeros((len(uv), 3), dtype=np.float32)
+    shade.sh_tex2d(handle, len(uv), uv.ctypes.data, got.ctypes.data)
+    L = orc.lib()
+    L.orc_tex2d.argtypes = [C.c_uint64, C.c_float, C.c_float, C.POINTER(C.c_float * 3)]
+    L.orc_tex2d.restype = None
+    want = np.zeros_like(got)
+    for i, (u, v) in enumerate(uv):
+        out = (C.c_float * 3)()
+        L.orc_tex2d(handle, float(u), float(v), C.byref(out))
+        want[i] = out[:]
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
