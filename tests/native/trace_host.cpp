@@ -43,6 +43,17 @@ unsigned long long __shfl_down_sync(unsigned, unsigned long long, int);
 
 #include "trace.cuh"
 
+// The exported arrays as the kernels see them: 16-byte aligned copies (nodes, triangles and instance records are read as uint4 /
+// float4) and instance records as rtc_ias_build writes them (world->object rows 0..2, {GAS nodes pointer, GAS triangles pointer}).
+struct HostScene
+{
+  SceneDesc sc{};
+  std::vector<void*> owned;
+  ~HostScene() { for (void* p : owned) free(p); }
+  void* aligned(size_t bytes) { void* p = nullptr; if (posix_memalign(&p, 16, bytes ? bytes : 16)) p = nullptr; owned.push_back(p); return p; }
+  void* copy(const void* src, size_t bytes) { void* p = aligned(bytes); if (bytes) std::memcpy(p, src, bytes); return p; }
+};
+
 extern "C" {
 
 // the layout of orc_wide_scene (oracle/wide_bvh.inc), i.e. of oracle/orc.py WideScene
@@ -57,26 +68,17 @@ struct th_scene
   uint32_t numInstances;
 };
 
-// rays: rtc_ray; hits: rtc_hit; counts: nodes, triangles, instances.  skip: optional, per ray {t bits, instance, primitive}
-// -- when given, the SKIP instantiation runs (closest candidate AFTER the key) with tmin raised exactly as the device's
-// ExtendPathsAfter::load does.  numTlasNodes / numGasNodes / numGasTris size the 16-byte aligned copies.
-int th_trace(const th_scene* ws, uint32_t numTlasNodes, uint32_t numTlasLeaves, uint32_t numGas, const uint32_t* numGasNodes,
-             const uint32_t* numGasTris, const rtc_ray* rays, uint64_t n, int any, const uint32_t* skip, rtc_hit* hits, uint64_t counts[3],
-             uint64_t* stackOverflows)
+static void build_host_scene(HostScene& hs, const th_scene* ws, uint32_t numTlasNodes, uint32_t numTlasLeaves, uint32_t numGas,
+                             const uint32_t* numGasNodes, const uint32_t* numGasTris)
 {
-  // 16-byte aligned copies: the traversal reads nodes, triangles and instance records as uint4 / float4
-  auto aligned = [](size_t bytes) { void* p = nullptr; if (posix_memalign(&p, 16, bytes ? bytes : 16)) return (void*)nullptr; return p; };
-  std::vector<void*> owned;
-  auto copy = [&](const void* src, size_t bytes) { void* p = aligned(bytes); owned.push_back(p); if (bytes) std::memcpy(p, src, bytes); return p; };
   std::vector<const uint4*> gasNodes(numGas);
   std::vector<const float4*> gasTris(numGas);
   for (uint32_t g = 0; g < numGas; ++g)
   {
-    gasNodes[g] = (const uint4*)copy(ws->gasNodes[g], (size_t)numGasNodes[g] * 80u);
-    gasTris[g] = (const float4*)copy(ws->gasTris[g], (size_t)numGasTris[g] * 48u);
+    gasNodes[g] = (const uint4*)hs.copy(ws->gasNodes[g], (size_t)numGasNodes[g] * 80u);
+    gasTris[g] = (const float4*)hs.copy(ws->gasTris[g], (size_t)numGasTris[g] * 48u);
   }
-  // instance records as rtc_ias_build writes them: world->object rows 0..2, {GAS nodes pointer, GAS triangles pointer}
-  float4* inst = (float4*)aligned((size_t)ws->numInstances * 64u); owned.push_back(inst);
+  float4* inst = (float4*)hs.aligned((size_t)ws->numInstances * 64u);
   for (uint32_t i = 0; i < ws->numInstances; ++i)
   {
     const float* m = ws->worldToObject + 12u * (size_t)i;
@@ -85,11 +87,22 @@ int th_trace(const th_scene* ws, uint32_t numTlasNodes, uint32_t numTlasLeaves, 
     const uint32_t w[4] = { (uint32_t)np, (uint32_t)(np >> 32), (uint32_t)tp, (uint32_t)(tp >> 32) };
     std::memcpy(&inst[4u * i + 3], w, 16);
   }
-  SceneDesc sc{};
-  sc.tlasNodes = (const uint4*)copy(ws->tlasNodes, (size_t)numTlasNodes * 80u);
-  sc.tlasLeaves = (const uint32_t*)copy(ws->tlasLeaves, (size_t)numTlasLeaves * 4u);
-  sc.instances = inst;
-  sc.numInstances = ws->numInstances; sc.numTlasNodes = numTlasNodes; sc.numTlasLeaves = numTlasLeaves;
+  hs.sc.tlasNodes = (const uint4*)hs.copy(ws->tlasNodes, (size_t)numTlasNodes * 80u);
+  hs.sc.tlasLeaves = (const uint32_t*)hs.copy(ws->tlasLeaves, (size_t)numTlasLeaves * 4u);
+  hs.sc.instances = inst;
+  hs.sc.numInstances = ws->numInstances; hs.sc.numTlasNodes = numTlasNodes; hs.sc.numTlasLeaves = numTlasLeaves;
+}
+
+// rays: rtc_ray; hits: rtc_hit; counts: nodes, triangles, instances.  skip: optional, per ray {t bits, instance, primitive}
+// -- when given, the SKIP instantiation runs (closest candidate AFTER the key) with tmin raised exactly as the device's
+// ExtendPathsAfter::load does.  numTlasNodes / numGasNodes / numGasTris size the 16-byte aligned copies.
+int th_trace(const th_scene* ws, uint32_t numTlasNodes, uint32_t numTlasLeaves, uint32_t numGas, const uint32_t* numGasNodes,
+             const uint32_t* numGasTris, const rtc_ray* rays, uint64_t n, int any, const uint32_t* skip, rtc_hit* hits, uint64_t counts[3],
+             uint64_t* stackOverflows)
+{
+  HostScene hs;
+  build_host_scene(hs, ws, numTlasNodes, numTlasLeaves, numGas, numGasNodes, numGasTris);
+  const SceneDesc& sc = hs.sc;
 
   counts[0] = counts[1] = counts[2] = 0;
   const unsigned overflowsBefore = RTC_STACK_OVERFLOW_COUNTER;
@@ -117,7 +130,6 @@ int th_trace(const th_scene* ws, uint32_t numTlasNodes, uint32_t numTlasLeaves, 
     if (hits) { hits[i].t = h.t; hits[i].u = h.u; hits[i].v = h.v; hits[i].inst = h.inst; hits[i].prim = h.prim; }
   }
   if (stackOverflows) *stackOverflows = RTC_STACK_OVERFLOW_COUNTER - overflowsBefore;
-  for (void* p : owned) free(p);
   return 0;
 }
 
@@ -136,30 +148,9 @@ int th_simd_cost(const th_scene* ws, uint32_t numTlasNodes, uint32_t numTlasLeav
                  const uint32_t* numGasTris, const rtc_ray* rays, uint64_t n, int any, uint32_t fetchThreshold, uint32_t leafThreshold,
                  uint64_t out[10])
 {
-  auto aligned = [](size_t bytes) { void* p = nullptr; if (posix_memalign(&p, 16, bytes ? bytes : 16)) return (void*)nullptr; return p; };
-  std::vector<void*> owned;
-  auto copy = [&](const void* src, size_t bytes) { void* p = aligned(bytes); owned.push_back(p); if (bytes) std::memcpy(p, src, bytes); return p; };
-  std::vector<const uint4*> gasNodes(numGas);
-  std::vector<const float4*> gasTris(numGas);
-  for (uint32_t g = 0; g < numGas; ++g)
-  {
-    gasNodes[g] = (const uint4*)copy(ws->gasNodes[g], (size_t)numGasNodes[g] * 80u);
-    gasTris[g] = (const float4*)copy(ws->gasTris[g], (size_t)numGasTris[g] * 48u);
-  }
-  float4* inst = (float4*)aligned((size_t)ws->numInstances * 64u); owned.push_back(inst);
-  for (uint32_t i = 0; i < ws->numInstances; ++i)
-  {
-    const float* m = ws->worldToObject + 12u * (size_t)i;
-    for (int r = 0; r < 3; ++r) inst[4u * i + r] = make_float4(m[4 * r], m[4 * r + 1], m[4 * r + 2], m[4 * r + 3]);
-    const uint64_t np = (uint64_t)(uintptr_t)gasNodes[ws->instGas[i]], tp = (uint64_t)(uintptr_t)gasTris[ws->instGas[i]];
-    const uint32_t w[4] = { (uint32_t)np, (uint32_t)(np >> 32), (uint32_t)tp, (uint32_t)(tp >> 32) };
-    std::memcpy(&inst[4u * i + 3], w, 16);
-  }
-  SceneDesc sc{};
-  sc.tlasNodes = (const uint4*)copy(ws->tlasNodes, (size_t)numTlasNodes * 80u);
-  sc.tlasLeaves = (const uint32_t*)copy(ws->tlasLeaves, (size_t)numTlasLeaves * 4u);
-  sc.instances = inst;
-  sc.numInstances = ws->numInstances; sc.numTlasNodes = numTlasNodes; sc.numTlasLeaves = numTlasLeaves;
+  HostScene hs;
+  build_host_scene(hs, ws, numTlasNodes, numTlasLeaves, numGas, numGasNodes, numGasTris);
+  const SceneDesc& sc = hs.sc;
 
   for (int k = 0; k < 10; ++k) out[k] = 0;
   struct Lane { uint2 smStack[RTC_SM_STACK]; float smRay[RTC_SM_RAY_WORDS]; uint2 lmStack[RTC_LM_STACK]; bool active = false; };
@@ -228,7 +219,6 @@ int th_simd_cost(const th_scene* ws, uint32_t numTlasNodes, uint32_t numTlasLeav
   };
   if (any) simulate(Traversal<true, true, 1, false>());
   else     simulate(Traversal<false, true, 1, false>());
-  for (void* p : owned) free(p);
   return 0;
 }
 
