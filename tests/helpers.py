@@ -182,11 +182,10 @@ def product_trace_lib(defs=()):
     return _trace_host[key]
 
 
-def product_trace(export, rays, any_hit=False, skip=None, defs=()):
-    """Runs the host build of csrc/trace.cuh over an exported (or host-built) wide BVH: (hits, (nodes, tris, instances), stack
-    overflows).  skip: [n, 3] uint32 keys (t bits, instance, primitive) -> the closest candidate AFTER the key (SKIP variant)."""
+def _wide_scene(export):
+    """An exported (or host-built) wide BVH marshalled for tests/native/trace_host.cpp: (WideScene, the scalar / size arguments that
+    follow it, the arrays that must stay alive during the call)."""
     import ctypes as C
-    L = product_trace_lib(defs)
     handles = sorted(export["gas"])
     slot = {g: k for k, g in enumerate(handles)}
     inst_gas = np.ascontiguousarray([slot[int(g)] for g in export["instance_gas"]], dtype=np.uint32)
@@ -199,6 +198,16 @@ def product_trace(export, rays, any_hit=False, skip=None, defs=()):
     tn, tl, w2o = (np.ascontiguousarray(export[k]) for k in ("tlas_nodes", "tlas_leaves", "world_to_object"))
     ws = orc.WideScene(tn.ctypes.data, tl.ctypes.data, w2o.ctypes.data, inst_gas.ctypes.data, C.cast(node_ptrs, C.c_void_p), C.cast(tri_ptrs, C.c_void_p),
                        len(export["instance_gas"]))
+    sizes = (len(tn), len(tl), len(handles), n_nodes.ctypes.data_as(C.c_void_p), n_tris.ctypes.data_as(C.c_void_p))
+    return ws, sizes, (inst_gas, keep_n, keep_t, node_ptrs, tri_ptrs, n_nodes, n_tris, tn, tl, w2o)
+
+
+def product_trace(export, rays, any_hit=False, skip=None, defs=()):
+    """Runs the host build of csrc/trace.cuh over an exported (or host-built) wide BVH: (hits, (nodes, tris, instances), stack
+    overflows).  skip: [n, 3] uint32 keys (t bits, instance, primitive) -> the closest candidate AFTER the key (SKIP variant)."""
+    import ctypes as C
+    L = product_trace_lib(defs)
+    ws, sizes, keep = _wide_scene(export)
     rays = np.ascontiguousarray(rays, dtype=orc.RAY_DTYPE)
     hits = np.zeros(len(rays), dtype=orc.HIT_DTYPE)
     counts = (C.c_uint64 * 3)()
@@ -209,8 +218,7 @@ def product_trace(export, rays, any_hit=False, skip=None, defs=()):
         skip_ptr = skip.ctypes.data_as(C.c_void_p)
     L.th_trace.argtypes = [C.POINTER(orc.WideScene), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int,
                            C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
-    rc = L.th_trace(C.byref(ws), len(tn), len(tl), len(handles), n_nodes.ctypes.data_as(C.c_void_p), n_tris.ctypes.data_as(C.c_void_p),
-                    rays.ctypes.data_as(C.c_void_p), len(rays), 1 if any_hit else 0, skip_ptr, hits.ctypes.data_as(C.c_void_p), counts, C.byref(overflows))
+    rc = L.th_trace(C.byref(ws), *sizes, rays.ctypes.data_as(C.c_void_p), len(rays), 1 if any_hit else 0, skip_ptr, hits.ctypes.data_as(C.c_void_p), counts, C.byref(overflows))
     assert rc == 0
     return hits, (int(counts[0]), int(counts[1]), int(counts[2])), int(overflows.value)
 
@@ -223,23 +231,11 @@ def product_simd_cost(export, rays, any_hit=False, fetch_threshold=12, defs=(), 
     th_simd_cost): dict of SIMD_COST_FIELDS.  A model of what a warp pays (the maximum over its lanes per iteration)."""
     import ctypes as C
     L = product_trace_lib(defs)
-    handles = sorted(export["gas"])
-    slot = {g: k for k, g in enumerate(handles)}
-    inst_gas = np.ascontiguousarray([slot[int(g)] for g in export["instance_gas"]], dtype=np.uint32)
-    keep_n = [np.ascontiguousarray(export["gas"][g][0]) for g in handles]
-    keep_t = [np.ascontiguousarray(export["gas"][g][1], dtype=np.float32) for g in handles]
-    node_ptrs = (C.c_void_p * max(len(handles), 1))(*[a.ctypes.data for a in keep_n])
-    tri_ptrs = (C.c_void_p * max(len(handles), 1))(*[a.ctypes.data for a in keep_t])
-    n_nodes = np.ascontiguousarray([len(a) for a in keep_n], dtype=np.uint32)
-    n_tris = np.ascontiguousarray([len(a) for a in keep_t], dtype=np.uint32)
-    tn, tl, w2o = (np.ascontiguousarray(export[k]) for k in ("tlas_nodes", "tlas_leaves", "world_to_object"))
-    ws = orc.WideScene(tn.ctypes.data, tl.ctypes.data, w2o.ctypes.data, inst_gas.ctypes.data, C.cast(node_ptrs, C.c_void_p), C.cast(tri_ptrs, C.c_void_p),
-                       len(export["instance_gas"]))
+    ws, sizes, keep = _wide_scene(export)
     rays = np.ascontiguousarray(rays, dtype=orc.RAY_DTYPE)
     out = (C.c_uint64 * 10)()
     L.th_simd_cost.argtypes = [C.POINTER(orc.WideScene), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int,
                                C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
-    rc = L.th_simd_cost(C.byref(ws), len(tn), len(tl), len(handles), n_nodes.ctypes.data_as(C.c_void_p), n_tris.ctypes.data_as(C.c_void_p),
-                        rays.ctypes.data_as(C.c_void_p), len(rays), 1 if any_hit else 0, fetch_threshold, leaf_threshold, out)
+    rc = L.th_simd_cost(C.byref(ws), *sizes, rays.ctypes.data_as(C.c_void_p), len(rays), 1 if any_hit else 0, fetch_threshold, leaf_threshold, out)
     assert rc == 0
     return {k: int(out[i]) for i, k in enumerate(SIMD_COST_FIELDS)}
