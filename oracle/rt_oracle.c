@@ -1561,4 +1561,79 @@ void orc_tonemap(const rt_TonemapperParams* p, const float* rgba, uint8_t* rgb, 
   }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * TEST HOOKS: function-level access to the BSDF and light restatements above.  tests/test_cpu_shade_source.py compares the
+ * PRODUCT's csrc/shade.cuh, compiled for the host, with them word for word.  prd = the 28 words of prd_t in declaration order
+ * (pos 0-2, distance 3, wo 4-6, wi 7-9, radiance 10-12, flags 13, f_over_pdf 14-16, pdf 17, sigma_t 18-20, ior 21-22,
+ * absorption_ior 23-26, seed 27); st = normalGeo, tangent, normal, albedo (12 floats); light out = direction, distance,
+ * emission, pdf (8 floats).
+ * ------------------------------------------------------------------------------------------ */
+static void prd_unpack(prd_t* p, const uint32_t w[28])
+{
+  float f[28]; memcpy(f, w, sizeof(f));
+  p->pos = (v3){ f[0], f[1], f[2] }; p->distance = f[3];
+  p->wo = (v3){ f[4], f[5], f[6] }; p->wi = (v3){ f[7], f[8], f[9] };
+  p->radiance = (v3){ f[10], f[11], f[12] }; p->flags = w[13];
+  p->f_over_pdf = (v3){ f[14], f[15], f[16] }; p->pdf = f[17];
+  p->sigma_t = (v3){ f[18], f[19], f[20] }; p->ior = (v2){ f[21], f[22] };
+  p->absorption_ior = (v4){ f[23], f[24], f[25], f[26] }; p->seed = w[27];
+}
+
+static void prd_pack(const prd_t* p, uint32_t w[28])
+{
+  const float f[28] = { p->pos.x, p->pos.y, p->pos.z, p->distance, p->wo.x, p->wo.y, p->wo.z, p->wi.x, p->wi.y, p->wi.z,
+                        p->radiance.x, p->radiance.y, p->radiance.z, 0.0f, p->f_over_pdf.x, p->f_over_pdf.y, p->f_over_pdf.z, p->pdf,
+                        p->sigma_t.x, p->sigma_t.y, p->sigma_t.z, p->ior.x, p->ior.y,
+                        p->absorption_ior.x, p->absorption_ior.y, p->absorption_ior.z, p->absorption_ior.w, 0.0f };
+  memcpy(w, f, sizeof(f));
+  w[13] = p->flags; w[27] = p->seed;
+}
+
+static state_t state_unpack(const float st[12])
+{
+  state_t s;
+  s.normalGeo = (v3){ st[0], st[1], st[2] }; s.tangent = (v3){ st[3], st[4], st[5] }; s.normal = (v3){ st[6], st[7], st[8] };
+  s.texcoord = (v3){ 0.0f, 0.0f, 0.0f }; s.albedo = (v3){ st[9], st[10], st[11] };
+  return s;
+}
+
+void orc_test_bsdf_sample(const rt_MaterialDefinition* m, const float st[12], uint32_t prd[28])
+{
+  const state_t s = state_unpack(st);
+  prd_t p; prd_unpack(&p, prd);
+  bsdf_sample(m, &s, &p);
+  prd_pack(&p, prd);
+}
+
+void orc_test_bsdf_eval(const rt_MaterialDefinition* m, const float st[12], const uint32_t prd[28], const float wiL[3], float out[4])
+{
+  const state_t s = state_unpack(st);
+  prd_t p; prd_unpack(&p, prd);
+  const v4 r = bsdf_eval(m, &s, &p, (v3){ wiL[0], wiL[1], wiL[2] });
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+static void light_pack(const light_sample_t* ls, float out[8])
+{
+  out[0] = ls->direction.x; out[1] = ls->direction.y; out[2] = ls->direction.z; out[3] = ls->distance;
+  out[4] = ls->emission.x; out[5] = ls->emission.y; out[6] = ls->emission.z; out[7] = ls->pdf;
+}
+
+void orc_test_light_constant(int numLights, const float sample[2], float out[8])
+{
+  light_sample_t ls; memset(&ls, 0, sizeof(ls));
+  light_env_constant(NULL, numLights, (v3){ 0.0f, 0.0f, 0.0f }, (v2){ sample[0], sample[1] }, &ls);
+  light_pack(&ls, out);
+}
+
+void orc_test_light_parallelogram(const rt_LightDefinition* light, int numLights, const float point[3], const float sample[2], float out[8])
+{
+  orc_scene tmp; memset(&tmp, 0, sizeof(tmp));
+  tmp.lights = (rt_LightDefinition*)light; tmp.numLightDefs = 1;
+  light_sample_t ls; memset(&ls, 0, sizeof(ls));
+  ls.index = 0;
+  light_parallelogram(&tmp, numLights, (v3){ point[0], point[1], point[2] }, (v2){ sample[0], sample[1] }, &ls);
+  light_pack(&ls, out);
+}
+
 #include "wide_bvh.inc"

@@ -9,8 +9,11 @@ flags of the device build of the shading translation unit: no FMA contraction, I
   * the texture fetch this repository defines (bilinear, wrap / wrap): equal to the oracle's, bit for bit, inside and far
     outside the unit square.
 
-This is the CPU twin of tests/test_gpu_trace_parity.py's primary-ray test; the BSDF, light and integrator code is only reachable
-through whole frames and stays a GPU test (tests/test_gpu_render_parity.py)."""
+  * the BSDF and light callables: the five sample callables, the eval callables, the constant-environment and parallelogram
+    lights equal the oracle's restatement word for word (function-level test hooks of the oracle, orc_test_*).
+
+This is the CPU twin of tests/test_gpu_trace_parity.py's primary-ray test and of what the frame tests prove about the callables;
+the closest-hit glue and the integrator are only reachable through whole frames and stay GPU tests (tests/test_gpu_render_parity.py)."""
 import ctypes as C
 import json
 import os
@@ -130,3 +133,105 @@ def test_texture_fetch_equals_the_oracle(built, shade):
         L.orc_tex2d(handle, float(u), float(v), C.byref(out))
         want[i] = out[:]
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def _bind_callables(shade):
+    L = orc.lib()
+    for lib, prefix in ((shade, "sh_"), (L, "orc_test_")):
+        getattr(lib, prefix + "bsdf_sample").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        getattr(lib, prefix + "bsdf_sample").restype = None
+        getattr(lib, prefix + "bsdf_eval").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        getattr(lib, prefix + "bsdf_eval").restype = None
+        getattr(lib, prefix + "light_constant").argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        getattr(lib, prefix + "light_constant").restype = None
+        getattr(lib, prefix + "light_parallelogram").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        getattr(lib, prefix + "light_parallelogram").restype = None
+    return L
+
+
+def _unit(rng, n):
+    v = rng.normal(size=(n, 3))
+    return (v / np.linalg.norm(v, axis=1, keepdims=True)).astype(np.float32)
+
+
+@pytest.mark.parametrize("bsdf", [0, 1, 2, 3, 4])
+def test_bsdf_callables_equal_the_oracle_word_for_word(built, shade, bsdf):
+    """The five BSDF sample callables and the two non-trivial eval callables of csrc/shade.cuh (diffuse, specular reflection,
+    specular transmission with nested-volume bookkeeping, GGX-Smith reflection and transmission) against the oracle's
+    restatement of bxdf_diffuse.cu / bxdf_specular.cu / bxdf_ggx_smith.cu: all 28 words of the per-ray data after the call,
+    random materials, frames, directions from both sides of the surface, flag combinations and seeds."""
+    L = _bind_callables(shade)
+    rng = np.random.default_rng(100 + bsdf)
+    n = 4000
+    normal, wo = _unit(rng, n), _unit(rng, n)
+    tangent = np.cross(normal, _unit(rng, n)).astype(np.float32)
+    tangent /= np.maximum(np.linalg.norm(tangent, axis=1, keepdims=True), 1e-6).astype(np.float32)
+    flip = rng.random(n) < 0.3                         # geometric normal on the other side for some
+    normal_geo = np.where(flip[:, None], -normal, normal).astype(np.float32)
+    mismatches = transmitted = terminated = sampled = 0
+    for i in range(n):
+        m = np.zeros(1, dtype=orc.MATERIAL_DTYPE)
+        m["indexBSDF"] = bsdf
+        m["roughness"] = rng.uniform(0.02, 0.9, 2).astype(np.float32) if rng.random() < 0.8 else np.float32([0.0, 0.0])
+        m["albedo"] = rng.uniform(0.05, 1.0, 3)
+        m["absorption"] = rng.uniform(0.0, 2.0, 3)
+        m["ior"] = rng.uniform(1.01, 2.4)
+        thin = rng.random() < 0.25
+        m["flags"] = 0x20 if thin else 0
+        st = np.concatenate([normal_geo[i], tangent[i], normal[i], rng.uniform(0.05, 1.0, 3)]).astype(np.float32)
+        prd = np.zeros(28, dtype=np.uint32)
+        f = prd.view(np.float32)
+        f[0:3] = rng.uniform(-2, 2, 3); f[3] = rng.uniform(0.1, 5.0)
+        f[4:7] = wo[i]
+        f[10:13] = rng.uniform(0, 1, 3)
+        prd[13] = (0x1 | (0x10 if rng.random() < 0.6 else 0) | (0x20 if thin else 0) | (0x1000 if rng.random() < 0.2 else 0))
+        f[14:17] = 1.0; f[17] = 1.0
+        f[18:21] = rng.uniform(0, 1, 3)
+        f[21:23] = [rng.uniform(1.0, 2.0), rng.uniform(1.0, 2.0)]
+        f[23:27] = rng.uniform(0.0, 2.0, 4)
+        prd[27] = rng.integers(0, 2 ** 32, dtype=np.uint64)
+        a, b = prd.copy(), prd.copy()
+        shade.sh_bsdf_sample(m.ctypes.data, st.ctypes.data, a.ctypes.data)
+        L.orc_test_bsdf_sample(m.ctypes.data, st.ctypes.data, b.ctypes.data)
+        if not np.array_equal(a, b):
+            mismatches += 1
+        transmitted += int(bool(a[13] & 0x100))
+        terminated += int(bool(a[13] & 0x80000000))
+        sampled += int(np.any(a[7:10] != 0))
+        wi_l = _unit(rng, 1)[0]
+        ea, eb = np.zeros(4, dtype=np.float32), np.zeros(4, dtype=np.float32)
+        shade.sh_bsdf_eval(m.ctypes.data, st.ctypes.data, a.ctypes.data, wi_l.ctypes.data, ea.ctypes.data)
+        L.orc_test_bsdf_eval(m.ctypes.data, st.ctypes.data, b.ctypes.data, wi_l.ctypes.data, eb.ctypes.data)
+        if not np.array_equal(ea.view(np.uint32), eb.view(np.uint32)):
+            mismatches += 1
+    assert mismatches == 0
+    # the cases are not degenerate: directions are sampled, transmissive lobes transmit, some samples end the path
+    assert sampled > 0.5 * n
+    assert (transmitted > 0.05 * n) == (bsdf in (2, 4))
+    if bsdf in (0, 3):
+        assert terminated > 0
+
+
+def test_light_callables_equal_the_oracle(built, shade):
+    L = _bind_callables(shade)
+    rng = np.random.default_rng(9)
+    for _ in range(3000):
+        sample = rng.random(2).astype(np.float32)
+        a, b = np.zeros(8, dtype=np.float32), np.zeros(8, dtype=np.float32)
+        num = int(rng.integers(1, 4))
+        shade.sh_light_constant(num, sample.ctypes.data, a.ctypes.data)
+        L.orc_test_light_constant(num, sample.ctypes.data, b.ctypes.data)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        light = np.zeros(1, dtype=orc.LIGHT_DTYPE)
+        light["type"] = 1
+        light["position"] = rng.uniform(-2, 2, 3)
+        u, v = rng.uniform(-2, 2, 3), rng.uniform(-2, 2, 3)
+        light["vecU"], light["vecV"] = u, v
+        nrm = np.cross(u, v)
+        light["area"] = np.linalg.norm(nrm)
+        light["normal"] = nrm / max(np.linalg.norm(nrm), 1e-6)
+        light["emission"] = rng.uniform(0, 20, 3)
+        point = rng.uniform(-3, 3, 3).astype(np.float32)
+        shade.sh_light_parallelogram(light.ctypes.data, num, point.ctypes.data, sample.ctypes.data, a.ctypes.data)
+        L.orc_test_light_parallelogram(light.ctypes.data, num, point.ctypes.data, sample.ctypes.data, b.ctypes.data)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
