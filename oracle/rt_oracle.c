@@ -1636,4 +1636,29 @@ void orc_test_light_parallelogram(const rt_LightDefinition* light, int numLights
   light_pack(&ls, out);
 }
 
+/* env: RGBA32F texels (w x h), the two CDF tables of the environment light, integral, rotation */
+static void env_scene(orc_scene* tmp, const float* texels, uint32_t w, uint32_t h, const float* cdfU, const float* cdfV, float integral)
+{
+  memset(tmp, 0, sizeof(*tmp));
+  tmp->envTexels = (float*)texels; tmp->envW = w; tmp->envH = h;
+  tmp->envCdfU = (float*)cdfU; tmp->envCdfV = (float*)cdfV; tmp->envIntegral = integral;
+}
+
+void orc_test_miss(const float* texels, uint32_t w, uint32_t h, float integral, float rotation, int miss, uint32_t prd[28])
+{
+  orc_scene tmp; env_scene(&tmp, texels, w, h, NULL, NULL, integral);
+  prd_t p; prd_unpack(&p, prd);
+  miss_program(&tmp, miss, rotation, &p);
+  prd_pack(&p, prd);
+}
+
+void orc_test_light_sphere(const float* texels, uint32_t w, uint32_t h, const float* cdfU, const float* cdfV, float integral, float rotation,
+                           int numLights, const float sample[2], float out[8])
+{
+  orc_scene tmp; env_scene(&tmp, texels, w, h, cdfU, cdfV, integral);
+  light_sample_t ls; memset(&ls, 0, sizeof(ls));
+  light_env_sphere(&tmp, numLights, rotation, (v3){ 0.0f, 0.0f, 0.0f }, (v2){ sample[0], sample[1] }, &ls);
+  light_pack(&ls, out);
+}
+
 #include "wide_bvh.inc"

@@ -2,8 +2,8 @@
 //
 // csrc/shade.cuh is included unchanged (its only CUDA intrinsic is __ldg) and compiled by g++ with the flags that mirror the
 // device build of the shading translation unit (no FMA contraction, IEEE division and square root): the TEA / LCG generators,
-// distribute(), start_path() with the three lens shaders, the software texture fetch, the five BSDF sample / eval callables and
-// the constant-environment and parallelogram light callables run here as they do in the kernels.  tests/test_cpu_shade_source.py holds them against the
+// distribute(), start_path() with the three lens shaders, the software texture fetch, the five BSDF sample / eval callables, the
+// three light callables and the three miss programs run here as they do in the kernels.  tests/test_cpu_shade_source.py holds them against the
 // oracle (which is pinned against the reference's own sources): primary rays bit for bit for every lens shader and every
 // device of a tiled multi-GPU launch, the generators against the reference's golden vectors, texture fetches bit for bit.
 #include <cmath>
@@ -123,6 +123,31 @@ void sh_light_parallelogram(const rt_LightDefinition* light, int numLights, cons
   LightSample ls; std::memset(&ls, 0, sizeof(ls));
   ls.index = 0;
   light_parallelogram(sys, f3(point[0], point[1], point[2]), make_float2(sample[0], sample[1]), ls);
+  light_pack(ls, out);
+}
+
+static rt_SystemData env_sys(const float* texels, uint32_t w, uint32_t h, const float* cdfU, const float* cdfV, float integral, float rotation, int numLights)
+{
+  rt_SystemData sys; std::memset(&sys, 0, sizeof(sys));
+  sys.envTexture = (uint64_t)(uintptr_t)texels; sys.envCDF_U = (uint64_t)(uintptr_t)cdfU; sys.envCDF_V = (uint64_t)(uintptr_t)cdfV;
+  sys.envWidth = w; sys.envHeight = h; sys.envIntegral = integral; sys.envRotation = rotation; sys.numLights = numLights;
+  return sys;
+}
+
+void sh_miss(const float* texels, uint32_t w, uint32_t h, float integral, float rotation, int miss, uint32_t prd[28])
+{
+  const rt_SystemData sys = env_sys(texels, w, h, nullptr, nullptr, integral, rotation, 1);
+  Prd p; prd_unpack(p, prd);
+  miss_program(sys, miss, p);
+  prd_pack(p, prd);
+}
+
+void sh_light_sphere(const float* texels, uint32_t w, uint32_t h, const float* cdfU, const float* cdfV, float integral, float rotation,
+                     int numLights, const float sample[2], float out[8])
+{
+  const rt_SystemData sys = env_sys(texels, w, h, cdfU, cdfV, integral, rotation, numLights);
+  LightSample ls; std::memset(&ls, 0, sizeof(ls));
+  light_env_sphere(sys, make_float2(sample[0], sample[1]), ls);
   light_pack(ls, out);
 }
 

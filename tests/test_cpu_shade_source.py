@@ -9,8 +9,9 @@ flags of the device build of the shading translation unit: no FMA contraction, I
   * the texture fetch this repository defines (bilinear, wrap / wrap): equal to the oracle's, bit for bit, inside and far
     outside the unit square.
 
-  * the BSDF and light callables: the five sample callables, the eval callables, the constant-environment and parallelogram
-    lights equal the oracle's restatement word for word (function-level test hooks of the oracle, orc_test_*).
+  * the BSDF, light and miss callables: the five sample callables, the eval callables, the constant / spherical environment and
+    parallelogram lights and the three miss programs equal the oracle's restatement word for word (function-level test hooks
+    of the oracle, orc_test_*).
 
 This is the CPU twin of tests/test_gpu_trace_parity.py's primary-ray test and of what the frame tests prove about the callables;
 the closest-hit glue and the integrator are only reachable through whole frames and stay GPU tests (tests/test_gpu_render_parity.py)."""
@@ -235,3 +236,42 @@ def test_light_callables_equal_the_oracle(built, shade):
         shade.sh_light_parallelogram(light.ctypes.data, num, point.ctypes.data, sample.ctypes.data, a.ctypes.data)
         L.orc_test_light_parallelogram(light.ctypes.data, num, point.ctypes.data, sample.ctypes.data, b.ctypes.data)
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_miss_programs_and_the_environment_light_equal_the_oracle(built, shade, tmp_path):
+    """__miss__env_null / _constant / _sphere and the importance-sampled spherical environment light (CDF search, bilinear
+    environment lookup with wrap in u and clamp in v, MIS weight) on the host's own environment map and CDF tables."""
+    L = orc.lib()
+    for lib, prefix in ((shade, "sh_"), (L, "orc_test_")):
+        getattr(lib, prefix + "miss").argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_int, C.c_void_p]
+        getattr(lib, prefix + "miss").restype = None
+        getattr(lib, prefix + "light_sphere").argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+        getattr(lib, prefix + "light_sphere").restype = None
+    app = host.App(H.write_system(tmp_path, "rtigo3_geometry", resolution="32 32", samplesSqrt=1, miss=2, envMap="procedural 64 32", envRotation=0.15),
+                   H.scene_path("rtigo3_geometry"), host_only=True)
+    texels, cdf_u, cdf_v, integral = app.environment()
+    app.close()
+    texels, cdf_u, cdf_v = (np.ascontiguousarray(a, dtype=np.float32) for a in (texels, cdf_u, cdf_v))
+    h, w = texels.shape[:2]
+    rng = np.random.default_rng(21)
+    for i in range(3000):
+        rotation = float(rng.random()) if i % 3 else 0.0
+        sample = rng.random(2).astype(np.float32)
+        a, b = np.zeros(8, dtype=np.float32), np.zeros(8, dtype=np.float32)
+        num = int(rng.integers(1, 4))
+        shade.sh_light_sphere(texels.ctypes.data, w, h, cdf_u.ctypes.data, cdf_v.ctypes.data, integral, rotation, num, sample.ctypes.data, a.ctypes.data)
+        L.orc_test_light_sphere(texels.ctypes.data, w, h, cdf_u.ctypes.data, cdf_v.ctypes.data, integral, rotation, num, sample.ctypes.data, b.ctypes.data)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        assert a[7] > 0.0 and abs(float(np.linalg.norm(a[:3])) - 1.0) < 1e-4
+        prd = np.zeros(28, dtype=np.uint32)
+        f = prd.view(np.float32)
+        f[7:10] = _unit(rng, 1)[0]
+        if i % 50 == 0:
+            f[7:10] = [0.0, 1.0 if i % 100 else -1.0, 0.0]          # the poles: clamp in v
+        prd[13] = 0x1 | (0x4 if rng.random() < 0.5 else 0)         # RT_FLAG_DIFFUSE selects the MIS weight
+        f[17] = rng.uniform(0.01, 3.0)
+        for miss in (0, 1, 2):
+            pa, pb = prd.copy(), prd.copy()
+            shade.sh_miss(texels.ctypes.data, w, h, integral, rotation, miss, pa.ctypes.data)
+            L.orc_test_miss(texels.ctypes.data, w, h, integral, rotation, miss, pb.ctypes.data)
+            assert np.array_equal(pa, pb) and (pa[13] & 0x80000000)
