@@ -18,6 +18,11 @@ if r.get("fractions"):
     out += ["fractions", {k: round(v, 3) for k, v in r["fractions"].items()}, "bound", r.get("bound")]
 if "extend_mrays_per_s" in r:
     out += ["extend", round(r["extend_mrays_per_s"]), "connect", round(r["connect"]["mrays_per_s"]), {k: round(v, 3) for k, v in r["kernel_share_of_step"].items()}]
+if "trace_schedule" in d:
+    t = d["trace_schedule"]
+    out += ["schedule", t.get("schedule")]
+    if t.get("measured"):
+        out += ["group/one/two ms", [round(min(t["group_ms"]), 2), round(t["one_tri_ms"], 2), round(t["two_tri_ms"], 2)]]
 if "clocks" in d:
     out += ["clocks", d["clocks"].get("sm_mhz"), d["clocks"].get("reasons")]
 print(*out)
